@@ -1,0 +1,234 @@
+"""Seeded synthetic inputs for the five BASELINE.json configs.
+
+Every generator returns a `PairBatch`: CSR-packed int8 code arrays (A0 C1 G2 T3 N4, as ssw_cpp.cpp:8-21 /
+pyssw.py:86-98 translate them) plus per-pair maskLen and the scoring that the reference callers use
+(ssw_cpp.cpp:23-48 builds +match/-mismatch with N = -mismatch; pyssw.py:61-79 builds N = 0).
+Reads are sampled from their target window with substitutions / insertions / deletions in equal parts.
+Generation is numpy-only and vectorised, so the 1 M-pair config builds in seconds.
+"""
+from dataclasses import dataclass, field
+import numpy as np
+
+
+def dna_matrix(match=4, mismatch=6, n_zero=False):
+    """5x5 matrix as ssw_cpp.cpp:23-48 (N row/col = -mismatch) or pyssw.py:61-79 (N row/col = 0)."""
+    m = np.full((5, 5), -mismatch, dtype=np.int8)
+    for i in range(4):
+        m[i, i] = match
+    if n_zero:
+        m[4, :] = 0
+        m[:, 4] = 0
+    return m.reshape(-1)
+
+
+@dataclass
+class PairBatch:
+    reads: np.ndarray       # int8 codes, concatenated
+    read_off: np.ndarray    # int64, n+1
+    refs: np.ndarray        # int8 codes, concatenated
+    ref_off: np.ndarray     # int64, n+1
+    masklen: np.ndarray     # int32, n
+    mat: np.ndarray = field(default_factory=dna_matrix)
+    n: int = 5
+    gapO: int = 8
+    gapE: int = 2
+    flag: int = 0
+    filters: int = 0
+    filterd: int = 32767
+    score_size: int = 2
+    name: str = ""
+
+    @property
+    def npairs(self):
+        return len(self.read_off) - 1
+
+    @property
+    def read_len(self):
+        return np.diff(self.read_off)
+
+    @property
+    def ref_len(self):
+        return np.diff(self.ref_off)
+
+    @property
+    def cells(self):
+        """forward-matrix cells, the GCUPS numerator."""
+        return int((self.read_len.astype(np.int64) * self.ref_len.astype(np.int64)).sum())
+
+    def subset(self, idx):
+        idx = np.asarray(idx, dtype=np.int64)
+        rl, fl = self.read_len[idx], self.ref_len[idx]
+        ro = np.zeros(len(idx) + 1, dtype=np.int64); np.cumsum(rl, out=ro[1:])
+        fo = np.zeros(len(idx) + 1, dtype=np.int64); np.cumsum(fl, out=fo[1:])
+        reads = np.empty(ro[-1], dtype=np.int8); refs = np.empty(fo[-1], dtype=np.int8)
+        for k, i in enumerate(idx):
+            reads[ro[k]:ro[k + 1]] = self.reads[self.read_off[i]:self.read_off[i + 1]]
+            refs[fo[k]:fo[k + 1]] = self.refs[self.ref_off[i]:self.ref_off[i + 1]]
+        return PairBatch(reads, ro, refs, fo, self.masklen[idx].copy(), self.mat, self.n, self.gapO, self.gapE, self.flag,
+                         self.filters, self.filterd, self.score_size, self.name + f"[subset {len(idx)}]")
+
+    def shard(self, rank, world):
+        """Contiguous shard of a length-sorted batch dealt round-robin: pair i goes to rank i % world."""
+        if world == 1:
+            return self
+        return self.subset(np.arange(rank, self.npairs, world))
+
+
+def _mutated_reads(rng, targets, tlen, rlen, offset, err):
+    """targets: [n, tlen] int8; returns list-free CSR reads of per-pair length rlen[i], sampled from targets[i, offset[i]:]
+    with error rate err split 1/3 substitution, 1/3 insertion, 1/3 deletion."""
+    n = targets.shape[0]
+    lmax = int(rlen.max())
+    u = rng.random((n, lmax), dtype=np.float32)
+    is_sub = u < err / 3
+    is_ins = (u >= err / 3) & (u < 2 * err / 3)
+    is_del = (u >= 2 * err / 3) & (u < err)
+    step = np.ones((n, lmax), dtype=np.int32)
+    step[is_ins] = 0
+    step[is_del] = 2
+    src = offset[:, None].astype(np.int64) + np.cumsum(step, axis=1) - step + (is_del.astype(np.int64))
+    np.clip(src, 0, tlen - 1, out=src)
+    base = np.take_along_axis(targets, src, axis=1)
+    rnd = rng.integers(0, 4, size=(n, lmax), dtype=np.int8)
+    base = np.where(is_ins, rnd, base)
+    base = np.where(is_sub, (base + 1 + (rnd % 3)) % 4, base).astype(np.int8)
+    keep = np.arange(lmax)[None, :] < rlen[:, None]
+    reads = base[keep]
+    off = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(rlen, out=off[1:])
+    return reads, off
+
+
+def make_pairs(npairs, read_len, ref_len, err=0.02, seed=1, flag=0, mask="half", name="", chunk=65536, n_frac=0.0, **kw):
+    """Generic generator.  read_len: int or (lo, hi) inclusive uniform; ref_len: int, or float multiple of the read length."""
+    rng = np.random.default_rng(seed)
+    reads_l, refs_l, rlens, flens = [], [], [], []
+    for c0 in range(0, npairs, chunk):
+        n = min(chunk, npairs - c0)
+        rl = (np.full(n, read_len, dtype=np.int64) if np.isscalar(read_len)
+              else rng.integers(read_len[0], read_len[1] + 1, size=n, dtype=np.int64))
+        if isinstance(ref_len, float):
+            fl = np.maximum((rl * ref_len).astype(np.int64), rl + 8)
+        else:
+            fl = np.full(n, ref_len, dtype=np.int64)
+        tmax = int(fl.max())
+        targets = rng.integers(0, 4, size=(n, tmax), dtype=np.int8)
+        if n_frac > 0:
+            targets[rng.random((n, tmax)) < n_frac] = 4
+        slack = np.maximum(fl - rl - (rl * err).astype(np.int64) - 4, 0)
+        offset = (rng.random(n) * (slack + 1)).astype(np.int64)
+        r, ro = _mutated_reads(rng, targets, tmax, rl, offset, err)
+        keep = np.arange(tmax)[None, :] < fl[:, None]
+        refs_l.append(targets[keep]); reads_l.append(r); rlens.append(rl); flens.append(fl)
+    rl = np.concatenate(rlens); fl = np.concatenate(flens)
+    ro = np.zeros(npairs + 1, dtype=np.int64); np.cumsum(rl, out=ro[1:])
+    fo = np.zeros(npairs + 1, dtype=np.int64); np.cumsum(fl, out=fo[1:])
+    if mask == "half":
+        ml = np.maximum(rl // 2, 15).astype(np.int32)
+    elif mask == "qlen":
+        ml = rl.astype(np.int32)
+    else:
+        ml = np.full(npairs, int(mask), dtype=np.int32)
+    return PairBatch(np.concatenate(reads_l), ro, np.concatenate(refs_l), fo, ml, flag=flag, name=name, **kw)
+
+
+def config1(npairs=10_000, seed=11):
+    """BASELINE configs[0]: score + end positions only, 250 bp reads vs 500 bp targets, flag 0, maskLen 125."""
+    return make_pairs(npairs, 250, 500, err=0.02, seed=seed, flag=0, mask=125, name="config1: 250bp x 500bp flag0")
+
+
+def config2(npairs=1_000_000, seed=12):
+    """BASELINE configs[1]: full ssw_align with traceback + CIGAR, reads U{150..300} vs 1 kb haplotypes, flag 1, maskLen readLen/2."""
+    return make_pairs(npairs, (150, 300), 1000, err=0.02, seed=seed, flag=1, mask="half", name="config2: 150-300bp x 1kb flag1 (CIGAR)")
+
+
+def config4(npairs=1024, seed=14, match=4, mismatch=6, flag=0):
+    """BASELINE configs[3]: ONT-scale, 10 kb reads at 8 % error vs 12 kb windows (scores land on the 32767 clamp with match=4)."""
+    b = make_pairs(npairs, 10_000, 12_000, err=0.08, seed=seed, flag=flag, mask="half", name=f"config4: 10kb x 12kb flag{flag}", chunk=64)
+    b.mat = dna_matrix(match, mismatch)
+    return b
+
+
+def config5(npairs=10_000_000, seed=15, lo=100, hi=20_000, flag=0):
+    """BASELINE configs[4]: mixed lengths, read length log-uniform on [lo, hi], target = 1.2 x read, 5 % errors.
+    (The distribution is not fixed by BASELINE.json; log-uniform is this repo's stated choice)
+    Built bin by bin so the padded generator never allocates npairs x hi."""
+    rng = np.random.default_rng(seed)
+    rl = np.exp(rng.uniform(np.log(lo), np.log(hi), size=npairs)).astype(np.int64)
+    rl.sort()
+    parts = []
+    edges = np.unique(np.concatenate([[0], np.searchsorted(rl, np.geomspace(lo, hi, 40)[1:-1]), [npairs]]))
+    for a, b in zip(edges[:-1], edges[1:]):
+        if b <= a:
+            continue
+        parts.append((rl[a:b], seed * 1000 + int(a)))
+    reads_l, refs_l, rls, fls = [], [], [], []
+    for lens, s in parts:
+        sub = make_pairs(len(lens), (int(lens.min()), int(lens.max())), 1.2, err=0.05, seed=s, flag=flag,
+                         chunk=max(1, min(65536, 200_000_000 // int(lens.max() * 1.3))))
+        reads_l.append(sub.reads); refs_l.append(sub.refs); rls.append(sub.read_len); fls.append(sub.ref_len)
+    rl2 = np.concatenate(rls); fl2 = np.concatenate(fls)
+    ro = np.zeros(len(rl2) + 1, dtype=np.int64); np.cumsum(rl2, out=ro[1:])
+    fo = np.zeros(len(fl2) + 1, dtype=np.int64); np.cumsum(fl2, out=fo[1:])
+    ml = np.maximum(rl2 // 2, 15).astype(np.int32)
+    return PairBatch(np.concatenate(reads_l), ro, np.concatenate(refs_l), fo, ml, flag=flag, name=f"config5: mixed {lo}bp-{hi}bp x{len(rl2)}")
+
+
+def fuzz_pairs(npairs, seed, max_read=700, max_ref=500, alphabet=4, flag=1, random_matrix=True, with_n=True):
+    """The adversarial distribution of SURVEY.md section 8c: random 5x5 matrices, gapE 1..3, gapO > gapE, low-complexity
+    alphabets (ties), reads derived from the target with jumps / random blocks / substitutions, occasional N, lengths from 1,
+    random maskLen >= 15.  One scoring per batch (the batched ABI takes one matrix per batch)."""
+    rng = np.random.default_rng(seed)
+    if random_matrix:
+        match = int(rng.integers(1, 6)); mism = int(rng.integers(1, 7))
+        mat = np.full((5, 5), -mism, dtype=np.int8)
+        for i in range(4):
+            mat[i, i] = match
+        if rng.random() < 0.5:
+            mat[4, :] = 0; mat[:, 4] = 0
+        elif rng.random() < 0.5:
+            x = -int(rng.integers(0, 4)); mat[4, :] = x; mat[:, 4] = x
+        if rng.random() < 0.3:     # fully random symmetric-free matrix, still with a positive diagonal
+            mat = rng.integers(-6, 3, size=(5, 5)).astype(np.int8)
+            for i in range(4):
+                mat[i, i] = int(rng.integers(1, 6))
+        gapE = int(rng.integers(1, 4)); gapO = gapE + int(rng.integers(1, 9))
+    else:
+        mat = dna_matrix().reshape(5, 5); gapO, gapE = 8, 2
+    reads_l, refs_l, rl, fl = [], [], [], []
+    for _ in range(npairs):
+        flen = int(rng.integers(1, max_ref + 1)) if rng.random() < 0.9 else int(rng.integers(1, 20))
+        ref = rng.integers(0, alphabet, size=flen, dtype=np.int8)
+        if rng.random() < 0.15:
+            rlen = int(rng.integers(1, 17))
+        else:
+            rlen = int(rng.integers(1, max_read + 1))
+        out = []
+        pos = int(rng.integers(0, flen))
+        while len(out) < rlen:
+            u = rng.random()
+            if u < 0.03:
+                pos += int(rng.integers(-30, 31))
+            elif u < 0.06:
+                out.extend(rng.integers(0, alphabet, size=int(rng.integers(1, 21))).tolist())
+                continue
+            pos = min(max(pos, 0), flen - 1)
+            b = int(ref[pos])
+            if rng.random() < 0.06:
+                b = int(rng.integers(0, alphabet))
+            if with_n and rng.random() < 0.004:
+                b = 4
+            out.append(b)
+            pos += 1
+            if pos >= flen:
+                pos = int(rng.integers(0, flen))
+        read = np.array(out[:rlen], dtype=np.int8)
+        if with_n and rng.random() < 0.1 and flen > 3:
+            ref = ref.copy(); ref[rng.integers(0, flen, size=2)] = 4
+        reads_l.append(read); refs_l.append(ref); rl.append(rlen); fl.append(flen)
+    rl = np.array(rl, dtype=np.int64); fl = np.array(fl, dtype=np.int64)
+    ro = np.zeros(npairs + 1, dtype=np.int64); np.cumsum(rl, out=ro[1:])
+    fo = np.zeros(npairs + 1, dtype=np.int64); np.cumsum(fl, out=fo[1:])
+    ml = np.maximum(15, rng.integers(15, 40, size=npairs) if rng.random() < 0.3 else (rl // 2 + rng.integers(0, 6, size=npairs))).astype(np.int32)
+    return PairBatch(np.concatenate(reads_l), ro, np.concatenate(refs_l), fo, ml, mat=mat.reshape(-1).astype(np.int8), gapO=gapO, gapE=gapE,
+                     flag=flag, name=f"fuzz seed {seed}")

@@ -1,0 +1,94 @@
+"""ctypes access to the parity checkers.  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this module.
+It never touches the GPU and nothing in megapath-nano_b200/ imports it.
+
+  ref_lib()      the UNMODIFIED reference ssw.c compiled into oracle/_ref/libssw_ref.so (oracle/Makefile)
+  port           the scalar restatement oracle/ssw_oracle.c (liboracle.so)
+  run_batch(...) one pair per call, `threads` POSIX threads (oracle/batch_driver.c), returns (results[n,8], cigars, seconds)
+"""
+import ctypes as ct
+import os
+import subprocess
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+_ORACLE_SO = os.path.join(HERE, "liboracle.so")
+_REF_SO = os.path.join(HERE, "_ref", "libssw_ref.so")
+_REALIGNER_REF = os.path.join(HERE, "_ref", "realigner_ref")
+
+FIELDS = ("score1", "score2", "ref_begin1", "ref_end1", "read_begin1", "read_end1", "ref_end2", "cigarLen")
+
+
+def build(force=False):
+    """Compile liboracle.so and, if /root/reference is present, oracle/_ref (outputs stay under oracle/)."""
+    need = force or not os.path.exists(_ORACLE_SO) or (
+        os.path.getmtime(_ORACLE_SO) < max(os.path.getmtime(os.path.join(HERE, f)) for f in ("ssw_oracle.c", "batch_driver.c")))
+    have_ref_src = os.path.exists("/root/reference/bin/realignment/realign/ssw.c")
+    if need:
+        subprocess.run(["make", "-C", HERE, os.path.join(HERE, "liboracle.so")], check=True, capture_output=True)
+    if have_ref_src and (force or not os.path.exists(_REF_SO) or not os.path.exists(_REALIGNER_REF)):
+        subprocess.run(["make", "-C", HERE, "ref"], check=True, capture_output=True)
+
+
+_port = None
+_ref = None
+
+
+def port_lib():
+    global _port
+    if _port is None:
+        build()
+        _port = ct.CDLL(_ORACLE_SO)
+        _port.oracle_run_batch.restype = ct.c_double
+        _port.oracle_run_batch_port.restype = ct.c_double
+    return _port
+
+
+def have_ref():
+    return os.path.exists(_REF_SO)
+
+
+def ref_lib():
+    global _ref
+    if _ref is None:
+        build()
+        _ref = ct.CDLL(_REF_SO)
+    return _ref
+
+
+def ref_path():
+    return _REF_SO
+
+
+def realigner_ref_path():
+    return _REALIGNER_REF
+
+
+def _p(a, t):
+    return a.ctypes.data_as(ct.POINTER(t))
+
+
+def run_batch(reads, read_off, refs, ref_off, masklen, mat, n, gapO=8, gapE=2, flag=1, filters=0, filterd=32767, score_size=2,
+              threads=1, impl="ref", cigar_cap=64, lib=None):
+    """impl: 'ref' (compiled reference ssw.c), 'port' (scalar restatement), or 'lib' with lib=<CDLL exporting the ssw.h ABI>."""
+    reads = np.ascontiguousarray(reads, dtype=np.int8)
+    refs = np.ascontiguousarray(refs, dtype=np.int8)
+    read_off = np.ascontiguousarray(read_off, dtype=np.int64)
+    ref_off = np.ascontiguousarray(ref_off, dtype=np.int64)
+    masklen = np.ascontiguousarray(masklen, dtype=np.int32)
+    mat = np.ascontiguousarray(mat, dtype=np.int8)
+    npairs = len(read_off) - 1
+    out = np.zeros((npairs, 8), dtype=np.int32)
+    cig = np.zeros((npairs, cigar_cap), dtype=np.uint32)
+    P = port_lib()
+    common = (_p(reads, ct.c_int8), _p(read_off, ct.c_int64), _p(refs, ct.c_int8), _p(ref_off, ct.c_int64), _p(masklen, ct.c_int32),
+              _p(mat, ct.c_int8), ct.c_int32(n), ct.c_int32(gapO), ct.c_int32(gapE), ct.c_int32(flag), ct.c_int32(filters), ct.c_int32(filterd),
+              ct.c_int32(score_size), ct.c_int64(npairs), ct.c_int32(threads), _p(out, ct.c_int32), _p(cig, ct.c_uint32), ct.c_int32(cigar_cap))
+    if impl == "port":
+        secs = P.oracle_run_batch_port(*common)
+    else:
+        L = ref_lib() if impl == "ref" else lib
+        fns = [ct.cast(getattr(L, nm), ct.c_void_p) for nm in ("ssw_init", "ssw_align", "init_destroy", "align_destroy")]
+        secs = P.oracle_run_batch(*fns, *common)
+    return out, cig, secs
