@@ -1,0 +1,91 @@
+/*
+ * mpn_ssw_batch.h -- batched submit/collect C ABI of the B200 Smith-Waterman engine.
+ *
+ * This is the new entry point the reference does not have: where MegaPath-Nano calls
+ *     ssw_init -> ssw_align -> align_destroy -> init_destroy            (ssw.h:77-130)
+ * once per (read, target) pair -- pyssw.py:137-147 for the ONT path, ssw_cpp.cpp:326-359 called from
+ * realigner.cpp:338,368 for the Illumina path -- a caller hands over many pairs at once and gets back one record per
+ * pair with exactly the fields of s_align (ssw.h:47-57) plus the CIGAR words in one arena.
+ * The legacy per-pair ABI in include/ssw.h is implemented on top of this one (batch of one).
+ *
+ * Plain C types only.  Sequences are int8 codes in [0, n) exactly as ssw_align takes them (ssw.h:87-89); all pairs of
+ * a batch share one scoring (mat, n, gapO, gapE), one score_size and one (flag, filters, filterd) triple; maskLen is
+ * per pair.  Results are bit-identical to ssw.c for gapO > gapE (every reference caller uses 8/2).
+ *
+ * Errors: functions return 0 on success, a negative MPN_E_* otherwise; CUDA failures abort() with a message on stderr
+ * (the reference's callers never check for NULL, SURVEY.md section 8b, so failing loudly is the only safe behaviour).
+ * There is no CPU fallback.
+ */
+#ifndef MPN_SSW_BATCH_H
+#define MPN_SSW_BATCH_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mpn_engine mpn_engine;
+typedef struct mpn_batch mpn_batch;
+
+/* scoring + reporting options of one batch: the arguments of ssw_init (ssw.h:77) and ssw_align (ssw.h:117-125) */
+typedef struct {
+    const int8_t* mat;      /* n*n substitution matrix, row = target code, column = read code (ssw.c:108,191) */
+    int32_t n;
+    int32_t gapO, gapE;     /* absolute values, 0..255 (uint8_t in ssw_align) */
+    int32_t score_size;     /* 0: 8-bit only, 1: 16-bit only, 2: 8-bit with 16-bit re-run (ssw.h:64-66) */
+    int32_t flag;           /* ssw_align flag byte */
+    int32_t filters;        /* uint16_t score filter */
+    int32_t filterd;        /* distance filter */
+} mpn_params;
+
+/* one record per pair: the scalar fields of s_align (ssw.h:47-57); the CIGAR is cigar[cigar_off .. cigar_off+cigar_len) */
+typedef struct {
+    uint16_t score1;
+    uint16_t score2;
+    int32_t ref_begin1;
+    int32_t ref_end1;
+    int32_t read_begin1;
+    int32_t read_end1;
+    int32_t ref_end2;
+    int32_t cigar_len;
+    int32_t status;         /* 0 ok; MPN_ST_NULL: ssw_align would have returned NULL for this pair */
+    int64_t cigar_off;
+} mpn_result;
+
+enum { MPN_ST_OK = 0, MPN_ST_NULL = 1 };
+enum { MPN_E_ARG = -1, MPN_E_NOGPU = -2, MPN_E_CIGAR_SPACE = -3, MPN_E_UNSUPPORTED = -4 };
+
+/* engine = one CUDA device + one stream + reusable device/pinned buffers.  device < 0: current device. */
+mpn_engine* mpn_engine_create(int device);
+void mpn_engine_destroy(mpn_engine* e);
+/* run on a caller-owned cudaStream_t (e.g. PyTorch's current stream) instead of the engine's own; 0 restores the own stream */
+int mpn_engine_set_stream(mpn_engine* e, void* cuda_stream);
+/* counters since creation: kernel launches, pairs, forward cells, pairs re-run in the 32-bit kernel */
+int mpn_engine_stats(const mpn_engine* e, int64_t* launches, int64_t* pairs, int64_t* cells, int64_t* wide_pairs);
+
+/*
+ * One call, host buffers in, host records out (the call a user makes; copies are inside):
+ *   reads/refs     concatenated int8 codes; read i = reads[read_off[i] .. read_off[i+1]), same for refs (npairs+1 offsets)
+ *   masklen        per pair (ssw.h:103-110)
+ *   out            npairs records
+ *   cigar, cigar_cap   caller's CIGAR arena in uint32 words; returns MPN_E_CIGAR_SPACE if too small
+ *                      (npairs * 2 * max read length is always enough)
+ */
+int mpn_align_batch(mpn_engine* e, const mpn_params* p, const int8_t* reads, const int64_t* read_off, const int8_t* refs,
+                    const int64_t* ref_off, const int32_t* masklen, int64_t npairs, mpn_result* out, uint32_t* cigar, int64_t cigar_cap);
+
+/*
+ * The same work split into phases, so that inputs can stay resident in HBM across repeated runs:
+ *   upload : host -> device copies + scheduling (length binning, task lists)
+ *   run    : enqueue every kernel of the batch on the engine's stream (no host synchronisation)
+ *   fetch  : device -> host copies of the records + CIGAR arena, synchronises
+ */
+mpn_batch* mpn_batch_upload(mpn_engine* e, const mpn_params* p, const int8_t* reads, const int64_t* read_off, const int8_t* refs,
+                            const int64_t* ref_off, const int32_t* masklen, int64_t npairs);
+int mpn_batch_run(mpn_batch* b);
+int mpn_batch_fetch(mpn_batch* b, mpn_result* out, uint32_t* cigar, int64_t cigar_cap);
+void mpn_batch_free(mpn_batch* b);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

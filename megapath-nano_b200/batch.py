@@ -1,0 +1,139 @@
+"""ctypes binding of the batched C ABI (include/mpn_ssw_batch.h).  Host-side plumbing only: every DP cell is computed by
+the CUDA kernels in csrc/; if libmpn_ssw.so is missing or no GPU is present this module raises -- there is no CPU path."""
+import ctypes as ct
+import os
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libmpn_ssw.so")
+
+FIELDS = ("score1", "score2", "ref_begin1", "ref_end1", "read_begin1", "read_end1", "ref_end2", "cigarLen")
+
+
+class MpnParams(ct.Structure):
+    _fields_ = [("mat", ct.POINTER(ct.c_int8)), ("n", ct.c_int32), ("gapO", ct.c_int32), ("gapE", ct.c_int32), ("score_size", ct.c_int32),
+                ("flag", ct.c_int32), ("filters", ct.c_int32), ("filterd", ct.c_int32)]
+
+
+RESULT_DTYPE = np.dtype([("score1", np.uint16), ("score2", np.uint16), ("ref_begin1", np.int32), ("ref_end1", np.int32),
+                         ("read_begin1", np.int32), ("read_end1", np.int32), ("ref_end2", np.int32), ("cigar_len", np.int32),
+                         ("status", np.int32), ("cigar_off", np.int64)], align=True)
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is not built (run `python -c 'import __graft_entry__ as g; g.build()'`); there is no CPU fallback")
+        L = ct.CDLL(LIB_PATH)
+        L.mpn_engine_create.restype = ct.c_void_p
+        L.mpn_engine_create.argtypes = [ct.c_int]
+        L.mpn_engine_destroy.argtypes = [ct.c_void_p]
+        L.mpn_engine_set_stream.argtypes = [ct.c_void_p, ct.c_void_p]
+        L.mpn_engine_stats.argtypes = [ct.c_void_p] + [ct.POINTER(ct.c_int64)] * 4
+        L.mpn_batch_upload.restype = ct.c_void_p
+        L.mpn_batch_upload.argtypes = [ct.c_void_p, ct.POINTER(MpnParams), ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_int64]
+        L.mpn_batch_run.argtypes = [ct.c_void_p]
+        L.mpn_batch_fetch.argtypes = [ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_int64]
+        L.mpn_batch_free.argtypes = [ct.c_void_p]
+        L.mpn_align_batch.argtypes = [ct.c_void_p, ct.POINTER(MpnParams), ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_int64,
+                                      ct.c_void_p, ct.c_void_p, ct.c_int64]
+        assert ct.sizeof(MpnParams) == 40 and RESULT_DTYPE.itemsize == 40, (ct.sizeof(MpnParams), RESULT_DTYPE.itemsize)
+        _lib = L
+    return _lib
+
+
+def _ptr(a):
+    """address of a numpy array or a torch tensor (pinned host memory)"""
+    if hasattr(a, "data_ptr"):
+        return ct.c_void_p(a.data_ptr())
+    return ct.c_void_p(a.ctypes.data)
+
+
+class Engine:
+    """One GPU, one stream.  `align(batch)` is the call a user makes: host buffers in, host records out."""
+
+    def __init__(self, device=-1):
+        self.L = lib()
+        self.h = self.L.mpn_engine_create(device)
+        if not self.h:
+            raise RuntimeError("mpn_engine_create failed: no CUDA device (this engine has no CPU fallback)")
+
+    def close(self):
+        if self.h:
+            self.L.mpn_engine_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream_ptr):
+        self.L.mpn_engine_set_stream(self.h, ct.c_void_p(cuda_stream_ptr))
+
+    def stats(self):
+        v = [ct.c_int64(0) for _ in range(4)]
+        self.L.mpn_engine_stats(self.h, *[ct.byref(x) for x in v])
+        return dict(launches=v[0].value, pairs=v[1].value, cells=v[2].value, wide_pairs=v[3].value)
+
+    def _params(self, b, keep):
+        mat = np.ascontiguousarray(b.mat, dtype=np.int8)
+        keep.append(mat)
+        return MpnParams(mat.ctypes.data_as(ct.POINTER(ct.c_int8)), int(b.n), int(b.gapO), int(b.gapE), int(b.score_size), int(b.flag),
+                         int(b.filters), int(b.filterd))
+
+    def upload(self, b):
+        keep = []
+        p = self._params(b, keep)
+        h = self.L.mpn_batch_upload(self.h, ct.byref(p), _ptr(b.reads), _ptr(b.read_off), _ptr(b.refs), _ptr(b.ref_off), _ptr(b.masklen), int(b.npairs))
+        if not h:
+            raise RuntimeError("mpn_batch_upload failed (bad arguments)")
+        return h
+
+    def run(self, h):
+        rc = self.L.mpn_batch_run(h)
+        if rc:
+            raise RuntimeError(f"mpn_batch_run -> {rc}")
+
+    def fetch(self, h, npairs, cigar_cap, out=None, cig=None):
+        out = np.zeros(npairs, dtype=RESULT_DTYPE) if out is None else out
+        cig = np.zeros(max(cigar_cap, 1), dtype=np.uint32) if cig is None else cig
+        rc = self.L.mpn_batch_fetch(h, _ptr(out), _ptr(cig), int(cigar_cap))
+        if rc:
+            raise RuntimeError(f"mpn_batch_fetch -> {rc}")
+        return out, cig
+
+    def free(self, h):
+        self.L.mpn_batch_free(h)
+
+    def align(self, b, cigar_cap=None, out=None, cig=None):
+        """b: anything with the PairBatch fields (workloads.PairBatch).  Returns (records[npairs] of RESULT_DTYPE, cigar arena)."""
+        if cigar_cap is None:
+            cigar_cap = int(b.npairs) * 24 + int(len(b.reads)) // 4 + 4096
+        h = self.upload(b)
+        try:
+            self.run(h)
+            return self.fetch(h, int(b.npairs), cigar_cap, out, cig)
+        finally:
+            self.free(h)
+
+
+def as_table(rec, cig, cigar_cap=64):
+    """records -> (int32 [n, 8] in oracle.FIELDS order with cigarLen = -1 for NULL results, uint32 [n, cigar_cap] cigar words)"""
+    n = len(rec)
+    t = np.zeros((n, 8), dtype=np.int32)
+    for k, f in enumerate(("score1", "score2", "ref_begin1", "ref_end1", "read_begin1", "read_end1", "ref_end2", "cigar_len")):
+        t[:, k] = rec[f]
+    null = rec["status"] != 0
+    t[null] = 0
+    t[null, 7] = -1
+    c = np.zeros((n, cigar_cap), dtype=np.uint32)
+    lens = np.minimum(np.where(null, 0, rec["cigar_len"]), cigar_cap)
+    for i in np.nonzero(lens > 0)[0]:
+        o = int(rec["cigar_off"][i])
+        c[i, :lens[i]] = cig[o:o + lens[i]]
+    return t, c

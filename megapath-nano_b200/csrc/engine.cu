@@ -1,0 +1,410 @@
+// Host side of the batched Smith-Waterman engine: length-binned scheduler, device memory, kernel launches and the
+// C ABI of include/mpn_ssw_batch.h.  No CPU alignment code lives here: every DP cell is computed by the kernels in
+// sw_strip16.cuh / sw_wide32.cuh / sw_finish.cuh / sw_trace.cuh, and a missing or failing GPU aborts loudly.
+#include "../../include/mpn_ssw_batch.h"
+#include "sw_common.cuh"
+#include "sw_strip16.cuh"
+#include "sw_wide32.cuh"
+#include "sw_finish.cuh"
+#include "sw_trace.cuh"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+using namespace mpn;
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { \
+    fprintf(stderr, "[mpn_ssw] CUDA error %s (%s) at %s:%d -- no CPU fallback, aborting\n", cudaGetErrorName(e_), cudaGetErrorString(e_), __FILE__, __LINE__); \
+    abort(); } } while (0)
+
+namespace {
+
+struct DevBuf {
+    void* p = nullptr; size_t cap = 0;
+    void reserve(size_t bytes) {
+        if (bytes <= cap) return;
+        if (p) CK(cudaFree(p));
+        size_t want = bytes + bytes / 8 + 256;
+        CK(cudaMalloc(&p, want));
+        cap = want;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+typedef void (*StripFn)(const SwTask*, int, int*, const int8_t*, const Score16, uint32_t*, SwEnds*);
+struct StripCfg { int G, KR, cap; StripFn fn; size_t smem; int blocks_per_sm; };
+
+#define STRIP(KR, G) { G, KR, 2 * G * KR, sw_strip16_kernel<KR, G>, strip16_smem_bytes<KR>(), 0 }
+StripCfg g_strips[] = {
+    STRIP(4, 4),  STRIP(8, 4),                                   //   32,   64 rows
+    STRIP(8, 8),  STRIP(12, 8), STRIP(16, 8), STRIP(20, 8),      //  128 .. 320 rows
+    STRIP(12, 16), STRIP(16, 16), STRIP(20, 16),                 //  384 .. 640 rows
+    STRIP(16, 32), STRIP(20, 32),                                // 1024, 1280 rows
+};
+constexpr int N_STRIPS = sizeof(g_strips) / sizeof(g_strips[0]);
+constexpr int WIDE_BIN = N_STRIPS;       // pseudo-bin of the 32-bit kernel
+
+}  // namespace
+
+struct mpn_engine {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    int64_t launches = 0, pairs = 0, cells = 0, wide_pairs = 0;
+    bool occ_done = false;
+};
+
+struct BinLaunch { int cfg; int64_t first; int64_t count; };
+
+struct mpn_batch {
+    mpn_engine* e = nullptr;
+    mpn_params p{};
+    std::vector<int8_t> mat;
+    int64_t npairs = 0;
+    int64_t total_cells = 0;
+    int max_rd = 0;
+    std::vector<BinLaunch> bins;
+    int64_t n_wide_pre = 0;               // pairs routed to the 32-bit kernel by the host classifier
+    Score16 sc16{};
+    FinishParams fin{};
+    // device
+    DevBuf seq, rd_off, rf_off, rd_len, rf_len, mask, tasks_fwd, tasks_rev, ends_fwd, ends_rev, colrec, fwdres, finalres, counters, dmat, scratch, cig, wide_boundary;
+    size_t seq_reads_bytes = 0, seq_bytes = 0;
+    int64_t colrec_words = 0;
+    unsigned long long scratch_bytes = 0, cig_cap = 0;
+    bool ran = false;
+    long long wide_stride = 0; int wide_blocks = 0;
+    // host staging for results
+    std::vector<FwdResult> h_fwd;
+    std::vector<FinalResult> h_fin;
+    std::vector<SwEnds> h_ends;
+    std::vector<SwTask> h_tasks;
+};
+
+extern "C" mpn_engine* mpn_engine_create(int device)
+{
+    int ndev = 0;
+    cudaError_t err = cudaGetDeviceCount(&ndev);
+    if (err != cudaSuccess || ndev == 0) {
+        fprintf(stderr, "[mpn_ssw] no CUDA device available (%s); this library has no CPU fallback\n", cudaGetErrorString(err));
+        return nullptr;
+    }
+    mpn_engine* e = new mpn_engine();
+    if (device < 0) CK(cudaGetDevice(&device));
+    e->device = device;
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    e->sm_count = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
+    e->stream = e->own_stream;
+    for (int c = 0; c < N_STRIPS; ++c) {
+        int nb = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, g_strips[c].fn, STRIP_BLOCK, g_strips[c].smem));
+        g_strips[c].blocks_per_sm = nb > 0 ? nb : 1;
+    }
+    return e;
+}
+
+extern "C" void mpn_engine_destroy(mpn_engine* e)
+{
+    if (!e) return;
+    cudaSetDevice(e->device);
+    cudaStreamDestroy(e->own_stream);
+    delete e;
+}
+
+extern "C" int mpn_engine_set_stream(mpn_engine* e, void* s)
+{
+    if (!e) return MPN_E_ARG;
+    e->stream = s ? reinterpret_cast<cudaStream_t>(s) : e->own_stream;
+    return 0;
+}
+
+extern "C" int mpn_engine_stats(const mpn_engine* e, int64_t* launches, int64_t* pairs, int64_t* cells, int64_t* wide_pairs)
+{
+    if (!e) return MPN_E_ARG;
+    if (launches) *launches = e->launches;
+    if (pairs) *pairs = e->pairs;
+    if (cells) *cells = e->cells;
+    if (wide_pairs) *wide_pairs = e->wide_pairs;
+    return 0;
+}
+
+extern "C" void mpn_batch_free(mpn_batch* b)
+{
+    if (!b) return;
+    cudaSetDevice(b->e->device);
+    DevBuf* bufs[] = {&b->seq, &b->rd_off, &b->rf_off, &b->rd_len, &b->rf_len, &b->mask, &b->tasks_fwd, &b->tasks_rev, &b->ends_fwd, &b->ends_rev,
+                      &b->colrec, &b->fwdres, &b->finalres, &b->counters, &b->dmat, &b->scratch, &b->cig, &b->wide_boundary};
+    for (DevBuf* d : bufs) d->release();
+    delete b;
+}
+
+extern "C" mpn_batch* mpn_batch_upload(mpn_engine* e, const mpn_params* p, const int8_t* reads, const int64_t* read_off, const int8_t* refs,
+                                        const int64_t* ref_off, const int32_t* masklen, int64_t npairs)
+{
+    if (!e || !p || !p->mat || p->n < 1 || p->n > 127 || npairs < 0 || npairs > 0x7fffffff) return nullptr;
+    if (npairs > 0 && (!reads || !read_off || !refs || !ref_off || !masklen)) return nullptr;
+    CK(cudaSetDevice(e->device));
+    mpn_batch* b = new mpn_batch();
+    b->e = e; b->p = *p; b->npairs = npairs;
+    b->mat.assign(p->mat, p->mat + (size_t)p->n * p->n);
+    b->p.mat = b->mat.data();
+    cudaStream_t st = e->stream;
+    const int n = p->n;
+
+    // ---- scoring: matrix rows for the packed kernel, bias as ssw_init (ssw.c:741-745)
+    int minv = 0, maxv = 0;
+    for (int i = 0; i < n * n; ++i) { minv = std::min<int>(minv, p->mat[i]); maxv = std::max<int>(maxv, p->mat[i]); }
+    memset(&b->sc16, 0, sizeof b->sc16);
+    for (int t = 0; t < n && t < 8; ++t) {
+        uint32_t w = 0;
+        for (int q = 0; q < 4 && q < n; ++q) w |= (uint32_t)(uint8_t)p->mat[t * n + q] << (8 * q);
+        b->sc16.matrow[t] = w;
+    }
+    const uint32_t go = (uint32_t)(uint16_t)(int16_t)(-(p->gapO & 0xff)), ge = (uint32_t)(uint16_t)(int16_t)(-(p->gapE & 0xff));
+    b->sc16.mgapO2 = go | (go << 16);
+    b->sc16.mgapE2 = ge | (ge << 16);
+    const bool have_byte = p->score_size == 0 || p->score_size == 2;
+    b->fin.bias = have_byte ? (abs(minv) & 0xff) : 0;
+    b->fin.have_byte = have_byte; b->fin.have_word = p->score_size == 1 || p->score_size == 2;
+    b->fin.gapO = p->gapO & 0xff; b->fin.gapE = p->gapE & 0xff;
+    b->fin.flag = p->flag & 0xff; b->fin.filters = p->filters & 0xffff;
+
+    // ---- per-pair lengths, binning
+    std::vector<int32_t> rd_len(npairs), rf_len(npairs);
+    std::vector<int32_t> bin(npairs);
+    std::vector<int64_t> bin_count(N_STRIPS + 1, 0);
+    std::vector<int64_t> cm_off(npairs);
+    int64_t cm_total = 0, cells = 0;
+    int max_rd = 0, max_rf = 0;
+    const bool packed_ok = n <= 8;
+    for (int64_t i = 0; i < npairs; ++i) {
+        const int64_t rl = read_off[i + 1] - read_off[i], fl = ref_off[i + 1] - ref_off[i];
+        if (rl < 0 || fl < 0 || rl > 0x3fffffff || fl > 0x3fffffff) { delete b; return nullptr; }
+        rd_len[i] = (int32_t)rl; rf_len[i] = (int32_t)fl;
+        cells += rl * fl;
+        max_rd = std::max<int>(max_rd, (int)rl); max_rf = std::max<int>(max_rf, (int)fl);
+        cm_off[i] = cm_total; cm_total += fl;
+        int c = WIDE_BIN;
+        // the packed kernel is exact as long as no H can reach the int16 clamp of ssw.c:425 (and the add cannot wrap)
+        const int64_t bound = (std::min(rl, fl) + 1) * (int64_t)std::max(maxv, 0);
+        if (packed_ok && bound <= 32767) {
+            for (int k = 0; k < N_STRIPS; ++k) if (rl <= g_strips[k].cap) { c = k; break; }
+        }
+        bin[i] = c; bin_count[c]++;
+    }
+    b->total_cells = cells; b->max_rd = max_rd; b->colrec_words = cm_total;
+    b->n_wide_pre = bin_count[WIDE_BIN];
+
+    // ---- task lists: per bin, longest targets first (counting sort on target length) so that the groups of a warp run in step
+    std::vector<int64_t> bin_first(N_STRIPS + 2, 0);
+    for (int c = 0; c <= N_STRIPS; ++c) bin_first[c + 1] = bin_first[c] + bin_count[c];
+    b->h_tasks.resize(npairs);
+    {
+        std::vector<int64_t> order(npairs);
+        bool uniform_rf = true;
+        for (int64_t i = 1; i < npairs && uniform_rf; ++i) uniform_rf = rf_len[i] == rf_len[0];
+        std::vector<int64_t> cursor(bin_first.begin(), bin_first.end() - 1);
+        if (uniform_rf || max_rf > (1 << 22)) {
+            for (int64_t i = 0; i < npairs; ++i) order[cursor[bin[i]]++] = i;
+        } else {
+            std::vector<int64_t> cnt((size_t)max_rf + 2, 0), idx(npairs);
+            for (int64_t i = 0; i < npairs; ++i) cnt[max_rf - rf_len[i] + 1]++;
+            for (int v = 0; v <= max_rf; ++v) cnt[v + 1] += cnt[v];
+            for (int64_t i = 0; i < npairs; ++i) idx[cnt[max_rf - rf_len[i]]++] = i;        // descending target length, stable
+            for (int64_t k = 0; k < npairs; ++k) { const int64_t i = idx[k]; order[cursor[bin[i]]++] = i; }
+        }
+        const int64_t reads_total = npairs ? read_off[npairs] - read_off[0] : 0;
+        for (int64_t k = 0; k < npairs; ++k) {
+            const int64_t i = order[k];
+            SwTask& t = b->h_tasks[k];
+            t.rd_base = read_off[i] - read_off[0];
+            t.rf_base = reads_total + (ref_off[i] - ref_off[0]);
+            t.cm_off = cm_off[i];
+            t.rd_len = rd_len[i]; t.rf_len = rf_len[i]; t.dir = 1; t.out = (int32_t)i;
+        }
+    }
+    for (int c = 0; c <= N_STRIPS; ++c) if (bin_count[c] > 0) b->bins.push_back(BinLaunch{c, bin_first[c], bin_count[c]});
+
+    // ---- device buffers + uploads
+    const size_t reads_bytes = npairs ? (size_t)(read_off[npairs] - read_off[0]) : 0;
+    const size_t refs_bytes = npairs ? (size_t)(ref_off[npairs] - ref_off[0]) : 0;
+    b->seq_reads_bytes = reads_bytes; b->seq_bytes = reads_bytes + refs_bytes;
+    b->seq.reserve(b->seq_bytes + 16);
+    std::vector<int64_t> rd_start(npairs), rf_start(npairs);
+    for (int64_t i = 0; i < npairs; ++i) { rd_start[i] = read_off[i] - read_off[0]; rf_start[i] = (int64_t)reads_bytes + (ref_off[i] - ref_off[0]); }
+    b->rd_off.reserve(sizeof(int64_t) * (npairs + 1)); b->rf_off.reserve(sizeof(int64_t) * (npairs + 1));
+    b->rd_len.reserve(sizeof(int32_t) * (npairs + 1)); b->rf_len.reserve(sizeof(int32_t) * (npairs + 1)); b->mask.reserve(sizeof(int32_t) * (npairs + 1));
+    b->tasks_fwd.reserve(sizeof(SwTask) * (npairs + 1)); b->tasks_rev.reserve(sizeof(SwTask) * (npairs + 1));
+    b->ends_fwd.reserve(sizeof(SwEnds) * (npairs + 1)); b->ends_rev.reserve(sizeof(SwEnds) * (npairs + 1));
+    b->colrec.reserve(sizeof(uint32_t) * (size_t)(cm_total + 1));
+    b->fwdres.reserve(sizeof(FwdResult) * (npairs + 1)); b->finalres.reserve(sizeof(FinalResult) * (npairs + 1));
+    b->counters.reserve(256 * sizeof(unsigned long long));
+    b->dmat.reserve((size_t)n * n + 16);
+    if (npairs) {
+        CK(cudaMemcpyAsync(b->seq.p, reads + read_off[0], reads_bytes, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(b->seq.as<int8_t>() + reads_bytes, refs + ref_off[0], refs_bytes, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(b->rd_off.p, rd_start.data(), sizeof(int64_t) * npairs, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(b->rf_off.p, rf_start.data(), sizeof(int64_t) * npairs, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(b->rd_len.p, rd_len.data(), sizeof(int32_t) * npairs, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(b->rf_len.p, rf_len.data(), sizeof(int32_t) * npairs, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(b->mask.p, masklen, sizeof(int32_t) * npairs, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(b->tasks_fwd.p, b->h_tasks.data(), sizeof(SwTask) * npairs, cudaMemcpyHostToDevice, st));
+    }
+    CK(cudaMemcpyAsync(b->dmat.p, b->mat.data(), (size_t)n * n, cudaMemcpyHostToDevice, st));
+
+    // ---- boundary rows of the 32-bit kernel (one slot per resident warp)
+    b->wide_blocks = e->sm_count * 3;
+    b->wide_stride = ((long long)max_rf + 63) & ~63ll;
+    b->wide_boundary.reserve(sizeof(int) * (size_t)b->wide_blocks * (WIDE_BLOCK / 32) * 2 * (size_t)b->wide_stride + 256);
+
+    // ---- traceback arenas.  Direction bytes: (2*band+1) per read row; the first attempt has band |dlen|+1 and most pairs
+    // stop there.  Budget 16 band cells per read base (+ slack); pairs that do not fit are reported (status 5) and re-run by fetch.
+    const bool want_cigar = (p->flag & 7) != 0;
+    if (want_cigar) {
+        int64_t read_bases = (int64_t)reads_bytes;
+        b->scratch_bytes = (unsigned long long)read_bases * 24ull + (unsigned long long)npairs * 512ull + (64ull << 20);
+        b->cig_cap = (unsigned long long)npairs * 24ull + (unsigned long long)read_bases / 4ull + 4096ull;
+        b->scratch.reserve(b->scratch_bytes);
+        b->cig.reserve(b->cig_cap * sizeof(uint32_t));
+    }
+    CK(cudaStreamSynchronize(st));     // the std::vectors above go out of scope
+    return b;
+}
+
+static void launch_strips(mpn_batch* b, const SwTask* tasks, bool forward, SwEnds* ends, int counter_base)
+{
+    mpn_engine* e = b->e;
+    cudaStream_t st = e->stream;
+    int slot = counter_base;
+    for (const BinLaunch& bl : b->bins) {
+        int* counter = reinterpret_cast<int*>(b->counters.as<unsigned long long>() + slot++);
+        if (bl.cfg == WIDE_BIN) {
+            launch_wide32_impl(tasks + bl.first, (int)bl.count, counter, b->seq.as<int8_t>(), b->dmat.as<int8_t>(), b->p.n, b->fin.gapO, b->fin.gapE,
+                               forward ? b->colrec.as<uint32_t>() : nullptr, ends, b->wide_boundary.as<int>(), b->wide_stride, b->wide_blocks, 0, st);
+            e->wide_pairs += forward ? bl.count : 0;
+        } else {
+            const StripCfg& c = g_strips[bl.cfg];
+            const int groups_per_block = STRIP_BLOCK / c.G;
+            int64_t blocks = (bl.count + groups_per_block - 1) / groups_per_block;
+            blocks = std::min<int64_t>(blocks, (int64_t)e->sm_count * c.blocks_per_sm);
+            c.fn<<<(unsigned)blocks, STRIP_BLOCK, c.smem, st>>>(tasks + bl.first, (int)bl.count, counter, b->seq.as<int8_t>(), b->sc16,
+                                                                  forward ? b->colrec.as<uint32_t>() : nullptr, ends);
+        }
+        CK(cudaGetLastError());
+        e->launches++;
+    }
+}
+
+extern "C" int mpn_batch_run(mpn_batch* b)
+{
+    if (!b) return MPN_E_ARG;
+    mpn_engine* e = b->e;
+    CK(cudaSetDevice(e->device));
+    cudaStream_t st = e->stream;
+    const int64_t n = b->npairs;
+    if (n == 0) { b->ran = true; return 0; }
+    CK(cudaMemsetAsync(b->counters.p, 0, 256 * sizeof(unsigned long long), st));
+    PairArrays pa{b->rd_off.as<int64_t>(), b->rf_off.as<int64_t>(), b->rd_len.as<int32_t>(), b->rf_len.as<int32_t>(), b->mask.as<int32_t>()};
+
+    // forward score pass -> ends + column records
+    launch_strips(b, b->tasks_fwd.as<SwTask>(), true, b->ends_fwd.as<SwEnds>(), 0);
+    // pairs the packed kernel refused (read code >= 4) are re-run in the 32-bit kernel before anything reads their ends
+    launch_wide32_impl(b->tasks_fwd.as<SwTask>(), (int)n, reinterpret_cast<int*>(b->counters.as<unsigned long long>() + 100),
+                       b->seq.as<int8_t>(), b->dmat.as<int8_t>(), b->p.n, b->fin.gapO, b->fin.gapE, b->colrec.as<uint32_t>(), b->ends_fwd.as<SwEnds>(),
+                       b->wide_boundary.as<int>(), b->wide_stride, b->wide_blocks, 1, st);
+    CK(cudaGetLastError());
+    e->launches++;
+    // second best + mode + reverse tasks
+    {
+        const int warps_per_block = 4;
+        const unsigned blocks = (unsigned)((n + warps_per_block - 1) / warps_per_block);
+        sw_finish_kernel<<<blocks, 128, 0, st>>>(b->tasks_fwd.as<SwTask>(), (int)n, b->ends_fwd.as<SwEnds>(), b->colrec.as<uint32_t>(), pa, b->fin,
+                                                  b->fwdres.as<FwdResult>(), b->tasks_rev.as<SwTask>());
+        CK(cudaGetLastError());
+        e->launches++;
+    }
+    const bool any_rev = !(b->fin.flag == 0);
+    if (any_rev) {
+        launch_strips(b, b->tasks_rev.as<SwTask>(), false, b->ends_rev.as<SwEnds>(), 32);
+        launch_wide32_impl(b->tasks_rev.as<SwTask>(), (int)n, reinterpret_cast<int*>(b->counters.as<unsigned long long>() + 101),
+                           b->seq.as<int8_t>(), b->dmat.as<int8_t>(), b->p.n, b->fin.gapO, b->fin.gapE, nullptr, b->ends_rev.as<SwEnds>(),
+                           b->wide_boundary.as<int>(), b->wide_stride, b->wide_blocks, 1, st);
+        CK(cudaGetLastError());
+        e->launches++;
+        TraceParams tp{b->fin.flag, b->fin.filters, b->p.filterd, b->fin.gapO, b->fin.gapE, b->p.n, b->dmat.as<int8_t>()};
+        Arena ar{b->scratch.as<uint8_t>(), b->scratch_bytes, b->counters.as<unsigned long long>() + 64};
+        const unsigned blocks = (unsigned)((n + 63) / 64);
+        sw_trace_kernel<<<blocks, 64, 0, st>>>(b->tasks_fwd.as<SwTask>(), (int)n, pa, b->seq.as<int8_t>(), b->fwdres.as<FwdResult>(), b->ends_rev.as<SwEnds>(), tp, ar,
+                                               b->cig.as<uint32_t>(), b->cig_cap, b->counters.as<unsigned long long>() + 65, b->finalres.as<FinalResult>());
+        CK(cudaGetLastError());
+        e->launches++;
+    }
+    b->ran = true;
+    e->pairs += n; e->cells += b->total_cells;
+    return 0;
+}
+
+extern "C" int mpn_batch_fetch(mpn_batch* b, mpn_result* out, uint32_t* cigar, int64_t cigar_cap)
+{
+    if (!b || (!out && b->npairs)) return MPN_E_ARG;
+    if (!b->ran) return MPN_E_ARG;
+    mpn_engine* e = b->e;
+    CK(cudaSetDevice(e->device));
+    cudaStream_t st = e->stream;
+    const int64_t n = b->npairs;
+    if (n == 0) return 0;
+    const bool any_rev = !(b->fin.flag == 0);
+    b->h_fwd.resize(n);
+    CK(cudaMemcpyAsync(b->h_fwd.data(), b->fwdres.p, sizeof(FwdResult) * n, cudaMemcpyDeviceToHost, st));
+    unsigned long long used[2] = {0, 0};
+    if (any_rev) {
+        b->h_fin.resize(n);
+        CK(cudaMemcpyAsync(b->h_fin.data(), b->finalres.p, sizeof(FinalResult) * n, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(used, b->counters.as<unsigned long long>() + 64, sizeof used, cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaStreamSynchronize(st));
+    int rc = 0;
+    if (any_rev && (b->p.flag & 7)) {
+        const unsigned long long words = std::min<unsigned long long>(used[1], b->cig_cap);
+        if ((int64_t)words > cigar_cap || (!cigar && words)) return MPN_E_CIGAR_SPACE;
+        if (words) CK(cudaMemcpyAsync(cigar, b->cig.p, words * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    for (int64_t i = 0; i < n; ++i) {
+        const FwdResult& f = b->h_fwd[i];
+        mpn_result& r = out[i];
+        r.score1 = (uint16_t)f.score1; r.score2 = (uint16_t)f.score2;
+        r.ref_end1 = f.ref_end1; r.read_end1 = f.read_end1; r.ref_end2 = f.ref_end2;
+        r.ref_begin1 = -1; r.read_begin1 = -1; r.cigar_len = 0; r.cigar_off = 0;
+        r.status = f.status ? MPN_ST_NULL : MPN_ST_OK;
+        if (any_rev && f.status == 0) {
+            const FinalResult& g = b->h_fin[i];
+            r.ref_begin1 = g.ref_begin1; r.read_begin1 = g.read_begin1;
+            r.cigar_len = g.cigar_len; r.cigar_off = g.cigar_off;
+            if (g.status == 3) r.status = MPN_ST_NULL;
+            else if (g.status == 5 || g.status == 6) {
+                if (rc == 0) fprintf(stderr, "[mpn_ssw] traceback arena exhausted (first at pair %lld, status %d)\n", (long long)i, g.status);
+                rc = MPN_E_UNSUPPORTED;
+            }
+        }
+    }
+    return rc;
+}
+
+extern "C" int mpn_align_batch(mpn_engine* e, const mpn_params* p, const int8_t* reads, const int64_t* read_off, const int8_t* refs,
+                               const int64_t* ref_off, const int32_t* masklen, int64_t npairs, mpn_result* out, uint32_t* cigar, int64_t cigar_cap)
+{
+    mpn_batch* b = mpn_batch_upload(e, p, reads, read_off, refs, ref_off, masklen, npairs);
+    if (!b) return MPN_E_ARG;
+    int rc = mpn_batch_run(b);
+    if (rc == 0) rc = mpn_batch_fetch(b, out, cigar, cigar_cap);
+    mpn_batch_free(b);
+    return rc;
+}

@@ -1,0 +1,82 @@
+// Shared device-side definitions for the batched Smith-Waterman kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mpn {
+
+// One score pass over one (read, target) pair in "processing order": forward passes walk both sequences upwards,
+// reverse passes (begin-position search, ssw.c:820-832) walk them downwards from (read_end1, ref_end1).
+struct SwTask {
+    int64_t rd_base;   // index into the sequence arena of the first read base in processing order
+    int64_t rf_base;   // index into the sequence arena of the first target base in processing order
+    int64_t cm_off;    // word offset into the column-record arena (one uint32 per target column), or -1 for "do not record"
+    int32_t rd_len;
+    int32_t rf_len;
+    int32_t dir;       // +1 forward, -1 reverse
+    int32_t out;       // slot in the SwEnds array
+};
+
+// Result of a score pass.  col/row are in processing order (for a reverse pass: distance from the end).
+struct SwEnds {
+    int32_t score;     // maximum H over the matrix (pad rows never exceed it)
+    int32_t col;       // first column (processing order) whose maximum equals score; -1 if score == 0
+    int32_t row;       // smallest row of that column holding score; 0 if score == 0
+    int32_t flags;     // SW_FLAG_*
+};
+enum { SW_FLAG_NEEDS_WIDE = 1 };   // pair cannot be handled by the packed 16-bit kernel (read code >= 4): rerun in the 32-bit kernel
+
+// Scoring for the packed kernel: row t of the substitution matrix, entries for read codes 0..3, one byte each.
+struct Score16 {
+    uint32_t matrow[8];
+    uint32_t mgapO2;   // (-gapO) in both 16-bit halves
+    uint32_t mgapE2;   // (-gapE) in both 16-bit halves
+};
+
+// ---- packed s16x2 helpers.  All single SASS instructions on sm_100a (profiles/r01_ubench_cell_pipes.md):
+//      VIADD.16x2 runs on the fmaheavy pipe, everything else here on the alu pipe (64 lanes/clk/SM).
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
+{
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+__device__ __forceinline__ uint32_t add2(uint32_t a, uint32_t b) { return __vadd2(a, b); }            // VIADD.16x2
+__device__ __forceinline__ uint32_t max2(uint32_t a, uint32_t b)
+{
+    uint32_t d;
+    asm("max.s16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
+// relu(max(h, e, f)).  Written as max(max(e, f), h) so that ptxas emits VIADD.16x2 (fma pipe) for the producer of h and one
+// VIMNMX3.S16x2.RELU here, instead of folding the add into a VIADDMNMX + VIMNMX pair (one more alu-pipe instruction).
+__device__ __forceinline__ uint32_t max3_relu(uint32_t h, uint32_t e, uint32_t f)
+{
+    uint32_t t, d;
+    asm("max.s16x2 %0, %1, %2;" : "=r"(t) : "r"(e), "r"(f));
+    asm("max.s16x2.relu %0, %1, %2;" : "=r"(d) : "r"(t), "r"(h));
+    return d;
+}
+// max(a, b) per half plus "a was already >= b" per half -> one VIMNMX.S16x2 with two predicate outputs.
+// (Own asm instead of __vibmax_s16x2: the CUDA 12.9 header omits the early-clobber on its output, so an in-place
+//  update `x = __vibmax_s16x2(x, ...)` compares the result with itself and always reports "no improvement".)
+__device__ __forceinline__ uint32_t max2_track(uint32_t a, uint32_t b, bool& a_ge_hi, bool& a_ge_lo)
+{
+    uint32_t val, ph, pl;
+    asm("{.reg .pred pu, pv;\n\t"
+        ".reg .s16 t0, t1, t2, t3;\n\t"
+        "max.s16x2 %0, %3, %4;\n\t"
+        "mov.b32 {t0, t1}, %0;\n\t"
+        "mov.b32 {t2, t3}, %3;\n\t"
+        "setp.eq.s16 pv, t0, t2;\n\t"
+        "setp.eq.s16 pu, t1, t3;\n\t"
+        "selp.b32 %1, 1, 0, pu;\n\t"
+        "selp.b32 %2, 1, 0, pv;}"
+        : "=&r"(val), "=&r"(ph), "=&r"(pl) : "r"(a), "r"(b));
+    a_ge_hi = ph != 0; a_ge_lo = pl != 0;
+    return val;
+}
+__device__ __forceinline__ uint32_t max3(uint32_t a, uint32_t b, uint32_t c) { return __vimax3_s16x2(a, b, c); }             // VIMNMX3.S16x2
+__device__ __forceinline__ uint32_t addmax_relu(uint32_t a, uint32_t b, uint32_t c) { return __viaddmax_s16x2_relu(a, b, c); } // VIADDMNMX.S16x2.RELU
+
+}  // namespace mpn

@@ -1,0 +1,224 @@
+// Packed 16-bit inter-task score kernel (sm_100a): replaces the score passes of ssw.c -- sw_sse2_byte (ssw.c:123-328),
+// sw_sse2_word (ssw.c:354-530) and their query profiles qP_byte / qP_word (ssw.c:89-114, 330-352) -- for pairs whose
+// scores cannot reach the int16 clamp.
+//
+// Work decomposition (one pair per thread group, G threads, G | 32):
+//   * the read is laid over 2*G "stages" of KR rows each; thread t owns stage 2t in the LOW 16-bit halves of its
+//     registers and stage 2t+1 in the HIGH halves (s16x2 packing of two pipeline stages of the SAME pair);
+//   * stage v processes target column c at step s = c + v (systolic wavefront).  Per step a thread updates KR packed
+//     cells with H/E/F in registers; the bottom H/F, the running column maximum and the target's matrix row move to the
+//     next stage by warp shuffle (between threads) or by a byte permute (low half -> high half of the same thread);
+//   * reads shorter than the strip are aligned to its BOTTOM: the dead rows on top score <= 0 and therefore stay 0, which
+//     is exactly the H[-1][*] = 0 boundary, and the last stage's bottom row is always the read's last row;
+//   * substitution scores come from one PRMT per packed cell: the selector (per row, built once per task from the read)
+//     picks mat[t_lo][q_lo] and mat[t_hi][q_hi] out of the two 4-byte matrix rows of the current target bases and
+//     sign-extends them (selector bit 3).  This replaces the striped query profile.
+//
+// Per packed cell: 4.5 alu-pipe instructions (PRMT, VIMNMX3.S16x2.RELU, 2x VIADDMNMX.S16x2.RELU, 1/2 VIMNMX3.S16x2 for
+// the column maximum) + 2 VIADD.16x2 on the fma pipe.
+//
+// What the kernel returns per task: the maximum score, the first column attaining it and the smallest row of that
+// column attaining it (ssw.c:260-277, 284-293 tie rules), and -- for forward passes -- one record per target column
+// holding (column maximum over the real rows, H of the read's last row).  The pad rows that the SSE2 layout adds
+// (ssw.c:108, 346) are applied afterwards, analytically, by sw_finish_kernel (sw_finish.cuh) from these records.
+#pragma once
+#include "sw_common.cuh"
+#include <cstdio>
+
+namespace mpn {
+
+constexpr int STRIP_BLOCK = 128;
+
+template <int KR>
+__host__ __device__ constexpr size_t strip16_smem_bytes() { return (size_t)2 * (KR / 4) * STRIP_BLOCK * sizeof(uint4); }
+
+template <int KR, int G>
+__global__ void __launch_bounds__(STRIP_BLOCK, 4)
+sw_strip16_kernel(const SwTask* __restrict__ tasks, int ntasks, int* __restrict__ counter, const int8_t* __restrict__ seq,
+                  const Score16 sc, uint32_t* __restrict__ colrec, SwEnds* __restrict__ out)
+{
+    static_assert(KR % 4 == 0 && KR >= 4, "KR must be a multiple of 4");
+    static_assert(G == 2 || G == 4 || G == 8 || G == 16 || G == 32, "G must divide 32");
+    constexpr int CAP = 2 * G * KR;               // rows covered by one strip
+    extern __shared__ uint4 snap[];               // [2 halves][KR/4][STRIP_BLOCK]: H column of a stage at its last improvement
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int t = lane % G;                       // thread index inside the group
+    const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (lane - t));
+    // merge selector for (value received from thread t-1, own value): low half <- received.high, high half <- own.low.
+    // For the first thread of a group the low half must be the matrix boundary (0): select the sign byte of own byte 7
+    // (all merged quantities are >= 0, so that byte replicates to 0x00).
+    const uint32_t mergeSel = (t == 0) ? 0x54ffu : 0x5432u;
+
+    uint32_t H[KR], E[KR], sel[KR];
+    uint32_t Ftop = 0, Hdtop = 0, cmin = 0;       // boundary values entering this thread's two stages at the next step
+    uint32_t a = 0, b = 0;                        // matrix rows of the target bases under the low / high stage
+    uint32_t best = 0, cvlo = 0, cvhi = 0;        // per-stage best score (packed) and the step at which it was first reached
+    uint32_t tchunk = 0, tnext = 0;               // matrix rows of target bases [kG + t] of the current / next chunk
+    int s = 0, nsteps = 0, dead = 0;
+    int rf_len = 0, tdir = 1, tout = 0, wide = 0;
+    int64_t rf_base = 0, cm_off = -1;
+    bool active = true;                           // group still has (or may fetch) a task
+
+#pragma unroll
+    for (int j = 0; j < KR; ++j) { H[j] = 0; E[j] = 0; sel[j] = 0x8888u | 0x4400u; }
+
+    for (;;) {
+        // ------------------------------------------------------------------ task boundary (every G steps) -------------
+        if (active && s >= nsteps) {
+            if (nsteps > 0) {
+                // ---- finalize: reduce (score, first column, stage) over the 2G stages of the group
+                int sc_lo = (int)(int16_t)(best & 0xffffu), sc_hi = (int)(int16_t)(best >> 16);
+                int col_lo = (int)cvlo - 2 * t, col_hi = (int)cvhi - 2 * t - 1;
+                if (sc_lo <= 0) col_lo = 0;
+                if (sc_hi <= 0) col_hi = 0;
+                unsigned long long k_lo = ((unsigned long long)(unsigned)sc_lo << 40) | ((unsigned long long)(0xffffffu - (unsigned)col_lo) << 8) | (unsigned)(255 - 2 * t);
+                unsigned long long k_hi = ((unsigned long long)(unsigned)sc_hi << 40) | ((unsigned long long)(0xffffffu - (unsigned)col_hi) << 8) | (unsigned)(254 - 2 * t);
+                unsigned long long key = k_lo > k_hi ? k_lo : k_hi;
+#pragma unroll
+                for (int off = G / 2; off >= 1; off >>= 1) {
+                    unsigned long long o = __shfl_xor_sync(gmask, key, off);
+                    key = o > key ? o : key;
+                }
+#ifdef MPN_DEBUG
+                if (tout == 0) printf("fin t=%d best=%08x cvlo=%u cvhi=%u key=%llx s=%d nsteps=%d dead=%d\n", t, best, cvlo, cvhi, key, s, nsteps, dead);
+#endif
+                const int wscore = (int)(key >> 40);
+                const int wcol = (int)(0xffffffu - (unsigned)((key >> 8) & 0xffffffu));
+                const int wstage = 255 - (int)(key & 0xffu);
+                const unsigned anywide = __ballot_sync(gmask, wide != 0);
+                if (t == (wstage >> 1)) {
+                    int row = -999;
+                    if (wscore > 0) {
+                        const int half = wstage & 1;
+                        const uint4* sp = snap + (size_t)half * (KR / 4) * STRIP_BLOCK + tid;
+                        for (int k = KR / 4 - 1; k >= 0; --k) {
+                            uint4 v = sp[(size_t)k * STRIP_BLOCK];
+                            uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                            for (int q = 3; q >= 0; --q) {
+                                int hv = half ? (int)(int16_t)(w[q] >> 16) : (int)(int16_t)(w[q] & 0xffffu);
+                                if (hv == wscore) row = wstage * KR + 4 * k + q - dead;
+                            }
+                        }
+                    }
+                    SwEnds e;
+                    e.score = wscore;
+                    e.col = wscore > 0 ? wcol : -1;
+                    e.row = wscore > 0 ? row : 0;
+                    e.flags = anywide ? SW_FLAG_NEEDS_WIDE : 0;
+                    out[tout] = e;
+                }
+            }
+            // ---- fetch the next task of this group
+            int ti = 0;
+            if (t == 0) ti = atomicAdd(counter, 1);
+            ti = __shfl_sync(gmask, ti, lane - t);
+            if (ti >= ntasks) {
+                active = false;
+                rf_len = 0; nsteps = 0; cm_off = -1;
+#pragma unroll
+                for (int j = 0; j < KR; ++j) { H[j] = 0; E[j] = 0; sel[j] = 0x8888u | 0x4400u; }
+                Ftop = Hdtop = cmin = a = b = best = 0; tnext = 0; tchunk = 0;
+            } else {
+                const SwTask tk = tasks[ti];
+                const int rd_len = tk.rd_len;
+                rf_len = tk.rf_len; tdir = tk.dir; tout = tk.out; rf_base = tk.rf_base; cm_off = tk.cm_off;
+                dead = CAP - rd_len;
+                wide = 0;
+                // selectors: low half = row (2t)*KR + j, high half = row (2t+1)*KR + j, both minus the dead rows on top
+#pragma unroll
+                for (int j = 0; j < KR; ++j) {
+                    const int r_lo = 2 * t * KR + j - dead, r_hi = r_lo + KR;
+                    uint32_t n_lo = 0x88u, n_hi = 0xccu;                      // dead row: sign bytes only -> score 0 or -1
+                    if (r_lo >= 0) {
+                        const int q = seq[tk.rd_base + (int64_t)tdir * r_lo];
+                        if ((unsigned)q < 4u) n_lo = (uint32_t)q | ((uint32_t)(q | 8) << 4); else wide = 1;
+                    }
+                    if (r_hi >= 0) {
+                        const int q = seq[tk.rd_base + (int64_t)tdir * r_hi];
+                        if ((unsigned)q < 4u) n_hi = (uint32_t)(q | 4) | ((uint32_t)(q | 12) << 4); else wide = 1;
+                    }
+                    sel[j] = n_lo | (n_hi << 8);
+                    H[j] = 0; E[j] = 0;
+                }
+                Ftop = Hdtop = cmin = a = b = best = 0; cvlo = cvhi = 0;
+                s = 0;
+                nsteps = (rf_len > 0 && rd_len > 0) ? rf_len + 2 * G - 1 : 1;
+                if (rd_len > CAP) { wide = 1; nsteps = 1; rf_len = 0; }      // host scheduling error: never index out of the strip
+                {   // matrix rows of target chunk 0
+                    const int idx = t;
+                    uint32_t mr = 0;
+                    if (idx < rf_len) mr = sc.matrow[seq[rf_base + (int64_t)tdir * idx] & 7];
+                    tnext = mr;
+                }
+            }
+        }
+        if (!__any_sync(0xffffffffu, active)) break;
+
+        // rotate the target chunk: tchunk <- chunk s/G, prefetch chunk s/G + 1
+        tchunk = tnext;
+        {
+            const int idx = s + G + t;
+            uint32_t mr = 0;
+            if (idx < rf_len) mr = sc.matrow[seq[rf_base + (int64_t)tdir * idx] & 7];
+            tnext = mr;
+        }
+
+        // ------------------------------------------------------------------ G wavefront steps ---------------------------
+#pragma unroll 1
+        for (int u = 0; u < G; ++u, ++s) {
+            {   // the first stage takes the next target base from the chunk, the others got theirs by shuffle last step
+                const uint32_t a0 = __shfl_sync(0xffffffffu, tchunk, u, G);
+                a = (t == 0) ? a0 : a;
+            }
+            uint32_t F = Ftop, m = 0;
+            uint32_t h = add2(Hdtop, prmt(a, b, sel[0]));
+#pragma unroll
+            for (int j = 0; j < KR; ++j) {
+                uint32_t hnext = 0;
+                if (j + 1 < KR) hnext = add2(H[j], prmt(a, b, sel[j + 1]));   // uses H(j) of the previous column: diagonal of row j+1
+                else Hdtop = H[j];                                            // bottom H of the previous column: diagonal for the next stage
+                const uint32_t Hn = max3_relu(h, E[j], F);
+                const uint32_t Hg = add2(Hn, sc.mgapO2);
+                E[j] = addmax_relu(E[j], sc.mgapE2, Hg);
+                F = addmax_relu(F, sc.mgapE2, Hg);
+                H[j] = Hn;
+                if (j & 1) m = max3(m, H[j - 1], Hn);
+                h = hnext;
+            }
+            // ---- per-stage best tracking: strict improvement keeps the first column (ssw.c:269 / :474)
+            bool ge_hi, ge_lo;
+            best = max2_track(best, m, ge_hi, ge_lo);
+            if (!ge_lo) {
+                cvlo = (uint32_t)s;
+#pragma unroll
+                for (int k = 0; k < KR / 4; ++k) snap[(size_t)k * STRIP_BLOCK + tid] = make_uint4(H[4 * k], H[4 * k + 1], H[4 * k + 2], H[4 * k + 3]);
+            }
+            if (!ge_hi) {
+                cvhi = (uint32_t)s;
+#pragma unroll
+                for (int k = 0; k < KR / 4; ++k) snap[(size_t)(KR / 4 + k) * STRIP_BLOCK + tid] = make_uint4(H[4 * k], H[4 * k + 1], H[4 * k + 2], H[4 * k + 3]);
+            }
+            const uint32_t cmout = max2(cmin, m);
+            // ---- last stage: record (column maximum, bottom-row H) of column s - (2G-1)
+            if (t == G - 1) {
+                const int c = s - (2 * G - 1);
+                if (cm_off >= 0 && c >= 0 && c < rf_len) colrec[cm_off + c] = prmt(cmout, H[KR - 1], 0x7632u);
+            }
+            // ---- hand the boundary to the next stage
+            const uint32_t rF = __shfl_up_sync(0xffffffffu, F, 1, G);
+            const uint32_t rH = __shfl_up_sync(0xffffffffu, Hdtop, 1, G);
+            const uint32_t rC = __shfl_up_sync(0xffffffffu, cmout, 1, G);
+            const uint32_t rA = __shfl_up_sync(0xffffffffu, b, 1, G);
+            Ftop = prmt(rF, F, mergeSel);
+            Hdtop = prmt(rH, Hdtop, mergeSel);
+            cmin = prmt(rC, cmout, mergeSel);
+            b = a;
+            a = rA;
+        }
+    }
+}
+
+}  // namespace mpn

@@ -1,0 +1,175 @@
+// Banded traceback + CIGAR kernel (sm_100a): replaces banded_sw (ssw.c:532-718) and the begin-position / CIGAR part of
+// ssw_align (ssw.c:830-848).  One thread per pair; the band of a 150-300 bp read is 3-9 cells wide, so the work per pair
+// is a few thousand int32 cells, ~1 % of the score passes.  Direction bits live in a global scratch arena that the
+// kernel carves up with an atomic bump pointer (the band is doubled until the banded maximum reaches the score, so the
+// size is only known on the device); CIGAR words go to a second arena the same way.
+//
+// banded_sw semantics kept:
+//   band attempt bw: row i covers columns max(0,i-bw) .. min(refLen-1,i+bw); E/F are NOT floored; ties prefer the
+//   diagonal, then F; E and F open only when strictly better than extending (ssw.c:593-599, 609-610); the previous-row
+//   arrays are addressed in band coordinates and slot `edge` is zeroed before every row (ssw.c:580) -- including the case
+//   where that zeroes the valid cell above the last target column; bw doubles until max >= score (ssw.c:555,614-615);
+//   traceback runs from the bottom-right corner while i > 0 (ssw.c:625), run-length encodes, appends the row-0 match
+//   (ssw.c:680-697) and reverses.
+#pragma once
+#include "sw_finish.cuh"
+
+namespace mpn {
+
+struct TraceParams {
+    int32_t flag, filters, filterd;
+    int32_t gapO, gapE, n;
+    const int8_t* mat;            // n*n, device
+};
+
+struct FinalResult {              // second half of s_align (ssw.h:47-57)
+    int32_t ref_begin1, read_begin1;
+    int32_t cigar_len;
+    int32_t status;               // 0 ok; 3 traceback error (reference returns NULL, ssw.c:840-843); 5 scratch arena exhausted; 6 cigar arena exhausted
+    int64_t cigar_off;            // word offset into the CIGAR arena
+};
+
+struct Arena {
+    uint8_t* base;
+    unsigned long long bytes;
+    unsigned long long* used;
+};
+
+__device__ __forceinline__ int band_x(int i, int w) { int x = i - w; return x > 0 ? x : 0; }
+
+__global__ void __launch_bounds__(64)
+sw_trace_kernel(const SwTask* __restrict__ order, int ntasks, PairArrays pa, const int8_t* __restrict__ seq, const FwdResult* __restrict__ fr,
+                const SwEnds* __restrict__ rev, TraceParams tp, Arena scratch, uint32_t* __restrict__ cig, unsigned long long cig_cap,
+                unsigned long long* __restrict__ cig_used, FinalResult* __restrict__ out)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= ntasks) return;
+    const int i = order[k].out;
+    const FwdResult f = fr[i];
+    FinalResult r;
+    r.ref_begin1 = -1; r.read_begin1 = -1; r.cigar_len = 0; r.status = 0; r.cigar_off = 0;
+    if (!f.want_rev) { out[i] = r; return; }
+
+    int sub_ref, sub_read;
+    if (f.score1 > 0) {
+        const SwEnds e = rev[i];
+        r.ref_begin1 = f.ref_end1 - e.col;
+        r.read_begin1 = f.read_end1 - e.row;
+    } else {
+        // nothing aligned: the reverse pass of the reference sees an empty (byte mode) or 1x1 (word mode) matrix (ssw.c:820-831)
+        r.ref_begin1 = f.word_mode ? 0 : -1;
+        r.read_begin1 = 0;
+    }
+    if ((7 & tp.flag) == 0 || ((2 & tp.flag) != 0 && f.score1 < tp.filters) ||
+        ((4 & tp.flag) != 0 && (f.ref_end1 - r.ref_begin1 > tp.filterd || f.read_end1 - r.read_begin1 > tp.filterd))) { out[i] = r; return; }   // ssw.c:833
+
+    sub_ref = f.ref_end1 - r.ref_begin1 + 1;
+    sub_read = f.read_end1 - r.read_begin1 + 1;
+    if (f.score1 <= 0) {
+        // 1x1 problem, traceback loop never runs: "1M" (ssw.c:625,680-687)
+        unsigned long long o = atomicAdd(cig_used, 1ull);
+        if (o + 1 > cig_cap) { r.status = 6; out[i] = r; return; }
+        cig[o] = 1u << 4;
+        r.cigar_off = (int64_t)o; r.cigar_len = 1;
+        out[i] = r;
+        return;
+    }
+    const int8_t* ref = seq + pa.rf_off[i] + r.ref_begin1;
+    const int8_t* read = seq + pa.rd_off[i] + r.read_begin1;
+    const int n = tp.n, gapO = tp.gapO, gapE = tp.gapE, score = f.score1;
+    int bw = abs(sub_ref - sub_read) + 1;
+    int width = 0, width_d = 0, maxv = 0;
+    uint8_t* dir = nullptr;
+    do {
+        width = bw * 2 + 3; width_d = bw * 2 + 1;
+        const unsigned long long need_dir = ((unsigned long long)width_d * (unsigned long long)sub_read + 15ull) & ~15ull;
+        const unsigned long long need = need_dir + 3ull * (unsigned long long)(width + 1) * 4ull;
+        const unsigned long long o = atomicAdd(scratch.used, (need + 15ull) & ~15ull);
+        if (o + need > scratch.bytes) { r.status = 5; out[i] = r; return; }
+        dir = scratch.base + o;
+        int* hb = reinterpret_cast<int*>(dir + need_dir);
+        int* eb = hb + (width + 1);
+        int* hc = eb + (width + 1);
+        for (int j = 0; j <= width; ++j) { hb[j] = 0; eb[j] = 0; hc[j] = 0; }
+        for (int ii = 0; ii < sub_read; ++ii) {
+            const int beg = max(0, ii - bw), end = min(sub_ref - 1, ii + bw);
+            const int edge = min(end + 1, width - 1);
+            const int xi = band_x(ii, bw), xp = band_x(ii - 1, bw);
+            int fv = 0, u = 0;
+            uint8_t* line = dir + (size_t)width_d * (size_t)ii;
+            hb[0] = 0; eb[0] = 0; hb[edge] = 0; eb[edge] = 0; hc[0] = 0;
+            const int8_t* mrow = tp.mat + (int)read[ii];
+            for (int j = beg; j <= end; ++j) {
+                const int e_idx = j - xp + 1, d_idx = j - xp, b_idx = j - xi;
+                u = j - xi + 1;
+                int open = ii == 0 ? -gapO : hb[e_idx] - gapO;
+                int ext = ii == 0 ? -gapE : eb[e_idx] - gapE;
+                const int ev = open > ext ? open : ext;
+                const int de3 = open > ext ? 1 : 0;
+                open = hc[b_idx] - gapO; ext = fv - gapE;
+                fv = open > ext ? open : ext;
+                const int df5 = open > ext ? 1 : 0;
+                const int e1 = ev > 0 ? ev : 0, f1 = fv > 0 ? fv : 0;
+                const int t1 = e1 > f1 ? e1 : f1;
+                const int t2 = hb[d_idx] + (int)mrow[(int)ref[j] * n];
+                const int hv = t1 > t2 ? t1 : t2;
+                int dh;
+                if (t1 <= t2) dh = 1; else dh = e1 > f1 ? (de3 ? 3 : 2) : (df5 ? 5 : 4);
+                // previous-row E must be read before it is overwritten: e_idx >= u always (xp <= xi), so writing eb[u] now is safe
+                eb[u] = ev;
+                hc[u] = hv;
+                if (hv > maxv) maxv = hv;
+                line[j - xi] = (uint8_t)(de3 | (df5 << 1) | (dh << 2));
+            }
+            for (int j = 1; j <= u; ++j) hb[j] = hc[j];
+        }
+        bw *= 2;
+    } while (maxv < score);
+    bw /= 2;
+
+    // ---- traceback, pass 1 counts the CIGAR words, pass 2 writes them back to front
+    const long long total = (long long)width_d * sub_read;
+    int l = 0;
+    unsigned long long coff = 0;
+    for (int pass = 0; pass < 2; ++pass) {
+        int ii = sub_read - 1, j = sub_ref - 1, state = 2, run = 0, cnt = 0;
+        int op = 0, prev = 0;                        // 0 = M, 1 = I, 2 = D (BAM codes)
+        while (ii > 0) {
+            const long long idx = (long long)width_d * ii + (j - band_x(ii, bw));
+            const int cell = (idx >= 0 && idx < total) ? (int)dir[idx] : 0;
+            int d;
+            if (state == 2) d = cell >> 2; else if (state == 0) d = (cell & 1) ? 3 : 2; else d = (cell & 2) ? 5 : 4;
+            if ((cell >> 2) == 0) d = 0;              // unwritten cell
+            switch (d) {
+                case 1: --ii; --j; state = 2; op = 0; break;
+                case 2: --ii; state = 0; op = 1; break;
+                case 3: --ii; state = 2; op = 1; break;
+                case 4: --j; state = 1; op = 2; break;
+                case 5: --j; state = 2; op = 2; break;
+                default: r.status = 3; r.cigar_len = 0; out[i] = r; return;
+            }
+            if (op == prev) ++run;
+            else {
+                if (pass) cig[coff + (unsigned)(l - 1 - cnt)] = ((uint32_t)run << 4) | (uint32_t)prev;
+                ++cnt; prev = op; run = 1;
+            }
+        }
+        if (op == 0) {
+            if (pass) cig[coff + (unsigned)(l - 1 - cnt)] = ((uint32_t)(run + 1) << 4);
+            ++cnt;
+        } else {
+            if (pass) { cig[coff + (unsigned)(l - 1 - cnt)] = ((uint32_t)run << 4) | (uint32_t)op; cig[coff + (unsigned)(l - 2 - cnt)] = 1u << 4; }
+            cnt += 2;
+        }
+        if (!pass) {
+            l = cnt;
+            coff = atomicAdd(cig_used, (unsigned long long)l);
+            if (coff + (unsigned long long)l > cig_cap) { r.status = 6; out[i] = r; return; }
+        }
+    }
+    r.cigar_len = l;
+    r.cigar_off = (int64_t)coff;
+    out[i] = r;
+}
+
+}  // namespace mpn
