@@ -59,6 +59,10 @@ mpn_engine* mpn_engine_create(int device);
 void mpn_engine_destroy(mpn_engine* e);
 /* run on a caller-owned cudaStream_t (e.g. PyTorch's current stream) instead of the engine's own; 0 restores the own stream */
 int mpn_engine_set_stream(mpn_engine* e, void* cuda_stream);
+/* optional phase timing (CUDA events on the engine's stream): enable, run a batch, then read the milliseconds of
+ * {forward score kernels, second-best/mode epilogue, reverse score kernels, traceback+CIGAR} of the last mpn_batch_run */
+int mpn_engine_set_profile(mpn_engine* e, int on);
+int mpn_engine_phase_ms(mpn_engine* e, float* ms4);
 /* counters since creation: kernel launches, pairs, forward cells, pairs re-run in the 32-bit kernel */
 int mpn_engine_stats(const mpn_engine* e, int64_t* launches, int64_t* pairs, int64_t* cells, int64_t* wide_pairs);
 
@@ -83,6 +87,8 @@ mpn_batch* mpn_batch_upload(mpn_engine* e, const mpn_params* p, const int8_t* re
                             const int64_t* ref_off, const int32_t* masklen, int64_t npairs);
 int mpn_batch_run(mpn_batch* b);
 int mpn_batch_fetch(mpn_batch* b, mpn_result* out, uint32_t* cigar, int64_t cigar_cap);
+/* bytes copied host->device by upload and device->host by fetch for this batch */
+int mpn_batch_io_bytes(const mpn_batch* b, int64_t* h2d, int64_t* d2h);
 void mpn_batch_free(mpn_batch* b);
 
 #ifdef __cplusplus

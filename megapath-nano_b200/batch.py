@@ -33,6 +33,8 @@ def lib():
         L.mpn_engine_destroy.argtypes = [ct.c_void_p]
         L.mpn_engine_set_stream.argtypes = [ct.c_void_p, ct.c_void_p]
         L.mpn_engine_stats.argtypes = [ct.c_void_p] + [ct.POINTER(ct.c_int64)] * 4
+        L.mpn_engine_set_profile.argtypes = [ct.c_void_p, ct.c_int]
+        L.mpn_engine_phase_ms.argtypes = [ct.c_void_p, ct.POINTER(ct.c_float)]
         L.mpn_batch_upload.restype = ct.c_void_p
         L.mpn_batch_upload.argtypes = [ct.c_void_p, ct.POINTER(MpnParams), ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_int64]
         L.mpn_batch_run.argtypes = [ct.c_void_p]
@@ -74,6 +76,16 @@ class Engine:
 
     def set_stream(self, cuda_stream_ptr):
         self.L.mpn_engine_set_stream(self.h, ct.c_void_p(cuda_stream_ptr))
+
+    def set_profile(self, on=True):
+        self.L.mpn_engine_set_profile(self.h, 1 if on else 0)
+
+    def phase_ms(self):
+        """ms of {forward, finish, reverse, trace} of the last run (needs set_profile(True))"""
+        v = (ct.c_float * 4)()
+        if self.L.mpn_engine_phase_ms(self.h, v):
+            return None
+        return dict(forward=v[0], finish=v[1], reverse=v[2], trace=v[3])
 
     def stats(self):
         v = [ct.c_int64(0) for _ in range(4)]

@@ -24,14 +24,43 @@ namespace {
 
 struct DevBuf {
     void* p = nullptr; size_t cap = 0;
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+// Device allocations are recycled through the engine: a batch takes the smallest cached block that fits and gives it
+// back in mpn_batch_free, so steady-state batches of similar size never call cudaMalloc / cudaFree.
+struct DevPool {
+    std::vector<DevBuf> free_list;
+    void take(DevBuf& d, size_t bytes) {
+        if (bytes <= d.cap) return;
+        give(d);
+        int best = -1;
+        for (size_t i = 0; i < free_list.size(); ++i)
+            if (free_list[i].cap >= bytes && (best < 0 || free_list[i].cap < free_list[best].cap)) best = (int)i;
+        if (best >= 0 && free_list[best].cap <= bytes * 2 + (1u << 20)) { d = free_list[best]; free_list.erase(free_list.begin() + best); return; }
+        size_t want = bytes + bytes / 16 + 256;
+        cudaError_t err = cudaMalloc(&d.p, want);
+        if (err != cudaSuccess) {            // out of memory: drop the cache and retry once
+            cudaGetLastError();
+            clear();
+            CK(cudaMalloc(&d.p, want));
+        }
+        d.cap = want;
+    }
+    void give(DevBuf& d) { if (d.p) free_list.push_back(d); d.p = nullptr; d.cap = 0; }
+    void clear() { for (DevBuf& f : free_list) cudaFree(f.p); free_list.clear(); }
+};
+
+// grow-only pinned host staging
+struct PinBuf {
+    void* p = nullptr; size_t cap = 0;
     void reserve(size_t bytes) {
         if (bytes <= cap) return;
-        if (p) CK(cudaFree(p));
-        size_t want = bytes + bytes / 8 + 256;
-        CK(cudaMalloc(&p, want));
-        cap = want;
+        if (p) CK(cudaFreeHost(p));
+        cap = bytes + bytes / 8 + 4096;
+        CK(cudaHostAlloc(&p, cap, cudaHostAllocDefault));
     }
-    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
     template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
@@ -56,6 +85,13 @@ struct mpn_engine {
     cudaStream_t own_stream = nullptr, stream = nullptr;
     int64_t launches = 0, pairs = 0, cells = 0, wide_pairs = 0;
     bool occ_done = false;
+    bool profile = false;
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    int ev_valid = 0;
+    DevPool pool;
+    PinBuf pin_tasks, pin_fwd, pin_fin, pin_misc;
+    std::vector<int32_t> h_bin;
+    std::vector<int64_t> h_order, h_idx, h_cnt;
 };
 
 struct BinLaunch { int cfg; int64_t first; int64_t count; };
@@ -72,17 +108,13 @@ struct mpn_batch {
     Score16 sc16{};
     FinishParams fin{};
     // device
-    DevBuf seq, rd_off, rf_off, rd_len, rf_len, mask, tasks_fwd, tasks_rev, ends_fwd, ends_rev, colrec, fwdres, finalres, counters, dmat, scratch, cig, wide_boundary;
+    DevBuf seq, mask, tasks_fwd, tasks_rev, ends_fwd, ends_rev, colrec, fwdres, finalres, counters, dmat, scratch, cig, wide_boundary;
     size_t seq_reads_bytes = 0, seq_bytes = 0;
     int64_t colrec_words = 0;
     unsigned long long scratch_bytes = 0, cig_cap = 0;
     bool ran = false;
+    size_t h2d_bytes = 0, d2h_bytes = 0;
     long long wide_stride = 0; int wide_blocks = 0;
-    // host staging for results
-    std::vector<FwdResult> h_fwd;
-    std::vector<FinalResult> h_fin;
-    std::vector<SwEnds> h_ends;
-    std::vector<SwTask> h_tasks;
 };
 
 extern "C" mpn_engine* mpn_engine_create(int device)
@@ -106,6 +138,7 @@ extern "C" mpn_engine* mpn_engine_create(int device)
         int nb = 0;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, g_strips[c].fn, STRIP_BLOCK, g_strips[c].smem));
         g_strips[c].blocks_per_sm = nb > 0 ? nb : 1;
+        if (getenv("MPN_VERBOSE")) fprintf(stderr, "[mpn_ssw] strip G=%d KR=%d cap=%d smem=%zu blocks/SM=%d\n", g_strips[c].G, g_strips[c].KR, g_strips[c].cap, g_strips[c].smem, nb);
     }
     return e;
 }
@@ -115,6 +148,9 @@ extern "C" void mpn_engine_destroy(mpn_engine* e)
     if (!e) return;
     cudaSetDevice(e->device);
     cudaStreamDestroy(e->own_stream);
+    e->pool.clear();
+    e->pin_tasks.release(); e->pin_fwd.release(); e->pin_fin.release(); e->pin_misc.release();
+    if (e->ev[0]) for (int i = 0; i < 5; ++i) cudaEventDestroy(e->ev[i]);
     delete e;
 }
 
@@ -122,6 +158,25 @@ extern "C" int mpn_engine_set_stream(mpn_engine* e, void* s)
 {
     if (!e) return MPN_E_ARG;
     e->stream = s ? reinterpret_cast<cudaStream_t>(s) : e->own_stream;
+    return 0;
+}
+
+extern "C" int mpn_engine_set_profile(mpn_engine* e, int on)
+{
+    if (!e) return MPN_E_ARG;
+    CK(cudaSetDevice(e->device));
+    if (on && !e->ev[0]) for (int i = 0; i < 5; ++i) CK(cudaEventCreate(&e->ev[i]));
+    e->profile = on != 0;
+    e->ev_valid = 0;
+    return 0;
+}
+
+/* milliseconds of the last mpn_batch_run by phase: forward score kernels, score2/mode epilogue, reverse score kernels, traceback */
+extern "C" int mpn_engine_phase_ms(mpn_engine* e, float* ms4)
+{
+    if (!e || !ms4 || !e->profile || e->ev_valid < 5) return MPN_E_ARG;
+    CK(cudaEventSynchronize(e->ev[4]));
+    for (int i = 0; i < 4; ++i) CK(cudaEventElapsedTime(&ms4[i], e->ev[i], e->ev[i + 1]));
     return 0;
 }
 
@@ -139,9 +194,9 @@ extern "C" void mpn_batch_free(mpn_batch* b)
 {
     if (!b) return;
     cudaSetDevice(b->e->device);
-    DevBuf* bufs[] = {&b->seq, &b->rd_off, &b->rf_off, &b->rd_len, &b->rf_len, &b->mask, &b->tasks_fwd, &b->tasks_rev, &b->ends_fwd, &b->ends_rev,
+    DevBuf* bufs[] = {&b->seq, &b->mask, &b->tasks_fwd, &b->tasks_rev, &b->ends_fwd, &b->ends_rev,
                       &b->colrec, &b->fwdres, &b->finalres, &b->counters, &b->dmat, &b->scratch, &b->cig, &b->wide_boundary};
-    for (DevBuf* d : bufs) d->release();
+    for (DevBuf* d : bufs) b->e->pool.give(*d);
     delete b;
 }
 
@@ -177,24 +232,22 @@ extern "C" mpn_batch* mpn_batch_upload(mpn_engine* e, const mpn_params* p, const
     b->fin.flag = p->flag & 0xff; b->fin.filters = p->filters & 0xffff;
 
     // ---- per-pair lengths, binning
-    std::vector<int32_t> rd_len(npairs), rf_len(npairs);
-    std::vector<int32_t> bin(npairs);
+    std::vector<int32_t>& bin = e->h_bin;
+    bin.resize(npairs);
     std::vector<int64_t> bin_count(N_STRIPS + 1, 0);
-    std::vector<int64_t> cm_off(npairs);
     int64_t cm_total = 0, cells = 0;
-    int max_rd = 0, max_rf = 0;
+    int max_rd = 0, max_rf = 0, min_rf = 0x7fffffff;
     const bool packed_ok = n <= 8;
+    const int64_t maxpos = std::max(maxv, 0);
     for (int64_t i = 0; i < npairs; ++i) {
         const int64_t rl = read_off[i + 1] - read_off[i], fl = ref_off[i + 1] - ref_off[i];
         if (rl < 0 || fl < 0 || rl > 0x3fffffff || fl > 0x3fffffff) { delete b; return nullptr; }
-        rd_len[i] = (int32_t)rl; rf_len[i] = (int32_t)fl;
         cells += rl * fl;
-        max_rd = std::max<int>(max_rd, (int)rl); max_rf = std::max<int>(max_rf, (int)fl);
-        cm_off[i] = cm_total; cm_total += fl;
+        max_rd = std::max<int>(max_rd, (int)rl); max_rf = std::max<int>(max_rf, (int)fl); min_rf = std::min<int>(min_rf, (int)fl);
+        cm_total += fl;
         int c = WIDE_BIN;
         // the packed kernel is exact as long as no H can reach the int16 clamp of ssw.c:425 (and the add cannot wrap)
-        const int64_t bound = (std::min(rl, fl) + 1) * (int64_t)std::max(maxv, 0);
-        if (packed_ok && bound <= 32767) {
+        if (packed_ok && (std::min(rl, fl) + 1) * maxpos <= 32767) {
             for (int k = 0; k < N_STRIPS; ++k) if (rl <= g_strips[k].cap) { c = k; break; }
         }
         bin[i] = c; bin_count[c]++;
@@ -202,67 +255,68 @@ extern "C" mpn_batch* mpn_batch_upload(mpn_engine* e, const mpn_params* p, const
     b->total_cells = cells; b->max_rd = max_rd; b->colrec_words = cm_total;
     b->n_wide_pre = bin_count[WIDE_BIN];
 
-    // ---- task lists: per bin, longest targets first (counting sort on target length) so that the groups of a warp run in step
+    // ---- task lists in pinned staging: per bin, longest targets first (counting sort on target length) so that the groups of
+    //      a warp run in step and the tail of a launch is made of short tasks
     std::vector<int64_t> bin_first(N_STRIPS + 2, 0);
     for (int c = 0; c <= N_STRIPS; ++c) bin_first[c + 1] = bin_first[c] + bin_count[c];
-    b->h_tasks.resize(npairs);
+    e->pin_tasks.reserve(sizeof(SwTask) * (size_t)(npairs + 1));
+    SwTask* h_tasks = e->pin_tasks.as<SwTask>();
     {
-        std::vector<int64_t> order(npairs);
-        bool uniform_rf = true;
-        for (int64_t i = 1; i < npairs && uniform_rf; ++i) uniform_rf = rf_len[i] == rf_len[0];
+        std::vector<int64_t>& order = e->h_order;
+        order.resize(npairs);
         std::vector<int64_t> cursor(bin_first.begin(), bin_first.end() - 1);
-        if (uniform_rf || max_rf > (1 << 22)) {
+        if (npairs == 0 || min_rf == max_rf || max_rf > (1 << 22)) {
             for (int64_t i = 0; i < npairs; ++i) order[cursor[bin[i]]++] = i;
         } else {
-            std::vector<int64_t> cnt((size_t)max_rf + 2, 0), idx(npairs);
-            for (int64_t i = 0; i < npairs; ++i) cnt[max_rf - rf_len[i] + 1]++;
+            std::vector<int64_t>& cnt = e->h_cnt; std::vector<int64_t>& idx = e->h_idx;
+            cnt.assign((size_t)max_rf + 2, 0); idx.resize(npairs);
+            for (int64_t i = 0; i < npairs; ++i) cnt[max_rf - (ref_off[i + 1] - ref_off[i]) + 1]++;
             for (int v = 0; v <= max_rf; ++v) cnt[v + 1] += cnt[v];
-            for (int64_t i = 0; i < npairs; ++i) idx[cnt[max_rf - rf_len[i]]++] = i;        // descending target length, stable
+            for (int64_t i = 0; i < npairs; ++i) idx[cnt[max_rf - (ref_off[i + 1] - ref_off[i])]++] = i;     // descending target length, stable
             for (int64_t k = 0; k < npairs; ++k) { const int64_t i = idx[k]; order[cursor[bin[i]]++] = i; }
         }
         const int64_t reads_total = npairs ? read_off[npairs] - read_off[0] : 0;
+        int64_t cm = 0;
         for (int64_t k = 0; k < npairs; ++k) {
             const int64_t i = order[k];
-            SwTask& t = b->h_tasks[k];
+            SwTask& t = h_tasks[k];
             t.rd_base = read_off[i] - read_off[0];
             t.rf_base = reads_total + (ref_off[i] - ref_off[0]);
-            t.cm_off = cm_off[i];
-            t.rd_len = rd_len[i]; t.rf_len = rf_len[i]; t.dir = 1; t.out = (int32_t)i;
+            t.rd_len = (int32_t)(read_off[i + 1] - read_off[i]); t.rf_len = (int32_t)(ref_off[i + 1] - ref_off[i]);
+            t.cm_off = cm; cm += t.rf_len;            // column records are laid out in task order
+            t.dir = 1; t.out = (int32_t)i; t.stop = 0; t.pad_ = 0;
         }
     }
     for (int c = 0; c <= N_STRIPS; ++c) if (bin_count[c] > 0) b->bins.push_back(BinLaunch{c, bin_first[c], bin_count[c]});
 
-    // ---- device buffers + uploads
+    // ---- device buffers + uploads (straight from the caller's buffers: pinned caller memory gives full PCIe rate)
+    DevPool& pool = e->pool;
     const size_t reads_bytes = npairs ? (size_t)(read_off[npairs] - read_off[0]) : 0;
     const size_t refs_bytes = npairs ? (size_t)(ref_off[npairs] - ref_off[0]) : 0;
     b->seq_reads_bytes = reads_bytes; b->seq_bytes = reads_bytes + refs_bytes;
-    b->seq.reserve(b->seq_bytes + 16);
-    std::vector<int64_t> rd_start(npairs), rf_start(npairs);
-    for (int64_t i = 0; i < npairs; ++i) { rd_start[i] = read_off[i] - read_off[0]; rf_start[i] = (int64_t)reads_bytes + (ref_off[i] - ref_off[0]); }
-    b->rd_off.reserve(sizeof(int64_t) * (npairs + 1)); b->rf_off.reserve(sizeof(int64_t) * (npairs + 1));
-    b->rd_len.reserve(sizeof(int32_t) * (npairs + 1)); b->rf_len.reserve(sizeof(int32_t) * (npairs + 1)); b->mask.reserve(sizeof(int32_t) * (npairs + 1));
-    b->tasks_fwd.reserve(sizeof(SwTask) * (npairs + 1)); b->tasks_rev.reserve(sizeof(SwTask) * (npairs + 1));
-    b->ends_fwd.reserve(sizeof(SwEnds) * (npairs + 1)); b->ends_rev.reserve(sizeof(SwEnds) * (npairs + 1));
-    b->colrec.reserve(sizeof(uint32_t) * (size_t)(cm_total + 1));
-    b->fwdres.reserve(sizeof(FwdResult) * (npairs + 1)); b->finalres.reserve(sizeof(FinalResult) * (npairs + 1));
-    b->counters.reserve(256 * sizeof(unsigned long long));
-    b->dmat.reserve((size_t)n * n + 16);
+    pool.take(b->seq, b->seq_bytes + 16);
+    pool.take(b->mask, sizeof(int32_t) * (size_t)(npairs + 1));
+    pool.take(b->tasks_fwd, sizeof(SwTask) * (size_t)(npairs + 1)); pool.take(b->tasks_rev, sizeof(SwTask) * (size_t)(npairs + 1));
+    pool.take(b->ends_fwd, sizeof(SwEnds) * (size_t)(npairs + 1)); pool.take(b->ends_rev, sizeof(SwEnds) * (size_t)(npairs + 1));
+    pool.take(b->colrec, sizeof(uint32_t) * (size_t)(cm_total + 1));
+    pool.take(b->fwdres, sizeof(FwdResult) * (size_t)(npairs + 1)); pool.take(b->finalres, sizeof(FinalResult) * (size_t)(npairs + 1));
+    pool.take(b->counters, 256 * sizeof(unsigned long long));
+    pool.take(b->dmat, (size_t)n * n + 16);
     if (npairs) {
         CK(cudaMemcpyAsync(b->seq.p, reads + read_off[0], reads_bytes, cudaMemcpyHostToDevice, st));
         CK(cudaMemcpyAsync(b->seq.as<int8_t>() + reads_bytes, refs + ref_off[0], refs_bytes, cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(b->rd_off.p, rd_start.data(), sizeof(int64_t) * npairs, cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(b->rf_off.p, rf_start.data(), sizeof(int64_t) * npairs, cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(b->rd_len.p, rd_len.data(), sizeof(int32_t) * npairs, cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(b->rf_len.p, rf_len.data(), sizeof(int32_t) * npairs, cudaMemcpyHostToDevice, st));
         CK(cudaMemcpyAsync(b->mask.p, masklen, sizeof(int32_t) * npairs, cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(b->tasks_fwd.p, b->h_tasks.data(), sizeof(SwTask) * npairs, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(b->tasks_fwd.p, h_tasks, sizeof(SwTask) * npairs, cudaMemcpyHostToDevice, st));
     }
-    CK(cudaMemcpyAsync(b->dmat.p, b->mat.data(), (size_t)n * n, cudaMemcpyHostToDevice, st));
+    e->pin_misc.reserve(4096);
+    memcpy(e->pin_misc.p, b->mat.data(), (size_t)n * n);
+    CK(cudaMemcpyAsync(b->dmat.p, e->pin_misc.p, (size_t)n * n, cudaMemcpyHostToDevice, st));
+    b->h2d_bytes = reads_bytes + refs_bytes + (sizeof(int32_t) + sizeof(SwTask)) * (size_t)npairs + (size_t)n * n;
 
     // ---- boundary rows of the 32-bit kernel (one slot per resident warp)
     b->wide_blocks = e->sm_count * 3;
     b->wide_stride = ((long long)max_rf + 63) & ~63ll;
-    b->wide_boundary.reserve(sizeof(int) * (size_t)b->wide_blocks * (WIDE_BLOCK / 32) * 2 * (size_t)b->wide_stride + 256);
+    pool.take(b->wide_boundary, sizeof(int) * (size_t)b->wide_blocks * (WIDE_BLOCK / 32) * 2 * (size_t)b->wide_stride + 256);
 
     // ---- traceback arenas.  Direction bytes: (2*band+1) per read row; the first attempt has band |dlen|+1 and most pairs
     // stop there.  Budget 16 band cells per read base (+ slack); pairs that do not fit are reported (status 5) and re-run by fetch.
@@ -271,10 +325,11 @@ extern "C" mpn_batch* mpn_batch_upload(mpn_engine* e, const mpn_params* p, const
         int64_t read_bases = (int64_t)reads_bytes;
         b->scratch_bytes = (unsigned long long)read_bases * 24ull + (unsigned long long)npairs * 512ull + (64ull << 20);
         b->cig_cap = (unsigned long long)npairs * 24ull + (unsigned long long)read_bases / 4ull + 4096ull;
-        b->scratch.reserve(b->scratch_bytes);
-        b->cig.reserve(b->cig_cap * sizeof(uint32_t));
+        pool.take(b->scratch, b->scratch_bytes);
+        pool.take(b->cig, b->cig_cap * sizeof(uint32_t));
     }
-    CK(cudaStreamSynchronize(st));     // the std::vectors above go out of scope
+    // the task list sits in engine-owned pinned staging that the next upload overwrites: wait for its copy
+    CK(cudaStreamSynchronize(st));
     return b;
 }
 
@@ -311,8 +366,9 @@ extern "C" int mpn_batch_run(mpn_batch* b)
     const int64_t n = b->npairs;
     if (n == 0) { b->ran = true; return 0; }
     CK(cudaMemsetAsync(b->counters.p, 0, 256 * sizeof(unsigned long long), st));
-    PairArrays pa{b->rd_off.as<int64_t>(), b->rf_off.as<int64_t>(), b->rd_len.as<int32_t>(), b->rf_len.as<int32_t>(), b->mask.as<int32_t>()};
+    PairArrays pa{b->mask.as<int32_t>()};
 
+    if (e->profile) { CK(cudaEventRecord(e->ev[0], st)); e->ev_valid = 1; }
     // forward score pass -> ends + column records
     launch_strips(b, b->tasks_fwd.as<SwTask>(), true, b->ends_fwd.as<SwEnds>(), 0);
     // pairs the packed kernel refused (read code >= 4) are re-run in the 32-bit kernel before anything reads their ends
@@ -321,6 +377,7 @@ extern "C" int mpn_batch_run(mpn_batch* b)
                        b->wide_boundary.as<int>(), b->wide_stride, b->wide_blocks, 1, st);
     CK(cudaGetLastError());
     e->launches++;
+    if (e->profile) { CK(cudaEventRecord(e->ev[1], st)); e->ev_valid = 2; }
     // second best + mode + reverse tasks
     {
         const int warps_per_block = 4;
@@ -330,6 +387,7 @@ extern "C" int mpn_batch_run(mpn_batch* b)
         CK(cudaGetLastError());
         e->launches++;
     }
+    if (e->profile) { CK(cudaEventRecord(e->ev[2], st)); e->ev_valid = 3; }
     const bool any_rev = !(b->fin.flag == 0);
     if (any_rev) {
         launch_strips(b, b->tasks_rev.as<SwTask>(), false, b->ends_rev.as<SwEnds>(), 32);
@@ -338,13 +396,18 @@ extern "C" int mpn_batch_run(mpn_batch* b)
                            b->wide_boundary.as<int>(), b->wide_stride, b->wide_blocks, 1, st);
         CK(cudaGetLastError());
         e->launches++;
+        if (e->profile) { CK(cudaEventRecord(e->ev[3], st)); e->ev_valid = 4; }
         TraceParams tp{b->fin.flag, b->fin.filters, b->p.filterd, b->fin.gapO, b->fin.gapE, b->p.n, b->dmat.as<int8_t>()};
         Arena ar{b->scratch.as<uint8_t>(), b->scratch_bytes, b->counters.as<unsigned long long>() + 64};
-        const unsigned blocks = (unsigned)((n + 63) / 64);
-        sw_trace_kernel<<<blocks, 64, 0, st>>>(b->tasks_fwd.as<SwTask>(), (int)n, pa, b->seq.as<int8_t>(), b->fwdres.as<FwdResult>(), b->ends_rev.as<SwEnds>(), tp, ar,
+        const unsigned blocks = (unsigned)((n + TRACE_BLOCK - 1) / TRACE_BLOCK);
+        sw_trace_kernel<<<blocks, TRACE_BLOCK, TRACE_SMEM_BYTES, st>>>(b->tasks_fwd.as<SwTask>(), (int)n, b->seq.as<int8_t>(), b->fwdres.as<FwdResult>(), b->ends_rev.as<SwEnds>(), tp, ar,
                                                b->cig.as<uint32_t>(), b->cig_cap, b->counters.as<unsigned long long>() + 65, b->finalres.as<FinalResult>());
         CK(cudaGetLastError());
         e->launches++;
+    }
+    if (e->profile) {
+        if (!any_rev) CK(cudaEventRecord(e->ev[3], st));
+        CK(cudaEventRecord(e->ev[4], st)); e->ev_valid = 5;
     }
     b->ran = true;
     e->pairs += n; e->cells += b->total_cells;
@@ -361,13 +424,17 @@ extern "C" int mpn_batch_fetch(mpn_batch* b, mpn_result* out, uint32_t* cigar, i
     const int64_t n = b->npairs;
     if (n == 0) return 0;
     const bool any_rev = !(b->fin.flag == 0);
-    b->h_fwd.resize(n);
-    CK(cudaMemcpyAsync(b->h_fwd.data(), b->fwdres.p, sizeof(FwdResult) * n, cudaMemcpyDeviceToHost, st));
-    unsigned long long used[2] = {0, 0};
+    e->pin_fwd.reserve(sizeof(FwdResult) * (size_t)n);
+    CK(cudaMemcpyAsync(e->pin_fwd.p, b->fwdres.p, sizeof(FwdResult) * n, cudaMemcpyDeviceToHost, st));
+    b->d2h_bytes = sizeof(FwdResult) * (size_t)n;
+    e->pin_misc.reserve(4096);
+    unsigned long long* used = e->pin_misc.as<unsigned long long>() + 256;
+    used[0] = used[1] = 0;
     if (any_rev) {
-        b->h_fin.resize(n);
-        CK(cudaMemcpyAsync(b->h_fin.data(), b->finalres.p, sizeof(FinalResult) * n, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(used, b->counters.as<unsigned long long>() + 64, sizeof used, cudaMemcpyDeviceToHost, st));
+        e->pin_fin.reserve(sizeof(FinalResult) * (size_t)n);
+        CK(cudaMemcpyAsync(e->pin_fin.p, b->finalres.p, sizeof(FinalResult) * n, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(used, b->counters.as<unsigned long long>() + 64, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+        b->d2h_bytes += sizeof(FinalResult) * (size_t)n + 16;
     }
     CK(cudaStreamSynchronize(st));
     int rc = 0;
@@ -375,17 +442,19 @@ extern "C" int mpn_batch_fetch(mpn_batch* b, mpn_result* out, uint32_t* cigar, i
         const unsigned long long words = std::min<unsigned long long>(used[1], b->cig_cap);
         if ((int64_t)words > cigar_cap || (!cigar && words)) return MPN_E_CIGAR_SPACE;
         if (words) CK(cudaMemcpyAsync(cigar, b->cig.p, words * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
+        b->d2h_bytes += words * sizeof(uint32_t);
     }
+    const FwdResult* h_fwd = e->pin_fwd.as<FwdResult>();
+    const FinalResult* h_fin = e->pin_fin.as<FinalResult>();
     for (int64_t i = 0; i < n; ++i) {
-        const FwdResult& f = b->h_fwd[i];
+        const FwdResult& f = h_fwd[i];
         mpn_result& r = out[i];
         r.score1 = (uint16_t)f.score1; r.score2 = (uint16_t)f.score2;
         r.ref_end1 = f.ref_end1; r.read_end1 = f.read_end1; r.ref_end2 = f.ref_end2;
         r.ref_begin1 = -1; r.read_begin1 = -1; r.cigar_len = 0; r.cigar_off = 0;
         r.status = f.status ? MPN_ST_NULL : MPN_ST_OK;
         if (any_rev && f.status == 0) {
-            const FinalResult& g = b->h_fin[i];
+            const FinalResult& g = h_fin[i];
             r.ref_begin1 = g.ref_begin1; r.read_begin1 = g.read_begin1;
             r.cigar_len = g.cigar_len; r.cigar_off = g.cigar_off;
             if (g.status == 3) r.status = MPN_ST_NULL;
@@ -395,7 +464,16 @@ extern "C" int mpn_batch_fetch(mpn_batch* b, mpn_result* out, uint32_t* cigar, i
             }
         }
     }
+    CK(cudaStreamSynchronize(st));      // CIGAR arena copy
     return rc;
+}
+
+extern "C" int mpn_batch_io_bytes(const mpn_batch* b, int64_t* h2d, int64_t* d2h)
+{
+    if (!b) return MPN_E_ARG;
+    if (h2d) *h2d = (int64_t)b->h2d_bytes;
+    if (d2h) *d2h = (int64_t)b->d2h_bytes;
+    return 0;
 }
 
 extern "C" int mpn_align_batch(mpn_engine* e, const mpn_params* p, const int8_t* reads, const int64_t* read_off, const int8_t* refs,

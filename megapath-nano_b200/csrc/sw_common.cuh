@@ -15,6 +15,8 @@ struct SwTask {
     int32_t rf_len;
     int32_t dir;       // +1 forward, -1 reverse
     int32_t out;       // slot in the SwEnds array
+    int32_t stop;      // > 0: the pass may end once a column maximum equals this score (ssw.c:281 / :483 `terminate`)
+    int32_t pad_;
 };
 
 // Result of a score pass.  col/row are in processing order (for a reverse pass: distance from the end).

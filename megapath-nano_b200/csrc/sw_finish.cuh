@@ -21,11 +21,7 @@
 
 namespace mpn {
 
-struct PairArrays {               // device pointers, one entry per pair of the batch
-    const int64_t* rd_off;        // start of the read in the sequence arena
-    const int64_t* rf_off;        // start of the target in the sequence arena
-    const int32_t* rd_len;
-    const int32_t* rf_len;
+struct PairArrays {               // device pointers, one entry per pair of the batch (lengths / offsets travel in the SwTask)
     const int32_t* masklen;
 };
 
@@ -64,7 +60,7 @@ sw_finish_kernel(const SwTask* __restrict__ fwd_tasks, int ntasks, const SwEnds*
     const SwTask tk = fwd_tasks[k];
     const int i = tk.out;
     const SwEnds e = ends[i];
-    const int rd_len = pa.rd_len[i], rf_len = pa.rf_len[i], masklen = pa.masklen[i];
+    const int rd_len = tk.rd_len, rf_len = tk.rf_len, masklen = pa.masklen[i];
 
     FwdResult r;
     r.status = 0;
@@ -146,12 +142,12 @@ sw_finish_kernel(const SwTask* __restrict__ fwd_tasks, int ntasks, const SwEnds*
     if (lane == 0) {
         res[i] = r;
         SwTask rt;
-        rt.out = i; rt.cm_off = -1; rt.dir = -1;
+        rt.out = i; rt.cm_off = -1; rt.dir = -1; rt.stop = r.score1; rt.pad_ = 0;
         if (r.want_rev && r.score1 > 0) {
             rt.rd_len = r.read_end1 + 1; rt.rf_len = r.ref_end1 + 1;
-            rt.rd_base = pa.rd_off[i] + r.read_end1; rt.rf_base = pa.rf_off[i] + r.ref_end1;
+            rt.rd_base = tk.rd_base + r.read_end1; rt.rf_base = tk.rf_base + r.ref_end1;
         } else {
-            rt.rd_len = 0; rt.rf_len = 0; rt.rd_base = pa.rd_off[i]; rt.rf_base = pa.rf_off[i];
+            rt.rd_len = 0; rt.rf_len = 0; rt.rd_base = tk.rd_base; rt.rf_base = tk.rf_base;
         }
         rev_tasks[k] = rt;
     }

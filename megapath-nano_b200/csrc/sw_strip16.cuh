@@ -58,6 +58,7 @@ sw_strip16_kernel(const SwTask* __restrict__ tasks, int ntasks, int* __restrict_
     uint32_t tchunk = 0, tnext = 0;               // matrix rows of target bases [kG + t] of the current / next chunk
     int s = 0, nsteps = 0, dead = 0;
     int rf_len = 0, tdir = 1, tout = 0, wide = 0;
+    uint32_t stop2 = 0;                           // reverse passes: score at which the pass may end, in both halves (0: never)
     int64_t rf_base = 0, cm_off = -1;
     bool active = true;                           // group still has (or may fetch) a task
 
@@ -66,6 +67,13 @@ sw_strip16_kernel(const SwTask* __restrict__ tasks, int ntasks, int* __restrict_
 
     for (;;) {
         // ------------------------------------------------------------------ task boundary (every G steps) -------------
+        {   // early end of a reverse pass (ssw.c:281 / :483): once some stage has seen the terminating score in column c, every
+            // stage has passed column c after at most 2G-1 further steps; the usual first-column / first-row selection then applies.
+            const uint32_t x = best ^ stop2;
+            const bool hit = stop2 != 0u && ((x & 0xffffu) == 0u || (x >> 16) == 0u);
+            const unsigned hits = __ballot_sync(0xffffffffu, hit) & gmask;
+            if (hits != 0u) nsteps = min(nsteps, s + 2 * G);
+        }
         if (active && s >= nsteps) {
             if (nsteps > 0) {
                 // ---- finalize: reduce (score, first column, stage) over the 2G stages of the group
@@ -117,7 +125,7 @@ sw_strip16_kernel(const SwTask* __restrict__ tasks, int ntasks, int* __restrict_
             ti = __shfl_sync(gmask, ti, lane - t);
             if (ti >= ntasks) {
                 active = false;
-                rf_len = 0; nsteps = 0; cm_off = -1;
+                rf_len = 0; nsteps = 0; cm_off = -1; stop2 = 0;
 #pragma unroll
                 for (int j = 0; j < KR; ++j) { H[j] = 0; E[j] = 0; sel[j] = 0x8888u | 0x4400u; }
                 Ftop = Hdtop = cmin = a = b = best = 0; tnext = 0; tchunk = 0;
@@ -125,6 +133,7 @@ sw_strip16_kernel(const SwTask* __restrict__ tasks, int ntasks, int* __restrict_
                 const SwTask tk = tasks[ti];
                 const int rd_len = tk.rd_len;
                 rf_len = tk.rf_len; tdir = tk.dir; tout = tk.out; rf_base = tk.rf_base; cm_off = tk.cm_off;
+                stop2 = tk.stop > 0 ? ((uint32_t)tk.stop | ((uint32_t)tk.stop << 16)) : 0u;
                 dead = CAP - rd_len;
                 wide = 0;
                 // selectors: low half = row (2t)*KR + j, high half = row (2t+1)*KR + j, both minus the dead rows on top

@@ -37,14 +37,21 @@ struct Arena {
 
 __device__ __forceinline__ int band_x(int i, int w) { int x = i - w; return x > 0 ? x : 0; }
 
-__global__ void __launch_bounds__(64)
-sw_trace_kernel(const SwTask* __restrict__ order, int ntasks, PairArrays pa, const int8_t* __restrict__ seq, const FwdResult* __restrict__ fr,
+constexpr int TRACE_BLOCK = 64;
+constexpr int TRACE_SMEM_BW = 16;                         // bands up to this half-width keep their row buffers in shared memory
+constexpr int TRACE_SMEM_W = 2 * TRACE_SMEM_BW + 4;       // entries per row buffer
+constexpr size_t TRACE_SMEM_BYTES = 3ull * TRACE_SMEM_W * TRACE_BLOCK * sizeof(int);
+
+__global__ void __launch_bounds__(TRACE_BLOCK)
+sw_trace_kernel(const SwTask* __restrict__ order, int ntasks, const int8_t* __restrict__ seq, const FwdResult* __restrict__ fr,
                 const SwEnds* __restrict__ rev, TraceParams tp, Arena scratch, uint32_t* __restrict__ cig, unsigned long long cig_cap,
                 unsigned long long* __restrict__ cig_used, FinalResult* __restrict__ out)
 {
+    extern __shared__ int tsm[];                          // [3][TRACE_SMEM_W][TRACE_BLOCK], element (a, idx) of thread t at ((a*W + idx)*BLOCK + t)
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= ntasks) return;
-    const int i = order[k].out;
+    const SwTask tk = order[k];
+    const int i = tk.out;
     const FwdResult f = fr[i];
     FinalResult r;
     r.ref_begin1 = -1; r.read_begin1 = -1; r.cigar_len = 0; r.status = 0; r.cigar_off = 0;
@@ -74,54 +81,57 @@ sw_trace_kernel(const SwTask* __restrict__ order, int ntasks, PairArrays pa, con
         out[i] = r;
         return;
     }
-    const int8_t* ref = seq + pa.rf_off[i] + r.ref_begin1;
-    const int8_t* read = seq + pa.rd_off[i] + r.read_begin1;
+    const int8_t* ref = seq + tk.rf_base + r.ref_begin1;
+    const int8_t* read = seq + tk.rd_base + r.read_begin1;
     const int n = tp.n, gapO = tp.gapO, gapE = tp.gapE, score = f.score1;
     int bw = abs(sub_ref - sub_read) + 1;
     int width = 0, width_d = 0, maxv = 0;
     uint8_t* dir = nullptr;
     do {
         width = bw * 2 + 3; width_d = bw * 2 + 1;
+        const bool in_smem = bw <= TRACE_SMEM_BW;
         const unsigned long long need_dir = ((unsigned long long)width_d * (unsigned long long)sub_read + 15ull) & ~15ull;
-        const unsigned long long need = need_dir + 3ull * (unsigned long long)(width + 1) * 4ull;
+        const unsigned long long need = need_dir + (in_smem ? 0ull : 3ull * (unsigned long long)(width + 1) * 4ull);
         const unsigned long long o = atomicAdd(scratch.used, (need + 15ull) & ~15ull);
         if (o + need > scratch.bytes) { r.status = 5; out[i] = r; return; }
         dir = scratch.base + o;
-        int* hb = reinterpret_cast<int*>(dir + need_dir);
-        int* eb = hb + (width + 1);
-        int* hc = eb + (width + 1);
-        for (int j = 0; j <= width; ++j) { hb[j] = 0; eb[j] = 0; hc[j] = 0; }
+        // previous-row H, previous-row E, current-row H in band coordinates: shared memory (stride = block) for narrow bands
+        int* hb = in_smem ? tsm + threadIdx.x : reinterpret_cast<int*>(dir + need_dir);
+        const int st = in_smem ? TRACE_BLOCK : 1;
+        int* eb = hb + (in_smem ? TRACE_SMEM_W * TRACE_BLOCK : (width + 1));
+        int* hc = eb + (in_smem ? TRACE_SMEM_W * TRACE_BLOCK : (width + 1));
+        for (int j = 0; j <= width; ++j) { hb[j * st] = 0; eb[j * st] = 0; hc[j * st] = 0; }
         for (int ii = 0; ii < sub_read; ++ii) {
             const int beg = max(0, ii - bw), end = min(sub_ref - 1, ii + bw);
             const int edge = min(end + 1, width - 1);
             const int xi = band_x(ii, bw), xp = band_x(ii - 1, bw);
             int fv = 0, u = 0;
             uint8_t* line = dir + (size_t)width_d * (size_t)ii;
-            hb[0] = 0; eb[0] = 0; hb[edge] = 0; eb[edge] = 0; hc[0] = 0;
+            hb[0] = 0; eb[0] = 0; hb[edge * st] = 0; eb[edge * st] = 0; hc[0] = 0;
             const int8_t* mrow = tp.mat + (int)read[ii];
             for (int j = beg; j <= end; ++j) {
                 const int e_idx = j - xp + 1, d_idx = j - xp, b_idx = j - xi;
                 u = j - xi + 1;
-                int open = ii == 0 ? -gapO : hb[e_idx] - gapO;
-                int ext = ii == 0 ? -gapE : eb[e_idx] - gapE;
+                int open = ii == 0 ? -gapO : hb[e_idx * st] - gapO;
+                int ext = ii == 0 ? -gapE : eb[e_idx * st] - gapE;
                 const int ev = open > ext ? open : ext;
                 const int de3 = open > ext ? 1 : 0;
-                open = hc[b_idx] - gapO; ext = fv - gapE;
+                open = hc[b_idx * st] - gapO; ext = fv - gapE;
                 fv = open > ext ? open : ext;
                 const int df5 = open > ext ? 1 : 0;
                 const int e1 = ev > 0 ? ev : 0, f1 = fv > 0 ? fv : 0;
                 const int t1 = e1 > f1 ? e1 : f1;
-                const int t2 = hb[d_idx] + (int)mrow[(int)ref[j] * n];
+                const int t2 = hb[d_idx * st] + (int)mrow[(int)ref[j] * n];
                 const int hv = t1 > t2 ? t1 : t2;
                 int dh;
                 if (t1 <= t2) dh = 1; else dh = e1 > f1 ? (de3 ? 3 : 2) : (df5 ? 5 : 4);
                 // previous-row E must be read before it is overwritten: e_idx >= u always (xp <= xi), so writing eb[u] now is safe
-                eb[u] = ev;
-                hc[u] = hv;
+                eb[u * st] = ev;
+                hc[u * st] = hv;
                 if (hv > maxv) maxv = hv;
                 line[j - xi] = (uint8_t)(de3 | (df5 << 1) | (dh << 2));
             }
-            for (int j = 1; j <= u; ++j) hb[j] = hc[j];
+            for (int j = 1; j <= u; ++j) hb[j * st] = hc[j * st];
         }
         bw *= 2;
     } while (maxv < score);
