@@ -7,6 +7,7 @@
 #include "sw_wide32.cuh"
 #include "sw_finish.cuh"
 #include "sw_trace.cuh"
+#include "sw_trace_narrow.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -399,9 +400,17 @@ extern "C" int mpn_batch_run(mpn_batch* b)
         if (e->profile) { CK(cudaEventRecord(e->ev[3], st)); e->ev_valid = 4; }
         TraceParams tp{b->fin.flag, b->fin.filters, b->p.filterd, b->fin.gapO, b->fin.gapE, b->p.n, b->dmat.as<int8_t>()};
         Arena ar{b->scratch.as<uint8_t>(), b->scratch_bytes, b->counters.as<unsigned long long>() + 64};
+        {
+            const unsigned blocks = (unsigned)((n + NARROW_BLOCK - 1) / NARROW_BLOCK);
+            sw_trace_narrow_kernel<<<blocks, NARROW_BLOCK, narrow_smem_bytes(b->p.n), st>>>(b->tasks_fwd.as<SwTask>(), (int)n, b->seq.as<int8_t>(), b->fwdres.as<FwdResult>(),
+                b->ends_rev.as<SwEnds>(), tp, ar, b->cig.as<uint32_t>(), b->cig_cap, b->counters.as<unsigned long long>() + 65, b->finalres.as<FinalResult>());
+            CK(cudaGetLastError());
+            e->launches++;
+        }
+        // pairs whose band outgrew the narrow kernel (status 7) are redone by the generic one
         const unsigned blocks = (unsigned)((n + TRACE_BLOCK - 1) / TRACE_BLOCK);
-        sw_trace_kernel<<<blocks, TRACE_BLOCK, TRACE_SMEM_BYTES, st>>>(b->tasks_fwd.as<SwTask>(), (int)n, b->seq.as<int8_t>(), b->fwdres.as<FwdResult>(), b->ends_rev.as<SwEnds>(), tp, ar,
-                                               b->cig.as<uint32_t>(), b->cig_cap, b->counters.as<unsigned long long>() + 65, b->finalres.as<FinalResult>());
+        sw_trace_wide_kernel<<<blocks, TRACE_BLOCK, trace_smem_bytes(b->p.n), st>>>(b->tasks_fwd.as<SwTask>(), (int)n, b->seq.as<int8_t>(), b->fwdres.as<FwdResult>(), b->ends_rev.as<SwEnds>(), tp, ar,
+                                               b->cig.as<uint32_t>(), b->cig_cap, b->counters.as<unsigned long long>() + 65, b->finalres.as<FinalResult>(), 1);
         CK(cudaGetLastError());
         e->launches++;
     }

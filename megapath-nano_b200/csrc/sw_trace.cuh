@@ -38,104 +38,145 @@ struct Arena {
 __device__ __forceinline__ int band_x(int i, int w) { int x = i - w; return x > 0 ? x : 0; }
 
 constexpr int TRACE_BLOCK = 64;
-constexpr int TRACE_SMEM_BW = 16;                         // bands up to this half-width keep their row buffers in shared memory
+constexpr int TRACE_SMEM_BW = 6;                          // bands up to this half-width keep their row buffers in shared memory
 constexpr int TRACE_SMEM_W = 2 * TRACE_SMEM_BW + 4;       // entries per row buffer
 constexpr size_t TRACE_SMEM_BYTES = 3ull * TRACE_SMEM_W * TRACE_BLOCK * sizeof(int);
+inline size_t trace_smem_bytes(int n) { return TRACE_SMEM_BYTES + (((size_t)n * n + 15) & ~(size_t)15); }
 
+// The banded DP of every lane is driven by ONE warp-wide loop that advances each lane by one cell per iteration (row changes and
+// band restarts are predicated inside it), so lanes with different read lengths / band widths stay converged instead of
+// serialising their nested row x column loops.
 __global__ void __launch_bounds__(TRACE_BLOCK)
-sw_trace_kernel(const SwTask* __restrict__ order, int ntasks, const int8_t* __restrict__ seq, const FwdResult* __restrict__ fr,
+sw_trace_wide_kernel(const SwTask* __restrict__ order, int ntasks, const int8_t* __restrict__ seq, const FwdResult* __restrict__ fr,
                 const SwEnds* __restrict__ rev, TraceParams tp, Arena scratch, uint32_t* __restrict__ cig, unsigned long long cig_cap,
-                unsigned long long* __restrict__ cig_used, FinalResult* __restrict__ out)
+                unsigned long long* __restrict__ cig_used, FinalResult* __restrict__ out, int only_flagged)
 {
-    extern __shared__ int tsm[];                          // [3][TRACE_SMEM_W][TRACE_BLOCK], element (a, idx) of thread t at ((a*W + idx)*BLOCK + t)
+    extern __shared__ int tsm[];                          // [3][TRACE_SMEM_W][TRACE_BLOCK] row buffers, then the n*n matrix
+    int8_t* smat = reinterpret_cast<int8_t*>(tsm + 3 * TRACE_SMEM_W * TRACE_BLOCK);
+    const int n = tp.n, gapO = tp.gapO, gapE = tp.gapE;
+    for (int q = threadIdx.x; q < n * n; q += TRACE_BLOCK) smat[q] = tp.mat[q];
+    __syncthreads();
+
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= ntasks) return;
-    const SwTask tk = order[k];
+    const bool valid = k < ntasks;
+    SwTask tk; tk.out = 0; tk.rd_base = 0; tk.rf_base = 0;
+    if (valid) tk = order[k];
     const int i = tk.out;
-    const FwdResult f = fr[i];
+    FwdResult f; f.want_rev = 0; f.score1 = 0; f.ref_end1 = 0; f.read_end1 = 0; f.word_mode = 0;
+    if (valid) f = fr[i];
+    if (valid && only_flagged && out[i].status != 7) f.want_rev = -1;      // already done by the narrow-band kernel
     FinalResult r;
     r.ref_begin1 = -1; r.read_begin1 = -1; r.cigar_len = 0; r.status = 0; r.cigar_off = 0;
-    if (!f.want_rev) { out[i] = r; return; }
+    if (f.want_rev < 0) { f.want_rev = 0; r = out[i]; }
 
-    int sub_ref, sub_read;
-    if (f.score1 > 0) {
-        const SwEnds e = rev[i];
-        r.ref_begin1 = f.ref_end1 - e.col;
-        r.read_begin1 = f.read_end1 - e.row;
-    } else {
-        // nothing aligned: the reverse pass of the reference sees an empty (byte mode) or 1x1 (word mode) matrix (ssw.c:820-831)
-        r.ref_begin1 = f.word_mode ? 0 : -1;
-        r.read_begin1 = 0;
-    }
-    if ((7 & tp.flag) == 0 || ((2 & tp.flag) != 0 && f.score1 < tp.filters) ||
-        ((4 & tp.flag) != 0 && (f.ref_end1 - r.ref_begin1 > tp.filterd || f.read_end1 - r.read_begin1 > tp.filterd))) { out[i] = r; return; }   // ssw.c:833
-
-    sub_ref = f.ref_end1 - r.ref_begin1 + 1;
-    sub_read = f.read_end1 - r.read_begin1 + 1;
-    if (f.score1 <= 0) {
-        // 1x1 problem, traceback loop never runs: "1M" (ssw.c:625,680-687)
-        unsigned long long o = atomicAdd(cig_used, 1ull);
-        if (o + 1 > cig_cap) { r.status = 6; out[i] = r; return; }
-        cig[o] = 1u << 4;
-        r.cigar_off = (int64_t)o; r.cigar_len = 1;
-        out[i] = r;
-        return;
+    bool running = false;                                 // lane has a banded DP to do
+    int sub_ref = 1, sub_read = 1;
+    if (valid && f.want_rev) {
+        if (f.score1 > 0) {
+            const SwEnds e = rev[i];
+            r.ref_begin1 = f.ref_end1 - e.col;
+            r.read_begin1 = f.read_end1 - e.row;
+        } else {
+            // nothing aligned: the reverse pass of the reference sees an empty (byte mode) or 1x1 (word mode) matrix (ssw.c:820-831)
+            r.ref_begin1 = f.word_mode ? 0 : -1;
+            r.read_begin1 = 0;
+        }
+        const bool no_cigar = (7 & tp.flag) == 0 || ((2 & tp.flag) != 0 && f.score1 < tp.filters) ||
+            ((4 & tp.flag) != 0 && (f.ref_end1 - r.ref_begin1 > tp.filterd || f.read_end1 - r.read_begin1 > tp.filterd));   // ssw.c:833
+        if (!no_cigar) {
+            sub_ref = f.ref_end1 - r.ref_begin1 + 1;
+            sub_read = f.read_end1 - r.read_begin1 + 1;
+            if (f.score1 <= 0) {
+                // 1x1 problem, traceback loop never runs: "1M" (ssw.c:625,680-687)
+                unsigned long long o = atomicAdd(cig_used, 1ull);
+                if (o + 1 > cig_cap) r.status = 6;
+                else { cig[o] = 1u << 4; r.cigar_off = (int64_t)o; r.cigar_len = 1; }
+            } else running = true;
+        }
     }
     const int8_t* ref = seq + tk.rf_base + r.ref_begin1;
     const int8_t* read = seq + tk.rd_base + r.read_begin1;
-    const int n = tp.n, gapO = tp.gapO, gapE = tp.gapE, score = f.score1;
+    const int score = f.score1;
+
+    // ---- banded DP, one cell per lane per iteration
     int bw = abs(sub_ref - sub_read) + 1;
     int width = 0, width_d = 0, maxv = 0;
     uint8_t* dir = nullptr;
-    do {
-        width = bw * 2 + 3; width_d = bw * 2 + 1;
-        const bool in_smem = bw <= TRACE_SMEM_BW;
-        const unsigned long long need_dir = ((unsigned long long)width_d * (unsigned long long)sub_read + 15ull) & ~15ull;
-        const unsigned long long need = need_dir + (in_smem ? 0ull : 3ull * (unsigned long long)(width + 1) * 4ull);
-        const unsigned long long o = atomicAdd(scratch.used, (need + 15ull) & ~15ull);
-        if (o + need > scratch.bytes) { r.status = 5; out[i] = r; return; }
-        dir = scratch.base + o;
-        // previous-row H, previous-row E, current-row H in band coordinates: shared memory (stride = block) for narrow bands
-        int* hb = in_smem ? tsm + threadIdx.x : reinterpret_cast<int*>(dir + need_dir);
-        const int st = in_smem ? TRACE_BLOCK : 1;
-        int* eb = hb + (in_smem ? TRACE_SMEM_W * TRACE_BLOCK : (width + 1));
-        int* hc = eb + (in_smem ? TRACE_SMEM_W * TRACE_BLOCK : (width + 1));
-        for (int j = 0; j <= width; ++j) { hb[j * st] = 0; eb[j * st] = 0; hc[j * st] = 0; }
-        for (int ii = 0; ii < sub_read; ++ii) {
-            const int beg = max(0, ii - bw), end = min(sub_ref - 1, ii + bw);
-            const int edge = min(end + 1, width - 1);
-            const int xi = band_x(ii, bw), xp = band_x(ii - 1, bw);
-            int fv = 0, u = 0;
-            uint8_t* line = dir + (size_t)width_d * (size_t)ii;
-            hb[0] = 0; eb[0] = 0; hb[edge * st] = 0; eb[edge * st] = 0; hc[0] = 0;
-            const int8_t* mrow = tp.mat + (int)read[ii];
-            for (int j = beg; j <= end; ++j) {
-                const int e_idx = j - xp + 1, d_idx = j - xp, b_idx = j - xi;
-                u = j - xi + 1;
-                int open = ii == 0 ? -gapO : hb[e_idx * st] - gapO;
-                int ext = ii == 0 ? -gapE : eb[e_idx * st] - gapE;
+    int* hb = tsm; int* hc = tsm; int* eb = tsm; int st = 1;
+    int ii = 0, j = 0, end = -1, xi = 0, xp = 0, fv = 0, hleft = 0, hdiag = 0;
+    const int8_t* mrow = smat;
+    uint8_t* line = nullptr;
+    bool new_attempt = running, new_row = false;
+    while (__any_sync(0xffffffffu, running)) {
+        if (running) {
+            if (new_attempt) {
+                width = bw * 2 + 3; width_d = bw * 2 + 1;
+                const bool in_smem = bw <= TRACE_SMEM_BW;
+                const unsigned long long need_dir = ((unsigned long long)width_d * (unsigned long long)sub_read + 15ull) & ~15ull;
+                const unsigned long long need = need_dir + (in_smem ? 0ull : 3ull * (unsigned long long)(width + 1) * 4ull);
+                const unsigned long long o = atomicAdd(scratch.used, (need + 15ull) & ~15ull);
+                if (o + need > scratch.bytes) { r.status = 5; running = false; }
+                else {
+                    dir = scratch.base + o;
+                    // previous-row H, previous-row E, current-row H in band coordinates; shared memory (stride = block) for narrow bands
+                    st = in_smem ? TRACE_BLOCK : 1;
+                    hb = in_smem ? tsm + threadIdx.x : reinterpret_cast<int*>(dir + need_dir);
+                    eb = hb + (in_smem ? TRACE_SMEM_W * TRACE_BLOCK : (width + 1));
+                    hc = eb + (in_smem ? TRACE_SMEM_W * TRACE_BLOCK : (width + 1));
+                    for (int q = 0; q <= width; ++q) { hb[q * st] = 0; eb[q * st] = 0; hc[q * st] = 0; }
+                    ii = 0; new_row = true; new_attempt = false;
+                }
+            }
+            if (running && new_row) {
+                const int beg = max(0, ii - bw);
+                end = min(sub_ref - 1, ii + bw);
+                const int edge = min(end + 1, width - 1);
+                xi = band_x(ii, bw); xp = band_x(ii - 1, bw);
+                hb[0] = 0; eb[0] = 0; hb[edge * st] = 0; eb[edge * st] = 0; hc[0] = 0;      // ssw.c:580
+                fv = 0; hleft = 0; j = beg;
+                hdiag = hb[(beg - xp) * st];                                                 // H(ii-1, beg-1), 0 on the matrix edge
+                line = dir + (size_t)width_d * (size_t)ii;
+                mrow = smat + (int)read[ii];
+                new_row = false;
+            }
+            if (running) {
+                const int e_idx = j - xp + 1, u = j - xi + 1;
+                const int hup = hb[e_idx * st], eup = eb[e_idx * st];
+                int open = ii == 0 ? -gapO : hup - gapO;
+                int ext = ii == 0 ? -gapE : eup - gapE;
                 const int ev = open > ext ? open : ext;
                 const int de3 = open > ext ? 1 : 0;
-                open = hc[b_idx * st] - gapO; ext = fv - gapE;
+                open = hleft - gapO; ext = fv - gapE;
                 fv = open > ext ? open : ext;
                 const int df5 = open > ext ? 1 : 0;
                 const int e1 = ev > 0 ? ev : 0, f1 = fv > 0 ? fv : 0;
                 const int t1 = e1 > f1 ? e1 : f1;
-                const int t2 = hb[d_idx * st] + (int)mrow[(int)ref[j] * n];
+                const int t2 = hdiag + (int)mrow[(int)ref[j] * n];
                 const int hv = t1 > t2 ? t1 : t2;
                 int dh;
                 if (t1 <= t2) dh = 1; else dh = e1 > f1 ? (de3 ? 3 : 2) : (df5 ? 5 : 4);
-                // previous-row E must be read before it is overwritten: e_idx >= u always (xp <= xi), so writing eb[u] now is safe
-                eb[u * st] = ev;
+                eb[u * st] = ev;                      // e_idx >= u (xp <= xi): the old E of this column was read above
                 hc[u * st] = hv;
                 if (hv > maxv) maxv = hv;
                 line[j - xi] = (uint8_t)(de3 | (df5 << 1) | (dh << 2));
+                hleft = hv; hdiag = hup;
+                if (++j > end) {
+                    // row done: the current row becomes the previous one (the reference copies h_c[1..u] into h_b, ssw.c:612; entries
+                    // beyond u are never read before being rewritten or zeroed through `edge`, so swapping the buffers is equivalent)
+                    int* tmp = hb; hb = hc; hc = tmp;
+                    new_row = true;
+                    if (++ii >= sub_read) {
+                        bw *= 2;
+                        if (maxv < score) new_attempt = true;      // ssw.c:614-615
+                        else running = false;
+                    }
+                }
             }
-            for (int j = 1; j <= u; ++j) hb[j * st] = hc[j * st];
         }
-        bw *= 2;
-    } while (maxv < score);
+    }
     bw /= 2;
+    if (!(valid && f.want_rev)) { if (valid && !only_flagged) out[i] = r; return; }
+    if (r.status != 0 || r.cigar_len == 1 || dir == nullptr) { out[i] = r; return; }
 
     // ---- traceback, pass 1 counts the CIGAR words, pass 2 writes them back to front
     const long long total = (long long)width_d * sub_read;
