@@ -135,7 +135,7 @@ class Engine:
 
 
 def as_table(rec, cig, cigar_cap=64):
-    """records -> (int32 [n, 8] in oracle.FIELDS order with cigarLen = -1 for NULL results, uint32 [n, cigar_cap] cigar words)"""
+    """records -> (int32 [n, 8] in FIELDS order with cigarLen = -1 for NULL results, uint32 [n, cigar_cap] cigar words)"""
     n = len(rec)
     t = np.zeros((n, 8), dtype=np.int32)
     for k, f in enumerate(("score1", "score2", "ref_begin1", "ref_end1", "read_begin1", "read_end1", "ref_end2", "cigar_len")):

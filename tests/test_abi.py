@@ -1,0 +1,81 @@
+"""The C-ABI boundary without a GPU: the libraries load, export every function the headers in include/ declare, and the
+struct layouts that ctypes callers mirror (pyssw.py:7-16) are what the reference's are."""
+import ctypes as ct
+import importlib
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "megapath-nano_b200")
+LIBS = [os.path.join(PKG, "libmpn_ssw.so"), os.path.join(PKG, "realign", "libssw.so")]
+
+
+def declared_functions(header):
+    src = open(os.path.join(ROOT, "include", header)).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    names = re.findall(r"^\s*(?:[A-Za-z_][\w\s\*]*?)\b(\w+)\s*\([^;{]*\)\s*;", src, flags=re.M)
+    return [n for n in names if n not in ("defined",)]
+
+
+@pytest.fixture(scope="module")
+def built():
+    if not all(os.path.exists(p) for p in LIBS):
+        subprocess.run(["bash", os.path.join(ROOT, "build.sh")], check=True)
+    return LIBS
+
+
+def test_headers_declare_the_reference_entry_points():
+    assert set(declared_functions("ssw.h")) >= {"ssw_init", "init_destroy", "ssw_align", "align_destroy"}
+    assert set(declared_functions("mpn_ssw_batch.h")) >= {"mpn_engine_create", "mpn_align_batch", "mpn_batch_upload", "mpn_batch_run", "mpn_batch_fetch", "mpn_batch_free"}
+
+
+def test_libraries_export_every_declared_symbol(built):
+    want = declared_functions("ssw.h") + declared_functions("mpn_ssw_batch.h")
+    for path in built:
+        lib = ct.CDLL(path)
+        for name in want:
+            assert hasattr(lib, name), (path, name)
+
+
+def test_s_align_layout_is_the_reference_layout(tmp_path):
+    # compile a 10-line C program against include/ssw.h and compare offsets with the ctypes mirror the reference's callers use
+    src = tmp_path / "lay.c"
+    src.write_text('#include <stddef.h>\n#include "ssw.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(s_align), offsetof(s_align,score1),'
+                   'offsetof(s_align,score2), offsetof(s_align,ref_begin1), offsetof(s_align,ref_end1), offsetof(s_align,read_begin1), offsetof(s_align,read_end1),'
+                   'offsetof(s_align,ref_end2), offsetof(s_align,cigar), offsetof(s_align,cigarLen)); return 0;}\n')
+    exe = tmp_path / "lay"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)], check=True)
+    got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    assert got == [40, 0, 2, 4, 8, 12, 16, 20, 24, 32]
+    pyssw = importlib.import_module("megapath-nano_b200.pyssw")
+    assert ct.sizeof(pyssw.CAlignRes) == 40 and pyssw.CAlignRes.sCigar.offset == 24 and pyssw.CAlignRes.nCigarLen.offset == 32
+
+
+def test_cigar_helpers_match_reference_encoding(tmp_path):
+    src = tmp_path / "cig.c"
+    src.write_text('#include "ssw.h"\nint main(void){const char* ops="MIDNSHP=X"; for(int i=0;i<9;i++){unsigned v=to_cigar_int(7,ops[i]); if((v&15)!=(unsigned)i||cigar_int_to_len(v)!=7||cigar_int_to_op(v)!=ops[i]) return 1;}'
+                   ' if(cigar_int_to_op(0x7f)!=\'M\') return 2; if(to_cigar_int(3,\'?\')!=(3u<<4)) return 3; return 0;}\n')
+    exe = tmp_path / "cig"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)], check=True)
+    assert subprocess.run([str(exe)]).returncode == 0
+
+
+def test_no_gpu_means_loud_failure_not_fallback(built):
+    """without a CUDA device engine creation must fail (NULL), never silently compute on the CPU"""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    B = importlib.import_module("megapath-nano_b200.batch")
+    with pytest.raises(RuntimeError):
+        B.Engine()
+
+
+def test_product_never_imports_the_oracle():
+    for dirpath, _, files in os.walk(PKG):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                txt = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "oracle" not in txt, os.path.join(dirpath, f)

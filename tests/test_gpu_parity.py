@@ -1,0 +1,176 @@
+"""Parity tests proper: the CUDA path, called through the C ABI, against (a) the golden vectors of the compiled reference,
+(b) the oracle on seeded inputs, (c) size-independent properties at BASELINE sizes.  Bit-exact on every field and CIGAR word."""
+import ctypes as ct
+import importlib
+import os
+
+import numpy as np
+import pytest
+
+from golden_util import golden_cases, diff, CAP
+
+pytestmark = pytest.mark.gpu
+
+w = importlib.import_module("megapath-nano_b200.workloads")
+B = importlib.import_module("megapath-nano_b200.batch")
+pyssw = importlib.import_module("megapath-nano_b200.pyssw")
+
+
+@pytest.fixture(scope="module")
+def eng():
+    e = B.Engine(0)           # raises if the CUDA library or the GPU is missing: no fallback
+    yield e
+    e.close()
+
+
+def gpu_table(eng, b, cap=CAP):
+    rec, cig = eng.align(b)
+    return B.as_table(rec, cig, cap) + (rec, cig)
+
+
+def oracle_table(b, cap=CAP, threads=8):
+    from oracle import oracle
+    impl = "ref" if oracle.have_ref() else "port"
+    return oracle.run_batch(b.reads, b.read_off, b.refs, b.ref_off, b.masklen, b.mat, b.n, gapO=b.gapO, gapE=b.gapE, flag=b.flag, filters=b.filters,
+                            filterd=b.filterd, score_size=b.score_size, threads=threads, impl=impl, cigar_cap=cap)[:2]
+
+
+def test_golden_vectors(eng):
+    npairs = 0
+    for k, b, res, cig in golden_cases():
+        g, gc, _, _ = gpu_table(eng, b)
+        bad = diff(g, gc, res, cig)
+        assert len(bad) == 0, (k, b.name, bad[:5], g[bad[:1]], res[bad[:1]])
+        npairs += b.npairs
+    assert npairs > 3000
+
+
+@pytest.mark.parametrize("seed", range(300, 316))
+def test_fuzz_against_oracle(eng, seed):
+    flag = [1, 0, 8, 0x0f, 2, 4, 3, 5][seed % 8]
+    b = w.fuzz_pairs(250, seed, alphabet=2 if seed % 3 == 0 else 4, flag=flag)
+    b.filters = 90 if flag in (2, 3) else 0
+    b.filterd = 35 if flag in (4, 5) else 32767
+    g, gc, _, _ = gpu_table(eng, b)
+    r, c = oracle_table(b)
+    bad = diff(g, gc, r, c)
+    assert len(bad) == 0, (seed, bad[:5], g[bad[:1]], r[bad[:1]])
+
+
+def test_config1_full_size(eng):
+    """BASELINE configs[0] at its full size: 10 000 pairs, 250 bp x 500 bp, flag 0"""
+    b = w.config1()
+    g, gc, _, _ = gpu_table(eng, b)
+    r, c = oracle_table(b, threads=os.cpu_count() or 8)
+    assert len(diff(g, gc, r, c)) == 0
+
+
+def test_config2_sample_against_oracle(eng):
+    b = w.config2(60_000, seed=77)
+    g, gc, _, _ = gpu_table(eng, b)
+    r, c = oracle_table(b, threads=os.cpu_count() or 8)
+    assert len(diff(g, gc, r, c)) == 0
+
+
+def _rescore(b, rec, cig, i):
+    """score of the reported alignment path: must equal score1 (a property that needs no oracle)"""
+    mat = np.asarray(b.mat).reshape(b.n, b.n)
+    read = b.reads[b.read_off[i]:b.read_off[i + 1]]; ref = b.refs[b.ref_off[i]:b.ref_off[i + 1]]
+    qi, ti = int(rec["read_begin1"][i]), int(rec["ref_begin1"][i])
+    o, l = int(rec["cigar_off"][i]), int(rec["cigar_len"][i])
+    s = 0
+    for wd in cig[o:o + l]:
+        n, op = int(wd) >> 4, int(wd) & 15
+        if op == 0:
+            s += int(mat[ref[ti:ti + n], read[qi:qi + n]].sum()); qi += n; ti += n
+        elif op == 1:
+            s -= b.gapO + (n - 1) * b.gapE; qi += n
+        else:
+            s -= b.gapO + (n - 1) * b.gapE; ti += n
+    return s, qi - 1, ti - 1
+
+
+def test_config2_full_size_properties(eng):
+    """BASELINE configs[1] at a size the oracle would need minutes for: CIGAR paths re-score to score1, spans are consistent,
+    results do not depend on batch order, and a re-run is identical."""
+    n = 300_000
+    b = w.config2(n, seed=78)
+    rec, cig = eng.align(b)
+    assert (rec["status"] == 0).all()
+    rng = np.random.default_rng(1)
+    for i in rng.integers(0, n, size=400):
+        s, qe, te = _rescore(b, rec, cig, int(i))
+        assert s == int(rec["score1"][i]) and qe == int(rec["read_end1"][i]) and te == int(rec["ref_end1"][i]), i
+    assert (rec["score1"] >= rec["score2"]).all()
+    assert ((rec["ref_begin1"] >= 0) & (rec["ref_begin1"] <= rec["ref_end1"]) & (rec["ref_end1"] < 1000)).all()
+    rec2, cig2 = eng.align(b)
+    t1, c1 = B.as_table(rec, cig, 32); t2, c2 = B.as_table(rec2, cig2, 32)
+    assert np.array_equal(t1, t2) and np.array_equal(c1, c2)
+    perm = rng.permutation(20_000)
+    sb = b.subset(perm)
+    rec3, cig3 = eng.align(sb)
+    t3, c3 = B.as_table(rec3, cig3, 32)
+    assert np.array_equal(t3, t1[perm]) and np.array_equal(c3, c1[perm])
+
+
+def test_edge_shapes(eng):
+    """empty batch, 1-base sequences, reads longer than targets, all-N reads, reads needing the 32-bit kernel"""
+    dna = w.dna_matrix()
+    e = w.PairBatch(np.zeros(0, np.int8), np.zeros(1, np.int64), np.zeros(0, np.int8), np.zeros(1, np.int64), np.zeros(0, np.int32), mat=dna, flag=1)
+    rec, cig = eng.align(e)
+    assert len(rec) == 0
+    rng = np.random.default_rng(3)
+    reads, refs = [], []
+    for rl, fl in ((1, 1), (1, 40), (40, 1), (16, 16), (17, 300), (300, 17), (129, 129), (1281, 1500), (1500, 200), (2000, 2100)):
+        t = rng.integers(0, 4, size=fl).astype(np.int8)
+        r = np.resize(t, rl).copy(); r[rng.random(rl) < 0.05] = 3
+        reads.append(r); refs.append(t)
+    reads.append(np.full(50, 4, np.int8)); refs.append(rng.integers(0, 4, size=80).astype(np.int8))       # all-N read
+    n4 = rng.integers(0, 4, size=200).astype(np.int8); n4[::7] = 4
+    reads.append(n4); refs.append(np.concatenate([rng.integers(0, 4, size=30).astype(np.int8), np.where(n4 == 4, 1, n4), rng.integers(0, 4, size=30).astype(np.int8)]))
+    ro = np.concatenate([[0], np.cumsum([len(x) for x in reads])]).astype(np.int64)
+    fo = np.concatenate([[0], np.cumsum([len(x) for x in refs])]).astype(np.int64)
+    for flag in (0, 1, 0x0f):
+        b = w.PairBatch(np.concatenate(reads), ro, np.concatenate(refs), fo, np.full(len(reads), 15, np.int32), mat=dna, flag=flag)
+        g, gc, _, _ = gpu_table(eng, b)
+        r, c = oracle_table(b)
+        bad = diff(g, gc, r, c)
+        assert len(bad) == 0, (flag, bad, g[bad[:1]], r[bad[:1]])
+
+
+def test_legacy_per_pair_abi(eng):
+    """ssw_init / ssw_align / align_destroy / init_destroy of realign/libssw.so, driven exactly like the reference's batch driver"""
+    from oracle import oracle
+    lib = ct.CDLL(pyssw.lib_path)
+    b = w.fuzz_pairs(60, 41, flag=1, max_read=200, max_ref=250)
+    g, gc, _ = oracle.run_batch(b.reads, b.read_off, b.refs, b.ref_off, b.masklen, b.mat, b.n, gapO=b.gapO, gapE=b.gapE, flag=1, threads=2, impl="lib", lib=lib, cigar_cap=CAP)
+    r, c = oracle_table(b)
+    assert len(diff(g, gc, r, c)) == 0
+
+
+def test_pyssw_mirror(eng):
+    """the Python operator interface of the reference (pyssw.SSW.align) and its new batched form agree with each other and with ssw.c"""
+    rng = np.random.default_rng(9)
+    ref = "".join("ACGT"[i] for i in rng.integers(0, 4, size=601))
+    a = pyssw.SSW()
+    a.set_reference_sequence(ref)
+    queries = []
+    for k in range(24):
+        s = int(rng.integers(0, 200)); q = list(ref[s:s + 380])
+        del q[100:100 + (k % 5)]
+        q[200:200] = list("ACGTT"[:k % 4])
+        if k % 6 == 0:
+            q[50] = "N"
+        queries.append("".join(q))
+    queries.append("ACGTACGTAC")          # <= 30 bases: maskLen 15 branch of pyssw.py:142
+    single = [a.align(q) for q in queries]
+    batch = a.align_batch(queries)
+    assert single == batch
+    for (score, cigar, beg), q in zip(single, queries):
+        assert score > 0 and beg >= 0 and cigar
+    # cross-check one against the reference library when it is available
+    from oracle import oracle
+    if oracle.have_ref():
+        r = pyssw.SSW(lib_path=oracle.ref_path())
+        r.set_reference_sequence(ref)
+        assert [r.align(q) for q in queries[:6]] == single[:6]
