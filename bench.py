@@ -212,6 +212,7 @@ def main():
     e2e_ms = max(e2.elapsed_time(e3), 1e3 * (time.perf_counter() - t0))
     clocks = sampler.finish() if sampler else None
     recs = np.frombuffer(out.numpy(), dtype=B.RESULT_DTYPE)
+    assert int((recs["status"] != 0).sum()) == 0 and int(recs["score1"].min()) > 0, "e2e results look wrong"
     h2d = int(len(b.reads) + len(b.refs) + b.npairs * (4 + 40) + 25)
     d2h = int(b.npairs * (32 + 24) + int(recs["cigar_len"].sum()) * 4)
 

@@ -123,15 +123,20 @@ class Engine:
         self.L.mpn_batch_free(h)
 
     def align(self, b, cigar_cap=None, out=None, cig=None):
-        """b: anything with the PairBatch fields (workloads.PairBatch).  Returns (records[npairs] of RESULT_DTYPE, cigar arena)."""
+        """The public call: host buffers in, host records out (mpn_align_batch; large batches are pipelined in chunks inside).
+        b: anything with the PairBatch fields (workloads.PairBatch).  Returns (records[npairs] of RESULT_DTYPE, cigar arena)."""
+        n = int(b.npairs)
         if cigar_cap is None:
-            cigar_cap = int(b.npairs) * 24 + int(len(b.reads)) // 4 + 4096
-        h = self.upload(b)
-        try:
-            self.run(h)
-            return self.fetch(h, int(b.npairs), cigar_cap, out, cig)
-        finally:
-            self.free(h)
+            cigar_cap = n * 24 + int(len(b.reads)) // 4 + 4096
+        out = np.zeros(n, dtype=RESULT_DTYPE) if out is None else out
+        cig = np.zeros(max(cigar_cap, 1), dtype=np.uint32) if cig is None else cig
+        keep = []
+        p = self._params(b, keep)
+        rc = self.L.mpn_align_batch(self.h, ct.byref(p), _ptr(b.reads), _ptr(b.read_off), _ptr(b.refs), _ptr(b.ref_off), _ptr(b.masklen), n,
+                                    _ptr(out), _ptr(cig), int(cigar_cap))
+        if rc:
+            raise RuntimeError(f"mpn_align_batch -> {rc}")
+        return out, cig
 
 
 def as_table(rec, cig, cigar_cap=64):

@@ -8,6 +8,7 @@
 #include "sw_finish.cuh"
 #include "sw_trace.cuh"
 #include "sw_trace_narrow.cuh"
+#include "sw_trace_warp.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -90,7 +91,9 @@ struct mpn_engine {
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     int ev_valid = 0;
     DevPool pool;
-    PinBuf pin_tasks, pin_fwd, pin_fin, pin_misc;
+    struct Slot { cudaStream_t st = nullptr; PinBuf pin_tasks, pin_fwd, pin_fin, pin_misc; };
+    static constexpr int NSLOT = 3;                  // slot 0 serves the phased API on the engine stream; 1..2 are the pipeline of mpn_align_batch
+    Slot slot[NSLOT];
     std::vector<int32_t> h_bin;
     std::vector<int64_t> h_order, h_idx, h_cnt;
 };
@@ -109,11 +112,14 @@ struct mpn_batch {
     Score16 sc16{};
     FinishParams fin{};
     // device
-    DevBuf seq, mask, tasks_fwd, tasks_rev, ends_fwd, ends_rev, colrec, fwdres, finalres, counters, dmat, scratch, cig, wide_boundary;
+    DevBuf seq, mask, tasks_fwd, tasks_rev, ends_fwd, ends_rev, colrec, fwdres, finalres, counters, dmat, scratch, cig, wide_boundary, bandrec, flaglist;
     size_t seq_reads_bytes = 0, seq_bytes = 0;
     int64_t colrec_words = 0;
     unsigned long long scratch_bytes = 0, cig_cap = 0;
     bool ran = false;
+    mpn_engine::Slot* slot = nullptr;
+    cudaStream_t st = nullptr;            // stream every copy and kernel of this batch is enqueued on
+    bool pipelined = false;               // owned by mpn_align_batch's chunk pipeline: no host synchronisation inside upload
     size_t h2d_bytes = 0, d2h_bytes = 0;
     long long wide_stride = 0; int wide_blocks = 0;
 };
@@ -135,6 +141,7 @@ extern "C" mpn_engine* mpn_engine_create(int device)
     e->sm_count = prop.multiProcessorCount;
     CK(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
     e->stream = e->own_stream;
+    for (int k = 1; k < mpn_engine::NSLOT; ++k) CK(cudaStreamCreateWithFlags(&e->slot[k].st, cudaStreamNonBlocking));
     for (int c = 0; c < N_STRIPS; ++c) {
         int nb = 0;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, g_strips[c].fn, STRIP_BLOCK, g_strips[c].smem));
@@ -150,7 +157,11 @@ extern "C" void mpn_engine_destroy(mpn_engine* e)
     cudaSetDevice(e->device);
     cudaStreamDestroy(e->own_stream);
     e->pool.clear();
-    e->pin_tasks.release(); e->pin_fwd.release(); e->pin_fin.release(); e->pin_misc.release();
+    for (int k = 0; k < mpn_engine::NSLOT; ++k) {
+        mpn_engine::Slot& sl = e->slot[k];
+        sl.pin_tasks.release(); sl.pin_fwd.release(); sl.pin_fin.release(); sl.pin_misc.release();
+        if (k > 0 && sl.st) cudaStreamDestroy(sl.st);
+    }
     if (e->ev[0]) for (int i = 0; i < 5; ++i) cudaEventDestroy(e->ev[i]);
     delete e;
 }
@@ -196,13 +207,13 @@ extern "C" void mpn_batch_free(mpn_batch* b)
     if (!b) return;
     cudaSetDevice(b->e->device);
     DevBuf* bufs[] = {&b->seq, &b->mask, &b->tasks_fwd, &b->tasks_rev, &b->ends_fwd, &b->ends_rev,
-                      &b->colrec, &b->fwdres, &b->finalres, &b->counters, &b->dmat, &b->scratch, &b->cig, &b->wide_boundary};
+                      &b->colrec, &b->fwdres, &b->finalres, &b->counters, &b->dmat, &b->scratch, &b->cig, &b->wide_boundary, &b->bandrec, &b->flaglist};
     for (DevBuf* d : bufs) b->e->pool.give(*d);
     delete b;
 }
 
-extern "C" mpn_batch* mpn_batch_upload(mpn_engine* e, const mpn_params* p, const int8_t* reads, const int64_t* read_off, const int8_t* refs,
-                                        const int64_t* ref_off, const int32_t* masklen, int64_t npairs)
+static mpn_batch* upload_impl(mpn_engine* e, int slot_id, const mpn_params* p, const int8_t* reads, const int64_t* read_off, const int8_t* refs,
+                              const int64_t* ref_off, const int32_t* masklen, int64_t npairs)
 {
     if (!e || !p || !p->mat || p->n < 1 || p->n > 127 || npairs < 0 || npairs > 0x7fffffff) return nullptr;
     if (npairs > 0 && (!reads || !read_off || !refs || !ref_off || !masklen)) return nullptr;
@@ -211,7 +222,11 @@ extern "C" mpn_batch* mpn_batch_upload(mpn_engine* e, const mpn_params* p, const
     b->e = e; b->p = *p; b->npairs = npairs;
     b->mat.assign(p->mat, p->mat + (size_t)p->n * p->n);
     b->p.mat = b->mat.data();
-    cudaStream_t st = e->stream;
+    b->slot = &e->slot[slot_id];
+    b->st = slot_id == 0 ? e->stream : b->slot->st;
+    b->pipelined = slot_id != 0;
+    mpn_engine::Slot& sl = *b->slot;
+    cudaStream_t st = b->st;
     const int n = p->n;
 
     // ---- scoring: matrix rows for the packed kernel, bias as ssw_init (ssw.c:741-745)
@@ -260,8 +275,8 @@ extern "C" mpn_batch* mpn_batch_upload(mpn_engine* e, const mpn_params* p, const
     //      a warp run in step and the tail of a launch is made of short tasks
     std::vector<int64_t> bin_first(N_STRIPS + 2, 0);
     for (int c = 0; c <= N_STRIPS; ++c) bin_first[c + 1] = bin_first[c] + bin_count[c];
-    e->pin_tasks.reserve(sizeof(SwTask) * (size_t)(npairs + 1));
-    SwTask* h_tasks = e->pin_tasks.as<SwTask>();
+    sl.pin_tasks.reserve(sizeof(SwTask) * (size_t)(npairs + 1));
+    SwTask* h_tasks = sl.pin_tasks.as<SwTask>();
     {
         std::vector<int64_t>& order = e->h_order;
         order.resize(npairs);
@@ -309,9 +324,9 @@ extern "C" mpn_batch* mpn_batch_upload(mpn_engine* e, const mpn_params* p, const
         CK(cudaMemcpyAsync(b->mask.p, masklen, sizeof(int32_t) * npairs, cudaMemcpyHostToDevice, st));
         CK(cudaMemcpyAsync(b->tasks_fwd.p, h_tasks, sizeof(SwTask) * npairs, cudaMemcpyHostToDevice, st));
     }
-    e->pin_misc.reserve(4096);
-    memcpy(e->pin_misc.p, b->mat.data(), (size_t)n * n);
-    CK(cudaMemcpyAsync(b->dmat.p, e->pin_misc.p, (size_t)n * n, cudaMemcpyHostToDevice, st));
+    sl.pin_misc.reserve(4096 + (size_t)n * n);
+    memcpy(sl.pin_misc.as<char>() + 4096, b->mat.data(), (size_t)n * n);
+    CK(cudaMemcpyAsync(b->dmat.p, sl.pin_misc.as<char>() + 4096, (size_t)n * n, cudaMemcpyHostToDevice, st));
     b->h2d_bytes = reads_bytes + refs_bytes + (sizeof(int32_t) + sizeof(SwTask)) * (size_t)npairs + (size_t)n * n;
 
     // ---- boundary rows of the 32-bit kernel (one slot per resident warp)
@@ -322,6 +337,7 @@ extern "C" mpn_batch* mpn_batch_upload(mpn_engine* e, const mpn_params* p, const
     // ---- traceback arenas.  Direction bytes: (2*band+1) per read row; the first attempt has band |dlen|+1 and most pairs
     // stop there.  Budget 16 band cells per read base (+ slack); pairs that do not fit are reported (status 5) and re-run by fetch.
     const bool want_cigar = (p->flag & 7) != 0;
+    if ((p->flag & 0xff) != 0) { pool.take(b->bandrec, sizeof(BandRec) * (size_t)(npairs + 1)); pool.take(b->flaglist, sizeof(int) * (size_t)(npairs + 1)); }
     if (want_cigar) {
         int64_t read_bases = (int64_t)reads_bytes;
         b->scratch_bytes = (unsigned long long)read_bases * 24ull + (unsigned long long)npairs * 512ull + (64ull << 20);
@@ -329,15 +345,22 @@ extern "C" mpn_batch* mpn_batch_upload(mpn_engine* e, const mpn_params* p, const
         pool.take(b->scratch, b->scratch_bytes);
         pool.take(b->cig, b->cig_cap * sizeof(uint32_t));
     }
-    // the task list sits in engine-owned pinned staging that the next upload overwrites: wait for its copy
-    CK(cudaStreamSynchronize(st));
+    // the task list sits in slot-owned pinned staging that the next upload on this slot overwrites: the phased API waits for
+    // its copy here; the chunk pipeline reuses a slot only after fetching (= synchronising) the batch that used it
+    if (!b->pipelined) CK(cudaStreamSynchronize(st));
     return b;
+}
+
+extern "C" mpn_batch* mpn_batch_upload(mpn_engine* e, const mpn_params* p, const int8_t* reads, const int64_t* read_off, const int8_t* refs,
+                                        const int64_t* ref_off, const int32_t* masklen, int64_t npairs)
+{
+    return upload_impl(e, 0, p, reads, read_off, refs, ref_off, masklen, npairs);
 }
 
 static void launch_strips(mpn_batch* b, const SwTask* tasks, bool forward, SwEnds* ends, int counter_base)
 {
     mpn_engine* e = b->e;
-    cudaStream_t st = e->stream;
+    cudaStream_t st = b->st;
     int slot = counter_base;
     for (const BinLaunch& bl : b->bins) {
         int* counter = reinterpret_cast<int*>(b->counters.as<unsigned long long>() + slot++);
@@ -363,7 +386,7 @@ extern "C" int mpn_batch_run(mpn_batch* b)
     if (!b) return MPN_E_ARG;
     mpn_engine* e = b->e;
     CK(cudaSetDevice(e->device));
-    cudaStream_t st = e->stream;
+    cudaStream_t st = b->st;
     const int64_t n = b->npairs;
     if (n == 0) { b->ran = true; return 0; }
     CK(cudaMemsetAsync(b->counters.p, 0, 256 * sizeof(unsigned long long), st));
@@ -401,13 +424,29 @@ extern "C" int mpn_batch_run(mpn_batch* b)
         TraceParams tp{b->fin.flag, b->fin.filters, b->p.filterd, b->fin.gapO, b->fin.gapE, b->p.n, b->dmat.as<int8_t>()};
         Arena ar{b->scratch.as<uint8_t>(), b->scratch_bytes, b->counters.as<unsigned long long>() + 64};
         {
-            const unsigned blocks = (unsigned)((n + NARROW_BLOCK - 1) / NARROW_BLOCK);
-            sw_trace_narrow_kernel<<<blocks, NARROW_BLOCK, narrow_smem_bytes(b->p.n), st>>>(b->tasks_fwd.as<SwTask>(), (int)n, b->seq.as<int8_t>(), b->fwdres.as<FwdResult>(),
-                b->ends_rev.as<SwEnds>(), tp, ar, b->cig.as<uint32_t>(), b->cig_cap, b->counters.as<unsigned long long>() + 65, b->finalres.as<FinalResult>());
+            // narrow bands: lane-persistent DP kernel, then one-thread-per-pair traceback
+            int nb = 0;
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, sw_band_dp_kernel, NARROW_BLOCK, narrow_smem_bytes()));
+            // lanes are persistent workers: give each about 6 pairs (load balance across unequal bands) while keeping >= 4 blocks per SM
+            int64_t want = (n + NARROW_BLOCK * 6 - 1) / (NARROW_BLOCK * 6);
+            want = std::max<int64_t>(want, std::min<int64_t>((n + NARROW_BLOCK - 1) / NARROW_BLOCK, (int64_t)e->sm_count * 4));
+            const unsigned blocks = (unsigned)std::min<int64_t>(want, (int64_t)e->sm_count * std::max(nb, 1));
+            sw_band_dp_kernel<<<blocks, NARROW_BLOCK, narrow_smem_bytes(), st>>>(b->tasks_fwd.as<SwTask>(), (int)n, reinterpret_cast<int*>(b->counters.as<unsigned long long>() + 102),
+                b->seq.as<int8_t>(), b->fwdres.as<FwdResult>(), b->ends_rev.as<SwEnds>(), tp, ar, b->cig.as<uint32_t>(), b->cig_cap,
+                b->counters.as<unsigned long long>() + 65, b->finalres.as<FinalResult>(), b->bandrec.as<BandRec>(), b->flaglist.as<int>(),
+                reinterpret_cast<int*>(b->counters.as<unsigned long long>() + 103));
             CK(cudaGetLastError());
-            e->launches++;
+            sw_band_trace_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(b->tasks_fwd.as<SwTask>(), (int)n, b->fwdres.as<FwdResult>(), b->bandrec.as<BandRec>(), ar,
+                b->cig.as<uint32_t>(), b->cig_cap, b->counters.as<unsigned long long>() + 65, b->finalres.as<FinalResult>());
+            CK(cudaGetLastError());
+            // wide bands: one warp per flagged pair
+            sw_trace_warp_kernel<<<e->sm_count * 4, 32 * WARPTR_WARPS, warptr_smem_bytes(b->p.n), st>>>(b->tasks_fwd.as<SwTask>(), b->flaglist.as<int>(),
+                reinterpret_cast<int*>(b->counters.as<unsigned long long>() + 103), reinterpret_cast<int*>(b->counters.as<unsigned long long>() + 104), b->seq.as<int8_t>(),
+                b->fwdres.as<FwdResult>(), tp, ar, b->cig.as<uint32_t>(), b->cig_cap, b->counters.as<unsigned long long>() + 65, b->finalres.as<FinalResult>(), b->bandrec.as<BandRec>());
+            CK(cudaGetLastError());
+            e->launches += 3;
         }
-        // pairs whose band outgrew the narrow kernel (status 7) are redone by the generic one
+        // bands beyond the warp kernel's 512 cells (status 8) are redone by the generic kernel
         const unsigned blocks = (unsigned)((n + TRACE_BLOCK - 1) / TRACE_BLOCK);
         sw_trace_wide_kernel<<<blocks, TRACE_BLOCK, trace_smem_bytes(b->p.n), st>>>(b->tasks_fwd.as<SwTask>(), (int)n, b->seq.as<int8_t>(), b->fwdres.as<FwdResult>(), b->ends_rev.as<SwEnds>(), tp, ar,
                                                b->cig.as<uint32_t>(), b->cig_cap, b->counters.as<unsigned long long>() + 65, b->finalres.as<FinalResult>(), 1);
@@ -423,25 +462,27 @@ extern "C" int mpn_batch_run(mpn_batch* b)
     return 0;
 }
 
-extern "C" int mpn_batch_fetch(mpn_batch* b, mpn_result* out, uint32_t* cigar, int64_t cigar_cap)
+// fetch: device -> host.  `cigar_base` is added to every cigar_off (chunks of one user batch share the caller's arena);
+// *cigar_words receives the number of words this batch appended at cigar[0 ..).
+static int fetch_impl(mpn_batch* b, mpn_result* out, uint32_t* cigar, int64_t cigar_cap, int64_t cigar_base, int64_t* cigar_words)
 {
-    if (!b || (!out && b->npairs)) return MPN_E_ARG;
-    if (!b->ran) return MPN_E_ARG;
     mpn_engine* e = b->e;
     CK(cudaSetDevice(e->device));
-    cudaStream_t st = e->stream;
+    cudaStream_t st = b->st;
+    mpn_engine::Slot& sl = *b->slot;
     const int64_t n = b->npairs;
+    if (cigar_words) *cigar_words = 0;
     if (n == 0) return 0;
     const bool any_rev = !(b->fin.flag == 0);
-    e->pin_fwd.reserve(sizeof(FwdResult) * (size_t)n);
-    CK(cudaMemcpyAsync(e->pin_fwd.p, b->fwdres.p, sizeof(FwdResult) * n, cudaMemcpyDeviceToHost, st));
+    sl.pin_fwd.reserve(sizeof(FwdResult) * (size_t)n);
+    CK(cudaMemcpyAsync(sl.pin_fwd.p, b->fwdres.p, sizeof(FwdResult) * n, cudaMemcpyDeviceToHost, st));
     b->d2h_bytes = sizeof(FwdResult) * (size_t)n;
-    e->pin_misc.reserve(4096);
-    unsigned long long* used = e->pin_misc.as<unsigned long long>() + 256;
+    sl.pin_misc.reserve(4096);
+    unsigned long long* used = sl.pin_misc.as<unsigned long long>() + 256;
     used[0] = used[1] = 0;
     if (any_rev) {
-        e->pin_fin.reserve(sizeof(FinalResult) * (size_t)n);
-        CK(cudaMemcpyAsync(e->pin_fin.p, b->finalres.p, sizeof(FinalResult) * n, cudaMemcpyDeviceToHost, st));
+        sl.pin_fin.reserve(sizeof(FinalResult) * (size_t)n);
+        CK(cudaMemcpyAsync(sl.pin_fin.p, b->finalres.p, sizeof(FinalResult) * n, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(used, b->counters.as<unsigned long long>() + 64, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
         b->d2h_bytes += sizeof(FinalResult) * (size_t)n + 16;
     }
@@ -452,9 +493,10 @@ extern "C" int mpn_batch_fetch(mpn_batch* b, mpn_result* out, uint32_t* cigar, i
         if ((int64_t)words > cigar_cap || (!cigar && words)) return MPN_E_CIGAR_SPACE;
         if (words) CK(cudaMemcpyAsync(cigar, b->cig.p, words * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         b->d2h_bytes += words * sizeof(uint32_t);
+        if (cigar_words) *cigar_words = (int64_t)words;
     }
-    const FwdResult* h_fwd = e->pin_fwd.as<FwdResult>();
-    const FinalResult* h_fin = e->pin_fin.as<FinalResult>();
+    const FwdResult* h_fwd = sl.pin_fwd.as<FwdResult>();
+    const FinalResult* h_fin = sl.pin_fin.as<FinalResult>();
     for (int64_t i = 0; i < n; ++i) {
         const FwdResult& f = h_fwd[i];
         mpn_result& r = out[i];
@@ -465,16 +507,23 @@ extern "C" int mpn_batch_fetch(mpn_batch* b, mpn_result* out, uint32_t* cigar, i
         if (any_rev && f.status == 0) {
             const FinalResult& g = h_fin[i];
             r.ref_begin1 = g.ref_begin1; r.read_begin1 = g.read_begin1;
-            r.cigar_len = g.cigar_len; r.cigar_off = g.cigar_off;
+            r.cigar_len = g.cigar_len; r.cigar_off = g.cigar_len > 0 ? g.cigar_off + cigar_base : 0;
             if (g.status == 3) r.status = MPN_ST_NULL;
-            else if (g.status == 5 || g.status == 6) {
-                if (rc == 0) fprintf(stderr, "[mpn_ssw] traceback arena exhausted (first at pair %lld, status %d)\n", (long long)i, g.status);
+            else if (g.status != 0) {
+                if (rc == 0) fprintf(stderr, "[mpn_ssw] traceback could not complete (first at pair %lld, status %d: 5/6 = arena exhausted, 7/8 = band beyond kernel limits)\n", (long long)i, g.status);
                 rc = MPN_E_UNSUPPORTED;
             }
         }
     }
     CK(cudaStreamSynchronize(st));      // CIGAR arena copy
     return rc;
+}
+
+extern "C" int mpn_batch_fetch(mpn_batch* b, mpn_result* out, uint32_t* cigar, int64_t cigar_cap)
+{
+    if (!b || (!out && b->npairs)) return MPN_E_ARG;
+    if (!b->ran) return MPN_E_ARG;
+    return fetch_impl(b, out, cigar, cigar_cap, 0, nullptr);
 }
 
 extern "C" int mpn_batch_io_bytes(const mpn_batch* b, int64_t* h2d, int64_t* d2h)
@@ -488,10 +537,46 @@ extern "C" int mpn_batch_io_bytes(const mpn_batch* b, int64_t* h2d, int64_t* d2h
 extern "C" int mpn_align_batch(mpn_engine* e, const mpn_params* p, const int8_t* reads, const int64_t* read_off, const int8_t* refs,
                                const int64_t* ref_off, const int32_t* masklen, int64_t npairs, mpn_result* out, uint32_t* cigar, int64_t cigar_cap)
 {
-    mpn_batch* b = mpn_batch_upload(e, p, reads, read_off, refs, ref_off, masklen, npairs);
-    if (!b) return MPN_E_ARG;
-    int rc = mpn_batch_run(b);
-    if (rc == 0) rc = mpn_batch_fetch(b, out, cigar, cigar_cap);
-    mpn_batch_free(b);
+    if (!e || npairs < 0) return MPN_E_ARG;
+    // Small batches: one chunk on the engine stream.  Large batches: chunks of ~128 k pairs alternate between two pipeline slots
+    // (own stream + own pinned staging each), so the H2D copies and host-side scheduling of chunk k+1 overlap the kernels of chunk k
+    // and the D2H of chunk k-1.
+    const int64_t CHUNK = 131072;
+    if (npairs <= CHUNK + CHUNK / 2) {
+        mpn_batch* b = mpn_batch_upload(e, p, reads, read_off, refs, ref_off, masklen, npairs);
+        if (!b) return MPN_E_ARG;
+        int rc = mpn_batch_run(b);
+        if (rc == 0) rc = mpn_batch_fetch(b, out, cigar, cigar_cap);
+        mpn_batch_free(b);
+        return rc;
+    }
+    const int64_t nchunks = (npairs + CHUNK - 1) / CHUNK;
+    const int64_t per = (npairs + nchunks - 1) / nchunks;
+    mpn_batch* inflight[2] = {nullptr, nullptr};
+    int64_t start_of[2] = {0, 0};
+    int64_t cig_base = 0;
+    int rc = 0;
+    auto drain = [&](int s) {
+        if (!inflight[s]) return;
+        int64_t words = 0;
+        const int r2 = fetch_impl(inflight[s], out + start_of[s], cigar ? cigar + cig_base : nullptr, cigar_cap - cig_base, cig_base, &words);
+        if (r2 != 0 && rc == 0) rc = r2;
+        cig_base += words;
+        mpn_batch_free(inflight[s]);
+        inflight[s] = nullptr;
+    };
+    for (int64_t c = 0; c < nchunks; ++c) {
+        const int s = (int)(c & 1);
+        drain(s);
+        const int64_t c0 = c * per, n_c = std::min(per, npairs - c0);
+        if (n_c <= 0) break;
+        mpn_batch* b = upload_impl(e, 1 + s, p, reads, read_off + c0, refs, ref_off + c0, masklen + c0, n_c);
+        if (!b) { rc = MPN_E_ARG; break; }
+        mpn_batch_run(b);
+        inflight[s] = b; start_of[s] = c0;
+    }
+    // results must come back in chunk order for the CIGAR offsets: the older in-flight chunk first
+    const int first = (inflight[0] && inflight[1]) ? (start_of[0] < start_of[1] ? 0 : 1) : 0;
+    drain(first); drain(1 - first);
     return rc;
 }

@@ -38,7 +38,7 @@ struct Arena {
 __device__ __forceinline__ int band_x(int i, int w) { int x = i - w; return x > 0 ? x : 0; }
 
 constexpr int TRACE_BLOCK = 64;
-constexpr int TRACE_SMEM_BW = 6;                          // bands up to this half-width keep their row buffers in shared memory
+constexpr int TRACE_SMEM_BW = 24;                         // bands up to this half-width keep their row buffers in shared memory
 constexpr int TRACE_SMEM_W = 2 * TRACE_SMEM_BW + 4;       // entries per row buffer
 constexpr size_t TRACE_SMEM_BYTES = 3ull * TRACE_SMEM_W * TRACE_BLOCK * sizeof(int);
 inline size_t trace_smem_bytes(int n) { return TRACE_SMEM_BYTES + (((size_t)n * n + 15) & ~(size_t)15); }
@@ -64,7 +64,7 @@ sw_trace_wide_kernel(const SwTask* __restrict__ order, int ntasks, const int8_t*
     const int i = tk.out;
     FwdResult f; f.want_rev = 0; f.score1 = 0; f.ref_end1 = 0; f.read_end1 = 0; f.word_mode = 0;
     if (valid) f = fr[i];
-    if (valid && only_flagged && out[i].status != 7) f.want_rev = -1;      // already done by the narrow-band kernel
+    if (valid && only_flagged && out[i].status != 8) f.want_rev = -1;      // already done by the narrow-band / warp kernels
     FinalResult r;
     r.ref_begin1 = -1; r.read_begin1 = -1; r.cigar_len = 0; r.status = 0; r.cigar_off = 0;
     if (f.want_rev < 0) { f.want_rev = 0; r = out[i]; }

@@ -18,90 +18,116 @@ namespace mpn {
 constexpr int NARROW_BW = 7;
 constexpr int NARROW_W = 2 * NARROW_BW + 4;            // row-buffer entries (band coordinates 0 .. 2*bw+2)
 constexpr int NARROW_BLOCK = 64;
-inline size_t narrow_smem_bytes(int n) { return 3ull * NARROW_W * NARROW_BLOCK * sizeof(int) + (((size_t)n * n + 15) & ~(size_t)15); }
+inline size_t narrow_smem_bytes() { return 3ull * NARROW_W * NARROW_BLOCK * sizeof(int) + 8 * sizeof(unsigned long long); }
 
+// per-pair hand-over from the DP kernel to the traceback kernel
+struct BandRec {
+    unsigned long long dir_off;   // byte offset of the pair's direction words in the scratch arena
+    int32_t bw;                   // band half-width of the successful attempt
+    int32_t kind;                 // 0: nothing to trace, 2: trace from dir_off
+};
+
+// ---- DP: every LANE is a persistent worker that pulls the next pair from a global counter when its current one is done, so the 32
+//      lanes of a warp stay busy although band widths (3..15 cells per row) and read lengths differ from pair to pair.
 __global__ void __launch_bounds__(NARROW_BLOCK)
-sw_trace_narrow_kernel(const SwTask* __restrict__ order, int ntasks, const int8_t* __restrict__ seq, const FwdResult* __restrict__ fr,
-                       const SwEnds* __restrict__ rev, TraceParams tp, Arena scratch, uint32_t* __restrict__ cig, unsigned long long cig_cap,
-                       unsigned long long* __restrict__ cig_used, FinalResult* __restrict__ out)
+sw_band_dp_kernel(const SwTask* __restrict__ order, int ntasks, int* __restrict__ counter, const int8_t* __restrict__ seq,
+                  const FwdResult* __restrict__ fr, const SwEnds* __restrict__ rev, TraceParams tp, Arena scratch, uint32_t* __restrict__ cig,
+                  unsigned long long cig_cap, unsigned long long* __restrict__ cig_used, FinalResult* __restrict__ out, BandRec* __restrict__ recs, int* __restrict__ flag_list, int* __restrict__ nflag)
 {
-    extern __shared__ int nsm[];                       // [3][NARROW_W][NARROW_BLOCK]: element (a, idx) of thread t at ((a*W + idx)*BLOCK + t)
-    int8_t* smat = reinterpret_cast<int8_t*>(nsm + 3 * NARROW_W * NARROW_BLOCK);
+    extern __shared__ int nsm[];                       // [3][NARROW_W][NARROW_BLOCK] row buffers, then 8 packed score words
+    unsigned long long* srow = reinterpret_cast<unsigned long long*>(nsm + 3 * NARROW_W * NARROW_BLOCK);   // srow[q] = bytes mat[t*n+q], t = 0..7
     const int n = tp.n, gapO = tp.gapO, gapE = tp.gapE;
-    for (int q = threadIdx.x; q < n * n; q += NARROW_BLOCK) smat[q] = tp.mat[q];
+    if (threadIdx.x < 8) {
+        unsigned long long v = 0;
+        if ((int)threadIdx.x < n && n <= 8)
+            for (int t = 0; t < n; ++t) v |= (unsigned long long)(uint8_t)tp.mat[t * n + threadIdx.x] << (8 * t);
+        srow[threadIdx.x] = v;
+    }
     __syncthreads();
     int* const bufA = nsm + threadIdx.x;
     int* const ebuf = bufA + NARROW_W * NARROW_BLOCK;
     int* const bufB = ebuf + NARROW_W * NARROW_BLOCK;
     constexpr int ST = NARROW_BLOCK;
 
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool valid = k < ntasks;
-    SwTask tk; tk.out = 0; tk.rd_base = 0; tk.rf_base = 0;
-    if (valid) tk = order[k];
-    const int i = tk.out;
-    FwdResult f; f.want_rev = 0; f.score1 = 0; f.ref_end1 = 0; f.read_end1 = 0; f.word_mode = 0;
-    if (valid) f = fr[i];
-    FinalResult r;
-    r.ref_begin1 = -1; r.read_begin1 = -1; r.cigar_len = 0; r.status = 0; r.cigar_off = 0;
-
-    bool running = false;
-    int sub_ref = 1, sub_read = 1;
-    if (valid && f.want_rev) {
-        if (f.score1 > 0) {
-            const SwEnds e = rev[i];
-            r.ref_begin1 = f.ref_end1 - e.col;
-            r.read_begin1 = f.read_end1 - e.row;
-        } else {
-            r.ref_begin1 = f.word_mode ? 0 : -1;       // empty / 1x1 reverse matrix (ssw.c:820-831)
-            r.read_begin1 = 0;
-        }
-        const bool no_cigar = (7 & tp.flag) == 0 || ((2 & tp.flag) != 0 && f.score1 < tp.filters) ||
-            ((4 & tp.flag) != 0 && (f.ref_end1 - r.ref_begin1 > tp.filterd || f.read_end1 - r.read_begin1 > tp.filterd));   // ssw.c:833
-        if (!no_cigar) {
-            sub_ref = f.ref_end1 - r.ref_begin1 + 1;
-            sub_read = f.read_end1 - r.read_begin1 + 1;
-            if (f.score1 <= 0) {
-                unsigned long long o = atomicAdd(cig_used, 1ull);          // "1M" (ssw.c:625,680-687)
-                if (o + 1 > cig_cap) r.status = 6;
-                else { cig[o] = 1u << 4; r.cigar_off = (int64_t)o; r.cigar_len = 1; }
-            } else if (n > 8) r.status = 7;
-            else running = true;
-        }
-    }
-    const int8_t* ref = seq + tk.rf_base + r.ref_begin1;
-    const int8_t* read = seq + tk.rd_base + r.read_begin1;
-    const int score = f.score1;
-
-    int bw = abs(sub_ref - sub_read) + 1;
-    if (running && bw > NARROW_BW) { r.status = 7; running = false; }
-    int width = 0, width_d = 0, maxv = 0;
-    unsigned long long* dirrow = nullptr;              // one 64-bit word of 4-bit cells per read row
+    int state = 0;                                     // 0: needs a pair, 1: DP in progress, 2: no pairs left
+    int kcur = 0;
+    int i = 0, sub_ref = 1, sub_read = 1, score = 0, bw = 1, width = 0, maxv = 0;
+    const uint8_t* useq = reinterpret_cast<const uint8_t*>(seq);     // unsigned loads: no sign-extension op hanging on the load
+    const uint8_t* ref = useq; const uint8_t* read = useq;
+    unsigned long long* dirrow = nullptr;
+    unsigned long long dir_off = 0;
     int* hb = bufA; int* hc = bufB;
-    int ii = 0, j = 0, end = -1, xi = 0, xp = 0, wbase = 0, fv = 0, hleft = 0, hdiag = 0, rnext = 0;
+    int ii = 0, j = 0, end = -1, xi = 0, xp = 0, wbase = 0, fv = 0, hleft = 0, hdiag = 0;
+    unsigned rnext = 0, pending = 0;
     unsigned long long win_lo = 0, win_hi = 0, rscore = 0, dirword = 0;
-    bool new_attempt = running, new_row = false;
+    bool new_attempt = false, new_row = false;
 
-    while (__any_sync(0xffffffffu, running)) {
-        if (running && new_attempt) {
-            width = bw * 2 + 3; width_d = bw * 2 + 1;
-            const unsigned long long need = (unsigned long long)sub_read * 8ull;
-            const unsigned long long o = atomicAdd(scratch.used, (need + 15ull) & ~15ull);
-            if (o + need > scratch.bytes) { r.status = 5; running = false; }
+    for (;;) {
+        if (state == 0) {
+            const int k = atomicAdd(counter, 1);
+            if (k >= ntasks) state = 2;
             else {
-                dirrow = reinterpret_cast<unsigned long long*>(scratch.base + o);
-                hb = bufA; hc = bufB;
-                for (int q = 0; q <= width; ++q) { bufA[q * ST] = 0; ebuf[q * ST] = 0; bufB[q * ST] = 0; }
-                win_lo = 0; win_hi = 0;
-                for (int q = 0; q < 16; ++q) {
-                    const unsigned long long c = q < sub_ref ? (unsigned long long)(uint8_t)ref[q] : 0ull;
-                    if (q < 8) win_lo |= c << (8 * q); else win_hi |= c << (8 * (q - 8));
+                const SwTask tk = order[k];
+                kcur = k;
+                i = tk.out;
+                const FwdResult f = fr[i];
+                FinalResult r;
+                r.ref_begin1 = -1; r.read_begin1 = -1; r.cigar_len = 0; r.status = 0; r.cigar_off = 0;
+                BandRec br; br.dir_off = 0; br.bw = 0; br.kind = 0;
+                if (f.want_rev) {
+                    if (f.score1 > 0) {
+                        const SwEnds e = rev[i];
+                        r.ref_begin1 = f.ref_end1 - e.col;
+                        r.read_begin1 = f.read_end1 - e.row;
+                    } else {
+                        r.ref_begin1 = f.word_mode ? 0 : -1;       // empty / 1x1 reverse matrix (ssw.c:820-831)
+                        r.read_begin1 = 0;
+                    }
+                    const bool no_cigar = (7 & tp.flag) == 0 || ((2 & tp.flag) != 0 && f.score1 < tp.filters) ||
+                        ((4 & tp.flag) != 0 && (f.ref_end1 - r.ref_begin1 > tp.filterd || f.read_end1 - r.read_begin1 > tp.filterd));   // ssw.c:833
+                    if (!no_cigar) {
+                        sub_ref = f.ref_end1 - r.ref_begin1 + 1;
+                        sub_read = f.read_end1 - r.read_begin1 + 1;
+                        bw = abs(sub_ref - sub_read) + 1;
+                        if (f.score1 <= 0) {
+                            unsigned long long o = atomicAdd(cig_used, 1ull);          // "1M" (ssw.c:625,680-687)
+                            if (o + 1 > cig_cap) r.status = 6;
+                            else { cig[o] = 1u << 4; r.cigar_off = (int64_t)o; r.cigar_len = 1; }
+                        } else if (n > 8 || bw > NARROW_BW) { r.status = 7; br.bw = bw; flag_list[atomicAdd(nflag, 1)] = k; }
+                        else {
+                            ref = useq + tk.rf_base + r.ref_begin1;
+                            read = useq + tk.rd_base + r.read_begin1;
+                            score = f.score1; maxv = 0;
+                            state = 1; new_attempt = true;
+                        }
+                    }
                 }
-                wbase = 0; ii = 0; rnext = read[0];
-                new_row = true; new_attempt = false;
+                out[i] = r;
+                if (state != 1) recs[i] = br;
             }
         }
-        if (running && new_row) {
+        if (!__any_sync(0xffffffffu, state != 2)) break;
+        if (state != 1) continue;
+
+        if (new_attempt) {
+            width = bw * 2 + 3;
+            const unsigned long long need = (unsigned long long)sub_read * 8ull;
+            const unsigned long long o = atomicAdd(scratch.used, (need + 15ull) & ~15ull);
+            if (o + need > scratch.bytes) { out[i].status = 5; BandRec br; br.dir_off = 0; br.bw = 0; br.kind = 0; recs[i] = br; state = 0; continue; }
+            dir_off = o;
+            dirrow = reinterpret_cast<unsigned long long*>(scratch.base + o);
+            hb = bufA; hc = bufB;
+            for (int q = 0; q <= width; ++q) { bufA[q * ST] = 0; ebuf[q * ST] = 0; bufB[q * ST] = 0; }
+            win_lo = 0; win_hi = 0;
+            for (int q = 0; q < 16; ++q) {
+                const unsigned long long c = q < sub_ref ? (unsigned long long)ref[q] : 0ull;
+                if (q < 8) win_lo |= c << (8 * q); else win_hi |= c << (8 * (q - 8));
+            }
+            pending = 16 < sub_ref ? ref[16] : 0u;                                       // base that enters the window at the next slide
+            wbase = 0; ii = 0; rnext = read[0];
+            new_row = true; new_attempt = false;
+        }
+        if (new_row) {
             const int beg = max(0, ii - bw);
             end = min(sub_ref - 1, ii + bw);
             const int edge = min(end + 1, width - 1);
@@ -111,21 +137,17 @@ sw_trace_narrow_kernel(const SwTask* __restrict__ order, int ntasks, const int8_
             hdiag = hb[(beg - xp) * ST];                                                     // H(ii-1, beg-1); 0 on the matrix edge
             if (beg > wbase) {                                                               // slide the target window by one base
                 win_lo = (win_lo >> 8) | (win_hi << 56);
-                win_hi >>= 8;
-                const int nb = wbase + 16;
-                if (nb < sub_ref) win_hi |= (unsigned long long)(uint8_t)ref[nb] << 56;
+                win_hi = (win_hi >> 8) | ((unsigned long long)pending << 56);
                 wbase = beg;
+                const int nb = wbase + 16;                                                   // fetched now, needed one row from now
+                pending = nb < sub_ref ? ref[nb] : 0u;
             }
-            {   // scores of this read base against target codes 0..n-1, one byte each
-                const int rc = rnext;
-                rnext = ii + 1 < sub_read ? (int)read[ii + 1] : 0;
-                rscore = 0;
-                for (int t = 0; t < n; ++t) rscore |= (unsigned long long)(uint8_t)smat[t * n + rc] << (8 * t);
-            }
+            rscore = srow[rnext & 7];                                                        // scores of this read base vs target codes 0..7
+            rnext = ii + 1 < sub_read ? read[ii + 1] : 0u;
             dirword = 0;
             new_row = false;
         }
-        if (running) {
+        {
             const int e_idx = j - xp + 1, u = j - xi + 1;
             const int hup = hb[e_idx * ST], eup = ebuf[e_idx * ST];
             const int wpos = j - wbase;
@@ -153,32 +175,54 @@ sw_trace_narrow_kernel(const SwTask* __restrict__ order, int ntasks, const int8_
                 int* tmp = hb; hb = hc; hc = tmp;           // ssw.c:612 (see sw_trace.cuh for why a swap is equivalent)
                 new_row = true;
                 if (++ii >= sub_read) {
-                    bw *= 2;
-                    if (maxv >= score) running = false;                                       // ssw.c:614-615
-                    else if (bw > NARROW_BW) { r.status = 7; running = false; }
-                    else new_attempt = true;
+                    if (maxv >= score) {                                                      // ssw.c:614-615
+                        BandRec br; br.dir_off = dir_off; br.bw = bw; br.kind = 2; recs[i] = br;
+                        state = 0;
+                    } else {
+                        bw *= 2;
+                        if (bw > NARROW_BW) { out[i].status = 7; BandRec br; br.dir_off = 0; br.bw = bw; br.kind = 0; recs[i] = br; flag_list[atomicAdd(nflag, 1)] = kcur; state = 0; }
+                        else new_attempt = true;
+                    }
                 }
             }
         }
     }
-    bw /= 2;
-    if (!valid) return;
-    if (!f.want_rev || r.status != 0 || r.cigar_len == 1 || dirrow == nullptr) { out[i] = r; return; }
+}
 
-    // ---- traceback (ssw.c:618-697): pass 0 counts the CIGAR words, pass 1 writes them back to front
+// ---- traceback (ssw.c:618-697) from the packed direction words: one thread per pair
+__global__ void __launch_bounds__(128)
+sw_band_trace_kernel(const SwTask* __restrict__ order, int ntasks, const FwdResult* __restrict__ fr, const BandRec* __restrict__ recs, Arena scratch,
+                     uint32_t* __restrict__ cig, unsigned long long cig_cap, unsigned long long* __restrict__ cig_used, FinalResult* __restrict__ out)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= ntasks) return;
+    const int i = order[k].out;
+    const BandRec br = recs[i];
+    if (br.kind != 2) return;
+    const FwdResult f = fr[i];
+    FinalResult r = out[i];
+    const int sub_ref = f.ref_end1 - r.ref_begin1 + 1, sub_read = f.read_end1 - r.read_begin1 + 1;
+    const int bw = br.bw, width_d = 2 * bw + 1;
+    const unsigned long long* dirrow = reinterpret_cast<const unsigned long long*>(scratch.base + br.dir_off);
     int l = 0;
     unsigned long long coff = 0;
     for (int pass = 0; pass < 2; ++pass) {
         int ti = sub_read - 1, tj = sub_ref - 1, state = 2, run = 0, cnt = 0;
         int op = 0, prev = 0;                               // BAM codes: 0 = M, 1 = I, 2 = D
+        int cur_row = ti;
+        unsigned long long cur = dirrow[ti], nxt = ti > 0 ? dirrow[ti - 1] : 0ull;      // row ti and, prefetched, row ti-1
         while (ti > 0) {
             // the reference indexes a flat array; cells left or right of the band alias into the neighbouring rows
-            const long long lin = (long long)width_d * ti + (tj - band_x(ti, bw));
-            int cell = 0;
-            if (lin >= 0 && lin < (long long)width_d * sub_read) {
-                const int rr = (int)(lin / width_d), cc = (int)(lin % width_d);
-                cell = (int)((dirrow[rr] >> (4 * cc)) & 15ull);
+            const int cpos = tj - band_x(ti, bw);
+            unsigned long long word;
+            int cc = cpos;
+            if (cpos >= 0 && cpos < width_d) word = cur;
+            else {
+                const long long lin = (long long)width_d * ti + cpos;
+                if (lin >= 0 && lin < (long long)width_d * sub_read) { word = dirrow[lin / width_d]; cc = (int)(lin % width_d); }
+                else { word = 0; cc = 0; }
             }
+            const int cell = (int)((word >> (4 * cc)) & 15ull);
             const int src = cell >> 2;
             int d;
             if (src == 0) d = 0;
@@ -193,6 +237,7 @@ sw_trace_narrow_kernel(const SwTask* __restrict__ order, int ntasks, const int8_
                 case 5: --tj; state = 2; op = 2; break;
                 default: r.status = 3; r.cigar_len = 0; out[i] = r; return;
             }
+            if (ti != cur_row) { cur = nxt; cur_row = ti; nxt = ti > 0 ? dirrow[ti - 1] : 0ull; }
             if (op == prev) ++run;
             else {
                 if (pass) cig[coff + (unsigned)(l - 1 - cnt)] = ((uint32_t)run << 4) | (uint32_t)prev;
