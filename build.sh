@@ -5,6 +5,16 @@
 set -e
 cd "$(dirname "$0")"
 mkdir -p megapath-nano_b200/realign
-NVCC_FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -shared"
-nvcc $NVCC_FLAGS -o megapath-nano_b200/libmpn_ssw.so megapath-nano_b200/csrc/engine.cu megapath-nano_b200/csrc/ssw_abi.cu
+NVCC_FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC $MPN_EXTRA_NVCC_FLAGS"
+OBJ=build/obj${MPN_BUILD_TAG:+_$MPN_BUILD_TAG}
+OUT=${MPN_SSW_OUT:-megapath-nano_b200/libmpn_ssw.so}
+mkdir -p $OBJ
+pids=()
+for f in engine ssw_abi strip_inst_a strip_inst_b strip_inst_c strip_inst_d; do
+    nvcc $NVCC_FLAGS -c -o $OBJ/$f.o megapath-nano_b200/csrc/$f.cu &
+    pids+=($!)
+done
+for p in "${pids[@]}"; do wait $p; done
+nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $OUT $OBJ/engine.o $OBJ/ssw_abi.o $OBJ/strip_inst_a.o $OBJ/strip_inst_b.o $OBJ/strip_inst_c.o $OBJ/strip_inst_d.o
+[ -n "$MPN_SSW_OUT" ] && exit 0
 cp megapath-nano_b200/libmpn_ssw.so megapath-nano_b200/realign/libssw.so

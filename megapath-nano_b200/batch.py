@@ -5,7 +5,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmpn_ssw.so")
+LIB_PATH = os.environ.get("MPN_SSW_LIB") or os.path.join(HERE, "libmpn_ssw.so")   # override: A/B runs of kernel variants
 
 FIELDS = ("score1", "score2", "ref_begin1", "ref_end1", "read_begin1", "read_end1", "ref_end2", "cigarLen")
 

@@ -3,7 +3,7 @@
 // sw_strip16.cuh / sw_wide32.cuh / sw_finish.cuh / sw_trace.cuh, and a missing or failing GPU aborts loudly.
 #include "../../include/mpn_ssw_batch.h"
 #include "sw_common.cuh"
-#include "sw_strip16.cuh"
+#include "strip_table.h"
 #include "sw_wide32.cuh"
 #include "sw_finish.cuh"
 #include "sw_trace.cuh"
@@ -14,6 +14,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <vector>
 
 using namespace mpn;
@@ -66,18 +67,35 @@ struct PinBuf {
     template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
-typedef void (*StripFn)(const SwTask*, int, int*, const int8_t*, const Score16, uint32_t*, SwEnds*);
+constexpr int STRIP_BLOCK_THREADS = 128;   // = STRIP_BLOCK of sw_strip16.cuh (the kernels are compiled in strip_inst_*.cu)
 struct StripCfg { int G, KR, cap; StripFn fn; size_t smem; int blocks_per_sm; };
 
-#define STRIP(KR, G) { G, KR, 2 * G * KR, sw_strip16_kernel<KR, G>, strip16_smem_bytes<KR>(), 0 }
-StripCfg g_strips[] = {
-    STRIP(4, 4),  STRIP(8, 4),                                   //   32,   64 rows
-    STRIP(8, 8),  STRIP(12, 8), STRIP(16, 8), STRIP(20, 8),      //  128 .. 320 rows
-    STRIP(12, 16), STRIP(16, 16), STRIP(20, 16),                 //  384 .. 640 rows
-    STRIP(16, 32), STRIP(20, 32),                                // 1024, 1280 rows
-};
-constexpr int N_STRIPS = sizeof(g_strips) / sizeof(g_strips[0]);
-constexpr int WIDE_BIN = N_STRIPS;       // pseudo-bin of the 32-bit kernel
+// all instantiations of the packed kernel, sorted by the number of read rows one strip covers (cap = 2 * G * KR)
+std::vector<StripCfg> g_strips;
+std::vector<int16_t> g_bin_of_len;       // read length -> index into g_strips (smallest strip that fits)
+int N_STRIPS = 0;
+int WIDE_BIN = 0;                        // pseudo-bin of the 32-bit kernel
+
+void build_strip_table()
+{
+    if (!g_strips.empty()) return;
+    const StripEntry* parts[] = {g_strip_part_a, g_strip_part_b, g_strip_part_c, g_strip_part_d};
+    const int counts[] = {g_strip_part_a_n, g_strip_part_b_n, g_strip_part_c_n, g_strip_part_d_n};
+    for (int p = 0; p < 4; ++p)
+        for (int k = 0; k < counts[p]; ++k) {
+            const StripEntry& e = parts[p][k];
+            g_strips.push_back(StripCfg{e.G, e.KR, 2 * e.G * e.KR, e.fn, e.smem, 1});
+        }
+    std::stable_sort(g_strips.begin(), g_strips.end(), [](const StripCfg& a, const StripCfg& b) { return a.cap < b.cap; });
+    N_STRIPS = (int)g_strips.size();
+    WIDE_BIN = N_STRIPS;
+    g_bin_of_len.assign((size_t)g_strips.back().cap + 1, 0);
+    int k = 0;
+    for (int len = 0; len <= g_strips.back().cap; ++len) {
+        while (g_strips[k].cap < len) ++k;
+        g_bin_of_len[len] = (int16_t)k;
+    }
+}
 
 }  // namespace
 
@@ -88,6 +106,9 @@ struct mpn_engine {
     int64_t launches = 0, pairs = 0, cells = 0, wide_pairs = 0;
     bool occ_done = false;
     bool profile = false;
+    static constexpr int NAUX = 3;                   // side streams: the bins of one score pass run concurrently, so the tail of one launch overlaps the next
+    cudaStream_t aux[NAUX] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[NAUX] = {nullptr, nullptr, nullptr};
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     int ev_valid = 0;
     DevPool pool;
@@ -142,9 +163,16 @@ extern "C" mpn_engine* mpn_engine_create(int device)
     CK(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
     e->stream = e->own_stream;
     for (int k = 1; k < mpn_engine::NSLOT; ++k) CK(cudaStreamCreateWithFlags(&e->slot[k].st, cudaStreamNonBlocking));
+    for (int k = 0; k < mpn_engine::NAUX; ++k) {
+        CK(cudaStreamCreateWithFlags(&e->aux[k], cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&e->ev_join[k], cudaEventDisableTiming));
+    }
+    CK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+    static std::once_flag once;
+    std::call_once(once, build_strip_table);
     for (int c = 0; c < N_STRIPS; ++c) {
         int nb = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, g_strips[c].fn, STRIP_BLOCK, g_strips[c].smem));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, g_strips[c].fn, STRIP_BLOCK_THREADS, g_strips[c].smem));
         g_strips[c].blocks_per_sm = nb > 0 ? nb : 1;
         if (getenv("MPN_VERBOSE")) fprintf(stderr, "[mpn_ssw] strip G=%d KR=%d cap=%d smem=%zu blocks/SM=%d\n", g_strips[c].G, g_strips[c].KR, g_strips[c].cap, g_strips[c].smem, nb);
     }
@@ -156,6 +184,8 @@ extern "C" void mpn_engine_destroy(mpn_engine* e)
     if (!e) return;
     cudaSetDevice(e->device);
     cudaStreamDestroy(e->own_stream);
+    for (int k = 0; k < mpn_engine::NAUX; ++k) { cudaStreamDestroy(e->aux[k]); cudaEventDestroy(e->ev_join[k]); }
+    cudaEventDestroy(e->ev_fork);
     e->pool.clear();
     for (int k = 0; k < mpn_engine::NSLOT; ++k) {
         mpn_engine::Slot& sl = e->slot[k];
@@ -263,13 +293,29 @@ static mpn_batch* upload_impl(mpn_engine* e, int slot_id, const mpn_params* p, c
         cm_total += fl;
         int c = WIDE_BIN;
         // the packed kernel is exact as long as no H can reach the int16 clamp of ssw.c:425 (and the add cannot wrap)
-        if (packed_ok && (std::min(rl, fl) + 1) * maxpos <= 32767) {
-            for (int k = 0; k < N_STRIPS; ++k) if (rl <= g_strips[k].cap) { c = k; break; }
-        }
+        if (packed_ok && (std::min(rl, fl) + 1) * maxpos <= 32767 && rl < (int64_t)g_bin_of_len.size()) c = g_bin_of_len[rl];
         bin[i] = c; bin_count[c]++;
     }
     b->total_cells = cells; b->max_rd = max_rd; b->colrec_words = cm_total;
     b->n_wide_pre = bin_count[WIDE_BIN];
+    {   // a launch with too few tasks cannot fill the GPU and the launches of a batch run back to back: fold thin bins into the next
+        // larger strip (a few more dead rows, far better occupancy).  The largest packed bin keeps whatever it has.
+        const int64_t thin = (int64_t)e->sm_count * 64;
+        std::vector<int> remap(N_STRIPS + 1);
+        for (int c = 0; c <= N_STRIPS; ++c) remap[c] = c;
+        bool any = false;
+        for (int c = 0; c + 1 < N_STRIPS; ++c) {
+            if (bin_count[c] == 0 || bin_count[c] >= thin) continue;
+            int d = c + 1;
+            while (d + 1 < N_STRIPS && bin_count[d] == 0) ++d;
+            if (bin_count[d] == 0) continue;                    // nothing above: keep the bin
+            bin_count[d] += bin_count[c]; bin_count[c] = 0; remap[c] = d; any = true;
+        }
+        if (any) {
+            for (int c = N_STRIPS - 1; c >= 0; --c) remap[c] = remap[c] == c ? c : remap[remap[c]];
+            for (int64_t i = 0; i < npairs; ++i) bin[i] = remap[bin[i]];
+        }
+    }
 
     // ---- task lists in pinned staging: per bin, longest targets first (counting sort on target length) so that the groups of
     //      a warp run in step and the tail of a launch is made of short tasks
@@ -316,7 +362,7 @@ static mpn_batch* upload_impl(mpn_engine* e, int slot_id, const mpn_params* p, c
     pool.take(b->ends_fwd, sizeof(SwEnds) * (size_t)(npairs + 1)); pool.take(b->ends_rev, sizeof(SwEnds) * (size_t)(npairs + 1));
     pool.take(b->colrec, sizeof(uint32_t) * (size_t)(cm_total + 1));
     pool.take(b->fwdres, sizeof(FwdResult) * (size_t)(npairs + 1)); pool.take(b->finalres, sizeof(FinalResult) * (size_t)(npairs + 1));
-    pool.take(b->counters, 256 * sizeof(unsigned long long));
+    pool.take(b->counters, 512 * sizeof(unsigned long long));   // [0,128) misc (arena cursors at 64/65, task cursors at 100..104), [128,256) forward bins, [256,384) reverse bins
     pool.take(b->dmat, (size_t)n * n + 16);
     if (npairs) {
         CK(cudaMemcpyAsync(b->seq.p, reads + read_off[0], reads_bytes, cudaMemcpyHostToDevice, st));
@@ -360,9 +406,18 @@ extern "C" mpn_batch* mpn_batch_upload(mpn_engine* e, const mpn_params* p, const
 static void launch_strips(mpn_batch* b, const SwTask* tasks, bool forward, SwEnds* ends, int counter_base)
 {
     mpn_engine* e = b->e;
-    cudaStream_t st = b->st;
+    cudaStream_t main_st = b->st;
     int slot = counter_base;
-    for (const BinLaunch& bl : b->bins) {
+    // fork: with more than one bin, launches alternate over the side streams (largest strips first) and join back on the batch stream
+    const bool fork = b->bins.size() > 1 && !b->pipelined;
+    if (fork) {
+        CK(cudaEventRecord(e->ev_fork, main_st));
+        for (int k = 0; k < mpn_engine::NAUX; ++k) CK(cudaStreamWaitEvent(e->aux[k], e->ev_fork, 0));
+    }
+    int turn = 0;
+    for (size_t bi = b->bins.size(); bi-- > 0;) {
+        const BinLaunch& bl = b->bins[bi];
+        cudaStream_t st = fork ? e->aux[turn++ % mpn_engine::NAUX] : main_st;
         int* counter = reinterpret_cast<int*>(b->counters.as<unsigned long long>() + slot++);
         if (bl.cfg == WIDE_BIN) {
             launch_wide32_impl(tasks + bl.first, (int)bl.count, counter, b->seq.as<int8_t>(), b->dmat.as<int8_t>(), b->p.n, b->fin.gapO, b->fin.gapE,
@@ -370,14 +425,20 @@ static void launch_strips(mpn_batch* b, const SwTask* tasks, bool forward, SwEnd
             e->wide_pairs += forward ? bl.count : 0;
         } else {
             const StripCfg& c = g_strips[bl.cfg];
-            const int groups_per_block = STRIP_BLOCK / c.G;
+            const int groups_per_block = STRIP_BLOCK_THREADS / c.G;
             int64_t blocks = (bl.count + groups_per_block - 1) / groups_per_block;
             blocks = std::min<int64_t>(blocks, (int64_t)e->sm_count * c.blocks_per_sm);
-            c.fn<<<(unsigned)blocks, STRIP_BLOCK, c.smem, st>>>(tasks + bl.first, (int)bl.count, counter, b->seq.as<int8_t>(), b->sc16,
+            c.fn<<<(unsigned)blocks, STRIP_BLOCK_THREADS, c.smem, st>>>(tasks + bl.first, (int)bl.count, counter, b->seq.as<int8_t>(), b->sc16,
                                                                   forward ? b->colrec.as<uint32_t>() : nullptr, ends);
         }
         CK(cudaGetLastError());
         e->launches++;
+    }
+    if (fork) {
+        for (int k = 0; k < mpn_engine::NAUX; ++k) {
+            CK(cudaEventRecord(e->ev_join[k], e->aux[k]));
+            CK(cudaStreamWaitEvent(main_st, e->ev_join[k], 0));
+        }
     }
 }
 
@@ -389,12 +450,12 @@ extern "C" int mpn_batch_run(mpn_batch* b)
     cudaStream_t st = b->st;
     const int64_t n = b->npairs;
     if (n == 0) { b->ran = true; return 0; }
-    CK(cudaMemsetAsync(b->counters.p, 0, 256 * sizeof(unsigned long long), st));
+    CK(cudaMemsetAsync(b->counters.p, 0, 512 * sizeof(unsigned long long), st));
     PairArrays pa{b->mask.as<int32_t>()};
 
     if (e->profile) { CK(cudaEventRecord(e->ev[0], st)); e->ev_valid = 1; }
     // forward score pass -> ends + column records
-    launch_strips(b, b->tasks_fwd.as<SwTask>(), true, b->ends_fwd.as<SwEnds>(), 0);
+    launch_strips(b, b->tasks_fwd.as<SwTask>(), true, b->ends_fwd.as<SwEnds>(), 128);
     // pairs the packed kernel refused (read code >= 4) are re-run in the 32-bit kernel before anything reads their ends
     launch_wide32_impl(b->tasks_fwd.as<SwTask>(), (int)n, reinterpret_cast<int*>(b->counters.as<unsigned long long>() + 100),
                        b->seq.as<int8_t>(), b->dmat.as<int8_t>(), b->p.n, b->fin.gapO, b->fin.gapE, b->colrec.as<uint32_t>(), b->ends_fwd.as<SwEnds>(),
@@ -414,7 +475,7 @@ extern "C" int mpn_batch_run(mpn_batch* b)
     if (e->profile) { CK(cudaEventRecord(e->ev[2], st)); e->ev_valid = 3; }
     const bool any_rev = !(b->fin.flag == 0);
     if (any_rev) {
-        launch_strips(b, b->tasks_rev.as<SwTask>(), false, b->ends_rev.as<SwEnds>(), 32);
+        launch_strips(b, b->tasks_rev.as<SwTask>(), false, b->ends_rev.as<SwEnds>(), 256);
         launch_wide32_impl(b->tasks_rev.as<SwTask>(), (int)n, reinterpret_cast<int*>(b->counters.as<unsigned long long>() + 101),
                            b->seq.as<int8_t>(), b->dmat.as<int8_t>(), b->p.n, b->fin.gapO, b->fin.gapE, nullptr, b->ends_rev.as<SwEnds>(),
                            b->wide_boundary.as<int>(), b->wide_stride, b->wide_blocks, 1, st);

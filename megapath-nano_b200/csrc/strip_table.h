@@ -1,0 +1,19 @@
+// Table of the packed score-kernel instantiations (sw_strip16.cuh).  The template is instantiated in four translation
+// units (strip_inst_*.cu) only so that they compile in parallel; engine.cu merges the parts into one length-binned table.
+#pragma once
+#include "sw_common.cuh"
+#include <cstddef>
+
+namespace mpn {
+
+typedef void (*StripFn)(const SwTask*, int, int*, const int8_t*, const Score16, uint32_t*, SwEnds*);
+struct StripEntry { int G, KR; StripFn fn; size_t smem; };
+
+extern const StripEntry g_strip_part_a[]; extern const int g_strip_part_a_n;
+extern const StripEntry g_strip_part_b[]; extern const int g_strip_part_b_n;
+extern const StripEntry g_strip_part_c[]; extern const int g_strip_part_c_n;
+extern const StripEntry g_strip_part_d[]; extern const int g_strip_part_d_n;
+
+#define MPN_STRIP_ENTRY(KR, G) { G, KR, sw_strip16_kernel<KR, G>, strip16_smem_bytes<KR, G>() }
+
+}  // namespace mpn

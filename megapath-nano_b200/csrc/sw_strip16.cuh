@@ -29,18 +29,29 @@ namespace mpn {
 
 constexpr int STRIP_BLOCK = 128;
 
-template <int KR>
-__host__ __device__ constexpr size_t strip16_smem_bytes() { return (size_t)2 * (KR / 4) * STRIP_BLOCK * sizeof(uint4); }
+#ifndef MPN_STRIP_UNROLL
+#define MPN_STRIP_UNROLL 1
+#endif
+constexpr int STRIP_UNROLL = MPN_STRIP_UNROLL;
+#ifndef MPN_STRIP_MINB
+#define MPN_STRIP_MINB 4
+#endif
+
+// shared memory: H-column snapshots [2 halves][ceil(KR/4)][STRIP_BLOCK] uint4, then the column-record staging [G][STRIP_BLOCK] words
+template <int KR, int G>
+__host__ __device__ constexpr size_t strip16_smem_bytes() { return (size_t)2 * ((KR + 3) / 4) * STRIP_BLOCK * sizeof(uint4) + (size_t)G * STRIP_BLOCK * sizeof(uint32_t); }
 
 template <int KR, int G>
-__global__ void __launch_bounds__(STRIP_BLOCK, 4)
+__global__ void __launch_bounds__(STRIP_BLOCK, MPN_STRIP_MINB)
 sw_strip16_kernel(const SwTask* __restrict__ tasks, int ntasks, int* __restrict__ counter, const int8_t* __restrict__ seq,
                   const Score16 sc, uint32_t* __restrict__ colrec, SwEnds* __restrict__ out)
 {
-    static_assert(KR % 4 == 0 && KR >= 4, "KR must be a multiple of 4");
+    static_assert(KR >= 2, "KR too small");
+    constexpr int KRQ = (KR + 3) / 4;             // snapshot quads per half
     static_assert(G == 2 || G == 4 || G == 8 || G == 16 || G == 32, "G must divide 32");
     constexpr int CAP = 2 * G * KR;               // rows covered by one strip
-    extern __shared__ uint4 snap[];               // [2 halves][KR/4][STRIP_BLOCK]: H column of a stage at its last improvement
+    extern __shared__ uint4 snap[];               // [2 halves][KRQ][STRIP_BLOCK]: H column of a stage at its last improvement
+    uint32_t* const crow = reinterpret_cast<uint32_t*>(snap + 2 * KRQ * STRIP_BLOCK);   // [G][STRIP_BLOCK]: column records of the last G steps
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -100,14 +111,14 @@ sw_strip16_kernel(const SwTask* __restrict__ tasks, int ntasks, int* __restrict_
                     int row = -999;
                     if (wscore > 0) {
                         const int half = wstage & 1;
-                        const uint4* sp = snap + (size_t)half * (KR / 4) * STRIP_BLOCK + tid;
-                        for (int k = KR / 4 - 1; k >= 0; --k) {
+                        const uint4* sp = snap + (size_t)half * KRQ * STRIP_BLOCK + tid;
+                        for (int k = KRQ - 1; k >= 0; --k) {
                             uint4 v = sp[(size_t)k * STRIP_BLOCK];
                             uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
                             for (int q = 3; q >= 0; --q) {
                                 int hv = half ? (int)(int16_t)(w[q] >> 16) : (int)(int16_t)(w[q] & 0xffffu);
-                                if (hv == wscore) row = wstage * KR + 4 * k + q - dead;
+                                if (4 * k + q < KR && hv == wscore) row = wstage * KR + 4 * k + q - dead;
                             }
                         }
                     }
@@ -176,7 +187,7 @@ sw_strip16_kernel(const SwTask* __restrict__ tasks, int ntasks, int* __restrict_
         }
 
         // ------------------------------------------------------------------ G wavefront steps ---------------------------
-#pragma unroll 1
+#pragma unroll STRIP_UNROLL
         for (int u = 0; u < G; ++u, ++s) {
             {   // the first stage takes the next target base from the chunk, the others got theirs by shuffle last step
                 const uint32_t a0 = __shfl_sync(0xffffffffu, tchunk, u, G);
@@ -195,6 +206,7 @@ sw_strip16_kernel(const SwTask* __restrict__ tasks, int ntasks, int* __restrict_
                 F = addmax_relu(F, sc.mgapE2, Hg);
                 H[j] = Hn;
                 if (j & 1) m = max3(m, H[j - 1], Hn);
+                else if (j == KR - 1) m = max2(m, Hn);                        // odd KR: the last row has no partner
                 h = hnext;
             }
             // ---- per-stage best tracking: strict improvement keeps the first column (ssw.c:269 / :474)
@@ -202,20 +214,22 @@ sw_strip16_kernel(const SwTask* __restrict__ tasks, int ntasks, int* __restrict_
             best = max2_track(best, m, ge_hi, ge_lo);
             if (!ge_lo) {
                 cvlo = (uint32_t)s;
+#ifndef MPN_EXP_NOSNAP
 #pragma unroll
-                for (int k = 0; k < KR / 4; ++k) snap[(size_t)k * STRIP_BLOCK + tid] = make_uint4(H[4 * k], H[4 * k + 1], H[4 * k + 2], H[4 * k + 3]);
+                for (int k = 0; k < KRQ; ++k) snap[(size_t)k * STRIP_BLOCK + tid] = make_uint4(H[4 * k], H[min(4 * k + 1, KR - 1)], H[min(4 * k + 2, KR - 1)], H[min(4 * k + 3, KR - 1)]);
+#endif
             }
             if (!ge_hi) {
                 cvhi = (uint32_t)s;
+#ifndef MPN_EXP_NOSNAP
 #pragma unroll
-                for (int k = 0; k < KR / 4; ++k) snap[(size_t)(KR / 4 + k) * STRIP_BLOCK + tid] = make_uint4(H[4 * k], H[4 * k + 1], H[4 * k + 2], H[4 * k + 3]);
+                for (int k = 0; k < KRQ; ++k) snap[(size_t)(KRQ + k) * STRIP_BLOCK + tid] = make_uint4(H[4 * k], H[min(4 * k + 1, KR - 1)], H[min(4 * k + 2, KR - 1)], H[min(4 * k + 3, KR - 1)]);
+#endif
             }
             const uint32_t cmout = max2(cmin, m);
-            // ---- last stage: record (column maximum, bottom-row H) of column s - (2G-1)
-            if (t == G - 1) {
-                const int c = s - (2 * G - 1);
-                if (cm_off >= 0 && c >= 0 && c < rf_len) colrec[cm_off + c] = prmt(cmout, H[KR - 1], 0x7632u);
-            }
+            // ---- (column maximum, bottom-row H) of this step: staged in shared memory by every thread, only the last stage's
+            //      entry is a finished column (s - (2G-1)); the group writes G of them to global memory after the loop
+            crow[u * STRIP_BLOCK + tid] = prmt(cmout, H[KR - 1], 0x7632u);
             // ---- hand the boundary to the next stage
             const uint32_t rF = __shfl_up_sync(0xffffffffu, F, 1, G);
             const uint32_t rH = __shfl_up_sync(0xffffffffu, Hdtop, 1, G);
@@ -227,6 +241,14 @@ sw_strip16_kernel(const SwTask* __restrict__ tasks, int ntasks, int* __restrict_
             b = a;
             a = rA;
         }
+        // ---- column records of the G steps just done: thread t of the group stores the one of step s - G + t (one 4*G-byte run per group)
+        __syncwarp();
+        if (cm_off >= 0) {
+            const int c = s - G + t - (2 * G - 1);
+            const uint32_t v = crow[t * STRIP_BLOCK + tid - t + (G - 1)];
+            if (c >= 0 && c < rf_len) colrec[cm_off + c] = v;
+        }
+        __syncwarp();
     }
 }
 
