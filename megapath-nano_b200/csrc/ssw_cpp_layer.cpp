@@ -1,0 +1,244 @@
+// C++ front end (include/ssw_cpp.h) over the batched GPU engine.  Mirrors StripedSmithWaterman::Aligner of the reference
+// (ssw_cpp.cpp:214-477): translation, the flag/filter mapping of SetFlag (:209-212), and the post-processing that turns the
+// raw M/I/D words of ssw_align into the soft-clipped '=' / 'X' CIGAR plus a mismatch count (ConvertAlignment :50-86,
+// CalculateNumberMismatch :123-207).  Host code only: every DP cell is computed by the CUDA kernels behind mpn_align_batch.
+#include "../../include/ssw_cpp.h"
+#include "../../include/mpn_ssw_batch.h"
+#include "host_shared.h"
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+namespace StripedSmithWaterman {
+
+namespace {
+
+// ASCII -> {A0 C1 G2 T3 N4}; U/u read as A exactly like the reference table (ssw_cpp.cpp:8-21)
+void fill_dna_translation(std::vector<int8_t>& t)
+{
+    t.assign(128, 4);
+    const char* letters = "AaCcGgTtUu";
+    const int8_t codes[] = {0, 0, 1, 1, 2, 2, 3, 3, 0, 0};
+    for (int k = 0; letters[k]; ++k) t[(unsigned char)letters[k]] = codes[k];
+}
+
+void fill_dna_matrix(std::vector<int8_t>& m, uint8_t match, uint8_t mismatch)
+{
+    // 5 x 5: +match on the ACGT diagonal, -mismatch everywhere else including the whole N row and column (ssw_cpp.cpp:23-48)
+    m.assign(25, (int8_t)(-(int)mismatch));
+    for (int i = 0; i < 4; ++i) m[i * 5 + i] = (int8_t)match;
+}
+
+inline void append_run(std::string& s, std::vector<uint32_t>& words, uint32_t len, char op, uint32_t code)
+{
+    char buf[16];
+    const int k = snprintf(buf, sizeof buf, "%u%c", len, op);
+    s.append(buf, (size_t)k);
+    words.push_back((len << 4) | code);
+}
+
+}  // namespace
+
+// raw engine record -> Alignment, identical to ConvertAlignment followed by CalculateNumberMismatch
+void finish_alignment(const mpn_result& r, const uint32_t* cigar_arena, const int8_t* ref, const int8_t* query, int query_len, Alignment* al)
+{
+    al->Clear();
+    al->sw_score = r.score1; al->sw_score_next_best = r.score2;
+    al->ref_begin = r.ref_begin1; al->ref_end = r.ref_end1;
+    al->query_begin = r.read_begin1; al->query_end = r.read_end1;
+    al->ref_end_next_best = r.ref_end2;
+    enum { OP_EQ = 7, OP_X = 8, OP_S = 4 };
+    std::string& s = al->cigar_string;
+    std::vector<uint32_t>& w = al->cigar;
+    if (al->query_begin > 0) append_run(s, w, (uint32_t)al->query_begin, 'S', OP_S);
+    int mism = 0;
+    // With a negative begin (not computed, or score 0) the reference walks from ref[-1]; there is no M run longer than the
+    // "1M" placeholder in that case and the comparison it makes is between out-of-bounds bytes: treat that one base as a match.
+    const bool walkable = r.ref_begin1 >= 0 && r.read_begin1 >= 0;
+    const int8_t* tp = ref + (walkable ? r.ref_begin1 : 0);
+    const int8_t* qp = query + (walkable ? r.read_begin1 : 0);
+    uint32_t run = 0; bool run_is_x = false;
+    auto flush = [&]() { if (run) append_run(s, w, run, run_is_x ? 'X' : '=', run_is_x ? OP_X : OP_EQ); run = 0; };
+    for (int k = 0; k < r.cigar_len; ++k) {
+        const uint32_t word = cigar_arena[r.cigar_off + k];
+        const uint32_t len = word >> 4, op = word & 15u;
+        if (op == 0) {
+            for (uint32_t j = 0; j < len; ++j) {
+                const bool x = walkable ? (*tp != *qp) : false;
+                if (run && x != run_is_x) flush();
+                run_is_x = x; ++run; mism += x;
+                ++tp; ++qp;
+            }
+        } else if (op == 1) {
+            flush(); qp += len; mism += (int)len; append_run(s, w, len, 'I', 1);
+        } else if (op == 2) {
+            flush(); tp += len; mism += (int)len; append_run(s, w, len, 'D', 2);
+        }
+    }
+    flush();
+    const int tail = query_len - al->query_end - 1;
+    if (tail > 0) append_run(s, w, (uint32_t)tail, 'S', OP_S);
+    al->mismatches = mism;
+}
+
+Aligner::Aligner(void) { default_tables(); }
+
+Aligner::Aligner(const uint8_t& match_score, const uint8_t& mismatch_penalty, const uint8_t& gap_opening_penalty, const uint8_t& gap_extending_penalty)
+    : match_(match_score), mismatch_(mismatch_penalty), gap_open_(gap_opening_penalty), gap_extend_(gap_extending_penalty)
+{
+    default_tables();
+}
+
+Aligner::Aligner(const int8_t* score_matrix, const int& score_matrix_size, const int8_t* translation_matrix, const int& translation_matrix_size)
+    : n_(score_matrix_size)
+{
+    matrix_.assign(score_matrix, score_matrix + (size_t)n_ * n_);
+    translate_.assign(translation_matrix, translation_matrix + translation_matrix_size);
+}
+
+Aligner::~Aligner(void) {}
+
+void Aligner::default_tables()
+{
+    n_ = 5;
+    fill_dna_matrix(matrix_, match_, mismatch_);
+    fill_dna_translation(translate_);
+}
+
+static inline void translate_into(const std::vector<int8_t>& table, const char* s, int len, int8_t* out)
+{
+    const int tn = (int)table.size();
+    for (int i = 0; i < len; ++i) {
+        const int c = (unsigned char)s[i];
+        out[i] = c < tn ? table[c] : table[tn - 1];
+    }
+}
+
+int Aligner::SetReferenceSequence(const char* seq, const int& length)
+{
+    reference_.clear();
+    if (translate_.empty() || length <= 0) return 0;
+    reference_.resize((size_t)length);
+    translate_into(translate_, seq, length, reference_.data());
+    return length;
+}
+
+void Aligner::CleanReferenceSequence(void) { reference_.clear(); }
+
+bool Aligner::AlignPairs(const std::vector<PairView>& pairs, const Filter& filter, std::vector<Alignment>* out) const
+{
+    if (translate_.empty() || !out) return false;
+    const size_t np = pairs.size();
+    out->assign(np, Alignment());
+    // pack: skip empty queries (Align returns false for them) but keep their slot
+    std::vector<int64_t> qoff(1, 0), toff(1, 0);
+    std::vector<int32_t> mask; std::vector<size_t> slot;
+    size_t qbytes = 0, tbytes = 0;
+    for (const PairView& p : pairs) if (p.query_len > 0) { qbytes += (size_t)p.query_len; tbytes += (size_t)p.ref_len; }
+    std::vector<int8_t> q(qbytes + 1), t(tbytes + 1);
+    for (size_t i = 0; i < np; ++i) {
+        const PairView& p = pairs[i];
+        if (p.query_len <= 0) continue;
+        translate_into(translate_, p.query, p.query_len, q.data() + qoff.back());
+        // a target that is the aligner's stored reference is already translated
+        if (p.ref == nullptr) memcpy(t.data() + toff.back(), reference_.data(), (size_t)p.ref_len);
+        else translate_into(translate_, p.ref, p.ref_len, t.data() + toff.back());
+        qoff.push_back(qoff.back() + p.query_len); toff.push_back(toff.back() + p.ref_len);
+        mask.push_back(p.query_len);                       // maskLen = query_len (ssw_cpp.cpp:346)
+        slot.push_back(i);
+    }
+    const int64_t n = (int64_t)slot.size();
+    if (n == 0) return true;
+    uint8_t flag = 0;                                      // SetFlag, ssw_cpp.cpp:209-212
+    if (filter.report_begin_position) flag |= 0x08;
+    if (filter.report_cigar) flag |= 0x0f;
+    mpn_params pr;
+    pr.mat = matrix_.data(); pr.n = n_; pr.gapO = gap_open_; pr.gapE = gap_extend_; pr.score_size = 2;
+    pr.flag = flag; pr.filters = filter.score_filter; pr.filterd = filter.distance_filter;
+    std::vector<mpn_result> res((size_t)n);
+    std::vector<uint32_t> arena((size_t)(n * 24 + (int64_t)qbytes / 4 + 4096));
+    int rc;
+    for (int attempt = 0;; ++attempt) {
+        mpn::SharedEngineLock lk;
+        rc = mpn_align_batch(lk.engine(), &pr, q.data(), qoff.data(), t.data(), toff.data(), mask.data(), n, res.data(), arena.data(), (int64_t)arena.size());
+        if (rc != MPN_E_CIGAR_SPACE || attempt == 1) break;
+        arena.resize((size_t)(2 * ((int64_t)qbytes + (int64_t)tbytes) + 16 * n));        // always enough: a CIGAR has at most read + target runs
+    }
+    if (rc != 0) {
+        fprintf(stderr, "[ssw_cpp] GPU alignment failed (code %d); this library has no CPU fallback\n", rc);
+        abort();
+    }
+    for (int64_t k = 0; k < n; ++k) {
+        const PairView& p = pairs[slot[k]];
+        if (res[k].status != MPN_ST_OK) {                  // the reference dereferences a NULL s_align here; fail loudly instead
+            fprintf(stderr, "[ssw_cpp] ssw_align returned no result for pair %lld\n", (long long)slot[k]);
+            abort();
+        }
+        finish_alignment(res[k], arena.data(), t.data() + toff[k], q.data() + qoff[k], p.query_len, &(*out)[slot[k]]);
+    }
+    return true;
+}
+
+bool Aligner::AlignBatch(const std::vector<std::string>& queries, const Filter& filter, std::vector<Alignment>* out) const
+{
+    if (translate_.empty() || reference_.empty()) return false;
+    std::vector<PairView> pv(queries.size());
+    for (size_t i = 0; i < queries.size(); ++i) pv[i] = PairView{queries[i].c_str(), (int)strlen(queries[i].c_str()), nullptr, (int)reference_.size()};
+    return AlignPairs(pv, filter, out);
+}
+
+bool Aligner::Align(const char* query, const Filter& filter, Alignment* alignment) const
+{
+    if (translate_.empty() || reference_.empty()) return false;
+    const int qlen = (int)strlen(query);
+    if (qlen == 0) return false;
+    std::vector<PairView> pv(1, PairView{query, qlen, nullptr, (int)reference_.size()});
+    std::vector<Alignment> res;
+    if (!AlignPairs(pv, filter, &res)) return false;
+    *alignment = res[0];
+    return true;
+}
+
+bool Aligner::Align(const char* query, const char* ref, const int& ref_len, const Filter& filter, Alignment* alignment) const
+{
+    if (translate_.empty()) return false;
+    const int qlen = (int)strlen(query);
+    if (qlen == 0) return false;
+    std::vector<PairView> pv(1, PairView{query, qlen, ref, ref_len});
+    std::vector<Alignment> res;
+    if (!AlignPairs(pv, filter, &res)) return false;
+    *alignment = res[0];
+    return true;
+}
+
+void Aligner::Clear(void)
+{
+    matrix_.clear(); translate_.clear(); reference_.clear();
+}
+
+bool Aligner::ReBuild(void)
+{
+    if (!translate_.empty()) return false;
+    match_ = 4; mismatch_ = 6; gap_open_ = 8; gap_extend_ = 2;
+    default_tables();
+    return true;
+}
+
+bool Aligner::ReBuild(const uint8_t& match_score, const uint8_t& mismatch_penalty, const uint8_t& gap_opening_penalty, const uint8_t& gap_extending_penalty)
+{
+    if (!translate_.empty()) return false;
+    match_ = match_score; mismatch_ = mismatch_penalty; gap_open_ = gap_opening_penalty; gap_extend_ = gap_extending_penalty;
+    default_tables();
+    return true;
+}
+
+bool Aligner::ReBuild(const int8_t* score_matrix, const int& score_matrix_size, const int8_t* translation_matrix, const int& translation_matrix_size)
+{
+    n_ = score_matrix_size;
+    matrix_.assign(score_matrix, score_matrix + (size_t)n_ * n_);
+    translate_.assign(translation_matrix, translation_matrix + translation_matrix_size);
+    return true;
+}
+
+}  // namespace StripedSmithWaterman

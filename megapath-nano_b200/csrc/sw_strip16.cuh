@@ -30,7 +30,7 @@ namespace mpn {
 constexpr int STRIP_BLOCK = 128;
 
 #ifndef MPN_STRIP_UNROLL
-#define MPN_STRIP_UNROLL 1
+#define MPN_STRIP_UNROLL 2
 #endif
 constexpr int STRIP_UNROLL = MPN_STRIP_UNROLL;
 #ifndef MPN_STRIP_MINB
@@ -127,6 +127,9 @@ sw_strip16_kernel(const SwTask* __restrict__ tasks, int ntasks, int* __restrict_
                     e.col = wscore > 0 ? wcol : -1;
                     e.row = wscore > 0 ? row : 0;
                     e.flags = anywide ? SW_FLAG_NEEDS_WIDE : 0;
+#ifdef MPN_EXP_CLAMP                                                              // timing experiments with deliberately wrong kernels: keep later passes in bounds
+                    if (wscore > 0) { e.col = min(max(e.col, 0), rf_len - 1); e.row = min(max(e.row, 0), CAP - dead - 1); }
+#endif
                     out[tout] = e;
                 }
             }
@@ -229,12 +232,18 @@ sw_strip16_kernel(const SwTask* __restrict__ tasks, int ntasks, int* __restrict_
             const uint32_t cmout = max2(cmin, m);
             // ---- (column maximum, bottom-row H) of this step: staged in shared memory by every thread, only the last stage's
             //      entry is a finished column (s - (2G-1)); the group writes G of them to global memory after the loop
+#ifndef MPN_EXP_NOCROW
             crow[u * STRIP_BLOCK + tid] = prmt(cmout, H[KR - 1], 0x7632u);
+#endif
             // ---- hand the boundary to the next stage
+#ifdef MPN_EXP_NOSHFL
+            const uint32_t rF = F ^ 1u, rH = Hdtop, rC = cmout, rA = b;
+#else
             const uint32_t rF = __shfl_up_sync(0xffffffffu, F, 1, G);
             const uint32_t rH = __shfl_up_sync(0xffffffffu, Hdtop, 1, G);
             const uint32_t rC = __shfl_up_sync(0xffffffffu, cmout, 1, G);
             const uint32_t rA = __shfl_up_sync(0xffffffffu, b, 1, G);
+#endif
             Ftop = prmt(rF, F, mergeSel);
             Hdtop = prmt(rH, Hdtop, mergeSel);
             cmin = prmt(rC, cmout, mergeSel);

@@ -174,3 +174,36 @@ def test_pyssw_mirror(eng):
         r = pyssw.SSW(lib_path=oracle.ref_path())
         r.set_reference_sequence(ref)
         assert [r.align(q) for q in queries[:6]] == single[:6]
+
+
+@pytest.mark.parametrize("flag,match,mismatch", [(0, 4, 6), (1, 4, 6), (1, 2, 3)])
+def test_config4_ont_scale(eng, flag, match, mismatch):
+    """BASELINE configs[3]: 10 kb reads at 8 % error vs 12 kb windows.  match=4 puts score1 on the int16 clamp of ssw.c:425
+    (32-bit kernel with the clamp); match=2 stays below it (long un-saturated path).  flag 1 adds the reverse pass + wide-band traceback."""
+    b = w.config4(12, seed=14 + flag + match, match=match, mismatch=mismatch, flag=flag)
+    cap = 4096
+    g, gc, rec, _ = gpu_table(eng, b, cap=cap)
+    r, c = oracle_table(b, cap=cap, threads=os.cpu_count() or 8)
+    bad = diff(g, gc, r, c)
+    assert len(bad) == 0, (bad[:5], g[bad[:2]], r[bad[:2]])
+    if match == 4:
+        assert int(rec["score1"].max()) >= 32000
+    if flag:
+        assert int(rec["cigar_len"].min()) > 100
+
+
+def test_config5_mixed_lengths_sample(eng):
+    """BASELINE configs[4] on a seeded sample: read length log-uniform on [100, 20000], target = 1.2 x read, 5 % errors, flag 0 for the
+    bulk and flag 1 on a subsample -- every length bin of the scheduler (packed strips, 32-bit kernel, clamp) in one batch."""
+    b = w.config5(600, seed=15, flag=0)
+    g, gc, _, _ = gpu_table(eng, b)
+    r, c = oracle_table(b, threads=os.cpu_count() or 8)
+    bad = diff(g, gc, r, c)
+    assert len(bad) == 0, (bad[:5], g[bad[:2]], r[bad[:2]], b.read_len[bad[:5]])
+    sub = b.subset(np.arange(0, 600, 5))
+    sub.flag = 1
+    cap = 8192
+    g, gc, _, _ = gpu_table(eng, sub, cap=cap)
+    r, c = oracle_table(sub, cap=cap, threads=os.cpu_count() or 8)
+    bad = diff(g, gc, r, c)
+    assert len(bad) == 0, (bad[:5], g[bad[:2]], r[bad[:2]], sub.read_len[bad[:5]])
