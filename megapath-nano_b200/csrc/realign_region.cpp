@@ -1,0 +1,544 @@
+// Region realigner on the batched GPU engine: the host logic around the Smith-Waterman calls of the reference's
+// realigner.cpp, reorganised so that every alignment of a region (or of many regions) is ONE submit to the CUDA kernels.
+//
+// Per region, in the reference's order (ReAligner::AlignReads, realigner.cpp:88-117):
+//   1. k-mer index over the reads (k = 32, BuildIndex :429-451) and the <= 2-mismatch ungapped "fast pass" of every read
+//      against every haplotype (FastAlignReadsToHaplotype :170-230, FastAlignStrings :232-253)                    [host]
+//   2. haplotype -> reference alignments (AlignHaplotypesToReference :325-349) and, for reads the fast pass could not
+//      place, read -> haplotype alignments (SswAlignReadsToHaplotypes :351-384)                      [GPU, one batch]
+//   3. haplotype position maps (SetPositionsMap :453-509), best haplotype per read (GetBestReadAlignment :517-540) and
+//      composition of read->haplotype with haplotype->reference CIGARs (CalculateReadToRefAlignment :640-777)     [host]
+// Steps 1 and 3 are plain host code written against flat vectors (no std::list / std::regex); step 2 never runs on the CPU.
+#include "../../include/realigner.h"
+#include "../../include/ssw_cpp.h"
+
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <deque>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+namespace {
+
+using StripedSmithWaterman::Alignment;
+using StripedSmithWaterman::PairView;
+
+// ---- options fixed by ReAligner::set_options (realigner.cpp:62-72)
+constexpr int kKmer = 32;
+constexpr int kNominalReadSize = 250;
+constexpr int kMaxMismatches = 2;
+constexpr double kSimilarity = 0.16934;
+constexpr int kMatch = 4, kMismatch = 6, kGapOpen = 8, kGapExtend = 2;
+constexpr int kNotPlaced = -1;
+
+enum OpKind : int { OP_NONE = 0, OP_MATCH = 1, OP_INS = 2, OP_DEL = 3, OP_SKIP = 4, OP_SOFT = 5, OP_HARD = 6 };
+struct Op { OpKind kind; int len; };
+
+struct Placement {          // a read on a haplotype (ReadAlignment, realigner.h:103-127)
+    int pos = kNotPlaced;
+    int score = 0;
+    std::string cigar;
+    void reset() { pos = kNotPlaced; score = 0; cigar.clear(); }
+};
+
+struct HapRecord {          // HaplotypeReadsAlignment, realigner.h:163-211
+    int index = 0;
+    int score = 0;
+    std::vector<Placement> reads;
+    std::string cigar;      // haplotype -> reference
+    std::vector<Op> ops;
+    int ref_pos = 0;
+    std::vector<int> shift; // hap position -> cumulative shift against the reference
+    bool is_reference = false;
+    bool operator<(const HapRecord& o) const { return score < o.score; }
+};
+
+int ssw_score_threshold()
+{
+    // realigner.cpp:74-84: evaluated in double, truncated, floored at 1
+    int t = kMatch * kNominalReadSize * kSimilarity - kMismatch * kNominalReadSize * (1 - kSimilarity);
+    return t < 0 ? 1 : t;
+}
+
+// "<digits><op>" tokens with op in [XIDS=] (either case); anything else is skipped, like the reference's regex_search loop
+// (realigner.cpp:272-291).  Lower-case letters tokenise but map to OP_NONE (CigarOperationFromChar :255-270 is case sensitive).
+template <class F> void scan_cigar(const std::string& s, F&& emit)
+{
+    const size_t n = s.size();
+    size_t i = 0;
+    while (i < n) {
+        if (s[i] < '0' || s[i] > '9') { ++i; continue; }
+        size_t j = i;
+        while (j < n && s[j] >= '0' && s[j] <= '9') ++j;
+        if (j < n && strchr("XIDS=xids", s[j])) {
+            emit(atoi(s.substr(i, j - i).c_str()), s[j]);
+            i = j + 1;
+        } else {
+            i = j;
+        }
+    }
+}
+
+OpKind kind_of(char c)
+{
+    switch (c) {
+        case '=': case 'X': return OP_MATCH;
+        case 'S': return OP_SOFT;
+        case 'D': return OP_DEL;
+        case 'I': return OP_INS;
+        default: return OP_NONE;
+    }
+}
+
+std::vector<Op> parse_ops(const std::string& s)
+{
+    std::vector<Op> v;
+    scan_cigar(s, [&](int len, char c) { v.push_back(Op{kind_of(c), len}); });
+    return v;
+}
+
+std::string ops_to_string(const std::vector<Op>& ops)      // CigarVectorToString, realigner.cpp:294-317 (matches print as X)
+{
+    std::string out;
+    for (const Op& o : ops) {
+        out += std::to_string(o.len);
+        switch (o.kind) {
+            case OP_MATCH: out += 'X'; break;
+            case OP_INS: out += 'I'; break;
+            case OP_DEL: out += 'D'; break;
+            case OP_SOFT: out += 'S'; break;
+            default: break;
+        }
+    }
+    return out;
+}
+
+// ------------------------------------------------------------------------------------------------ k-mer index
+// The reference keys an unordered_map by the 32-character substring.  Here: k-mers made only of A/C/G/T pack into one
+// 64-bit word (sorted array + binary search, occurrences kept in insertion order = (read, offset) ascending); k-mers with
+// any other character (N, lower case) go to a small string-keyed map so that equality stays exact string equality.
+struct Occurrence { uint64_t key; int read; int offset; };
+
+inline int base2(char c)
+{
+    switch (c) { case 'A': return 0; case 'C': return 1; case 'G': return 2; case 'T': return 3; default: return -1; }
+}
+
+struct KmerIndex {
+    std::vector<Occurrence> packed;
+    std::unordered_map<std::string, std::vector<Occurrence>> odd;
+
+    void build(const std::vector<std::string>& reads)
+    {
+        size_t total = 0;
+        for (const std::string& r : reads) if ((int)r.size() > kKmer) total += r.size() - kKmer + 1;
+        packed.reserve(total);
+        for (int id = 0; id < (int)reads.size(); ++id) {
+            const std::string& r = reads[id];
+            if (r.length() <= (size_t)kKmer) continue;                      // AddReadToIndex, realigner.cpp:436-438
+            uint64_t key = 0; int valid = 0;
+            for (int i = 0; i < (int)r.size(); ++i) {
+                const int b = base2(r[i]);
+                if (b < 0) { valid = 0; key = 0; } else { key = (key << 2) | (uint64_t)b; ++valid; }
+                const int start = i - kKmer + 1;
+                if (start < 0) continue;
+                if (valid >= kKmer) packed.push_back(Occurrence{key, id, start});
+                else odd[r.substr((size_t)start, kKmer)].push_back(Occurrence{0, id, start});
+            }
+        }
+        std::stable_sort(packed.begin(), packed.end(), [](const Occurrence& a, const Occurrence& b) { return a.key < b.key; });
+    }
+
+    // occurrences of the k-mer starting at hap[i]; `key`/`valid` are the caller's rolling state for that window
+    std::pair<const Occurrence*, const Occurrence*> find(const std::string& hap, int i, uint64_t key, bool valid) const
+    {
+        if (valid) {
+            auto lo = std::lower_bound(packed.begin(), packed.end(), key, [](const Occurrence& a, uint64_t k) { return a.key < k; });
+            auto hi = lo;
+            while (hi != packed.end() && hi->key == key) ++hi;
+            return {packed.data() + (lo - packed.begin()), packed.data() + (hi - packed.begin())};
+        }
+        if (odd.empty()) return {nullptr, nullptr};
+        auto it = odd.find(hap.substr((size_t)i, kKmer));
+        if (it == odd.end()) return {nullptr, nullptr};
+        return {it->second.data(), it->second.data() + it->second.size()};
+    }
+};
+
+// ungapped comparison, FastAlignStrings (realigner.cpp:232-253): N on either side counts as a match; gives up at the
+// (max+1)-th mismatch with score 0
+int fast_compare(const char* hap, const char* read, int len, int give_up_at, int* mism)
+{
+    int same = 0;
+    *mism = 0;
+    for (int i = 0; i < len; ++i) {
+        const char a = hap[i], b = read[i];
+        if (a != b && a != 'N' && b != 'N') {
+            if (++*mism == give_up_at) return 0;
+        } else {
+            ++same;
+        }
+    }
+    return same * kMatch - *mism * kMismatch;
+}
+
+struct Region {
+    std::string reference;
+    std::vector<std::string> haplotypes;
+    std::vector<std::string> reads;
+    std::vector<int> in_pos;
+    std::vector<std::string> in_cigar;
+    int ref_start = 0, prefix = 0, suffix = 0;
+    // state
+    std::vector<HapRecord> haps;
+    // the Smith-Waterman work of this region inside the global batch
+    size_t first_pair = 0;
+    std::vector<std::pair<int, int>> read_hap_pairs;     // (read, index into haps) in the reference's loop order
+};
+
+// fast pass of every read against one haplotype (realigner.cpp:170-230)
+void fast_pass_one(const Region& rg, const KmerIndex& index, const std::string& hap, int* hap_score, std::vector<Placement>* placed)
+{
+    const bool is_ref = hap == rg.reference;
+    std::vector<int> coverage(hap.size(), 0);
+    if (hap.length() < (size_t)kKmer) return;            // the reference's unsigned loop bound wraps here and throws; nothing sensible to reproduce
+    const int last = (int)hap.length() - kKmer;
+    uint64_t key = 0; int valid = 0;
+    for (int i = 0; i < kKmer - 1; ++i) {
+        const int b = base2(hap[i]);
+        if (b < 0) { valid = 0; key = 0; } else { key = (key << 2) | (uint64_t)b; ++valid; }
+    }
+    for (int i = 0; i <= last; ++i) {
+        const int b = base2(hap[i + kKmer - 1]);
+        if (b < 0) { valid = 0; key = 0; } else { key = (key << 2) | (uint64_t)b; ++valid; }
+        auto range = index.find(hap, i, key, valid >= kKmer);
+        if (range.first == range.second) continue;       // no read shares this k-mer: the coverage test below is skipped too
+        for (const Occurrence* oc = range.first; oc != range.second; ++oc) {
+            const std::string& read = rg.reads[oc->read];
+            const int start = std::max(0, i - oc->offset);
+            const int rlen = (int)read.size();
+            if ((size_t)start + (size_t)rlen > hap.length()) continue;
+            Placement& pl = (*placed)[oc->read];
+            if (pl.pos != kNotPlaced && pl.pos == start) continue;
+            int mism = 0;
+            const int sc = fast_compare(hap.data() + start, read.data(), rlen, kMaxMismatches + 1, &mism);
+            if (mism <= kMaxMismatches) {
+                const int old = pl.score;
+                for (int p = start; p < start + rlen; ++p) coverage[p]++;
+                if (old < sc) {
+                    pl.score = sc;
+                    *hap_score += sc - old;
+                    pl.pos = start;
+                    pl.cigar = std::to_string(rlen) + "=";
+                }
+            }
+        }
+        if (coverage[i] == 0 && i >= rg.prefix && (size_t)i < hap.size() - (size_t)rg.suffix && !is_ref) {
+            *hap_score = 0;                               // a non-reference haplotype with an uncovered base inside the window is dropped
+            return;
+        }
+    }
+}
+
+void fast_pass(Region& rg)
+{
+    KmerIndex index;
+    index.build(rg.reads);
+    std::vector<Placement> placed(rg.reads.size());
+    rg.haps.clear();
+    rg.haps.reserve(rg.haplotypes.size());
+    for (int h = 0; h < (int)rg.haplotypes.size(); ++h) {
+        for (Placement& p : placed) p.reset();
+        int score = 0;
+        fast_pass_one(rg, index, rg.haplotypes[h], &score, &placed);
+        if (score == 0) for (Placement& p : placed) p.reset();
+        HapRecord rec;
+        rec.index = h; rec.score = score; rec.reads = placed;
+        rg.haps.push_back(std::move(rec));
+    }
+}
+
+// which (read, haplotype) pairs need Smith-Waterman (realigner.cpp:351-366)
+void plan_read_pairs(Region& rg)
+{
+    rg.read_hap_pairs.clear();
+    for (int r = 0; r < (int)rg.reads.size(); ++r) {
+        bool placed = false;
+        for (const HapRecord& h : rg.haps) if (h.reads[r].score > 0) { placed = true; break; }
+        if (placed) continue;
+        for (int k = 0; k < (int)rg.haps.size(); ++k) if (rg.haps[k].score != 0) rg.read_hap_pairs.push_back({r, k});
+    }
+}
+
+// hap position -> shift against the reference, SetPositionsMap (realigner.cpp:453-509)
+void build_shift_map(HapRecord& h, int hap_len)
+{
+    h.shift.assign((size_t)hap_len, 0);
+    int shift = 0, pos = 0;
+    auto put = [&](int p, int v) { if (p >= 0 && p < hap_len) h.shift[p] = v; };
+    scan_cigar(h.cigar, [&](int len, char c) {
+        switch (c) {
+            case '=': case 'X': for (int e = pos + len; pos != e; ++pos) put(pos, shift); break;
+            case 'S': shift -= len; for (int e = pos + len; pos != e; ++pos) put(pos, shift); break;
+            case 'D': shift += len; break;
+            case 'I': for (int e = pos + len; pos != e; ++pos) { put(pos, shift); --shift; } break;
+            default: break;
+        }
+    });
+}
+
+// ---- CIGAR composition.  `out` plus the number of read bases it already covers (deletions cover none).
+struct Composed {
+    std::vector<Op> ops;
+    int covered = 0;
+    // MergeCigarOp (realigner.cpp:553-577): clip to the read length, fuse with an equal trailing op
+    void merge(OpKind kind, int len, int read_len)
+    {
+        const OpKind last = ops.empty() ? OP_NONE : ops.back().kind;
+        const int before = covered;
+        const int take = kind != OP_DEL ? std::min(len, read_len - before) : len;
+        if (take <= 0 || before == read_len) return;
+        if (kind == last) ops.back().len += take; else ops.push_back(Op{kind, take});
+        if (kind != OP_DEL) covered += take;
+    }
+};
+
+inline bool matchlike(const Op& o) { return o.kind == OP_MATCH || o.kind == OP_SOFT; }
+
+// drop the part of the haplotype->reference CIGAR left of the read's start on the haplotype (realigner.cpp:581-612)
+std::deque<Op> trim_left(const std::vector<Op>& hap_ops, int read_pos, bool* ok)
+{
+    std::deque<Op> q(hap_ops.begin(), hap_ops.end());
+    int cur = 0;
+    *ok = true;
+    while (cur != read_pos) {
+        if (q.empty()) { *ok = false; return q; }           // the reference reads front() of an empty list here (undefined)
+        const Op o = q.front();
+        q.pop_front();
+        if (o.kind == OP_MATCH || o.kind == OP_HARD || o.kind == OP_SOFT || o.kind == OP_INS) {
+            if (o.len + cur > read_pos) q.push_front(Op{o.kind, o.len - (read_pos - cur)});
+            cur = std::min(o.len + cur, read_pos);
+        }
+    }
+    if (q.empty()) { *ok = false; return q; }
+    if (q.front().kind == OP_DEL) q.pop_front();
+    return q;
+}
+
+// read->haplotype o haplotype->reference (CalculateReadToRefAlignment, realigner.cpp:640-777); empty result = "keep the read as it was"
+std::vector<Op> compose(int read_len, const Placement& on_hap, const std::vector<Op>& hap_ops)
+{
+    Composed out;
+    std::vector<Op> parsed = parse_ops(on_hap.cigar);
+    std::deque<Op> rh(parsed.begin(), parsed.end());
+    bool ok = true;
+    std::deque<Op> hr = trim_left(hap_ops, on_hap.pos, &ok);
+    if (!ok) return {};
+    if (!rh.empty() && rh.front().kind == OP_SOFT) {
+        out.merge(OP_SOFT, rh.front().len, read_len);
+        rh.pop_front();
+    }
+    while ((!rh.empty() || !hr.empty()) && out.covered < read_len) {
+        if (!rh.empty() && hr.empty()) {
+            out.merge(rh.front().kind, rh.front().len, read_len);
+            rh.pop_front();
+            continue;
+        }
+        if (rh.empty()) break;
+        Op a = rh.front(); rh.pop_front();       // read -> haplotype
+        Op b = hr.front(); hr.pop_front();       // haplotype -> reference
+        if (matchlike(a) && matchlike(b)) {
+            const int n = std::min(a.len, b.len);
+            out.merge((a.kind == OP_SOFT || b.kind == OP_SOFT) ? OP_SOFT : OP_MATCH, n, read_len);
+            a.len -= n; if (a.len > 0) rh.push_front(a);
+            b.len -= n; if (b.len > 0) hr.push_front(b);
+        } else if (a.kind == OP_DEL && matchlike(b)) {
+            out.merge(OP_DEL, a.len, read_len);
+            b.len -= a.len; if (b.len > 0) hr.push_front(b);
+        } else if (b.kind == OP_DEL && matchlike(a)) {
+            out.merge(OP_DEL, b.len, read_len);
+            if (a.len > 0) rh.push_front(a);
+        } else if (a.kind == OP_DEL && b.kind == OP_DEL) {
+            out.merge(OP_DEL, a.len + b.len, read_len);
+        } else if (a.kind == OP_INS && matchlike(b)) {
+            a.len = std::min(read_len - out.covered, a.len);
+            out.merge(OP_INS, a.len, read_len);
+            if (b.len > 0) hr.push_front(b);
+        } else if (b.kind == OP_INS && matchlike(a)) {
+            b.len = std::min(read_len - out.covered, b.len);
+            out.merge(OP_INS, b.len, read_len);
+            a.len = std::max(0, a.len - b.len);
+            if (a.len > 0) rh.push_front(a);
+        } else if (a.kind == OP_INS && b.kind == OP_INS) {
+            out.merge(OP_INS, a.len + b.len, read_len);
+        } else {
+            return {};                               // combination the reference does not handle: alignment discarded
+        }
+    }
+    return out.ops;
+}
+
+// GetBestReadAlignment (realigner.cpp:517-540): highest score; on ties the later non-reference haplotype wins
+bool best_haplotype(const Region& rg, int read, int* best)
+{
+    int top = 0;
+    bool found = false;
+    for (int k = 0; k < (int)rg.haplotypes.size() && k < (int)rg.haps.size(); ++k) {
+        const int s = rg.haps[k].reads[read].score;
+        if (s > top || (top > 0 && s == top && !rg.haps[k].is_reference)) { top = s; *best = k; found = true; }
+    }
+    return found;
+}
+
+struct Stats { long long pairs = 0, cells = 0; double t_fast = 0, t_gpu = 0, t_compose = 0; };
+Stats g_last;
+
+double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+void load_region(Region& rg, const mpn_region& in)
+{
+    rg.reference = in.reference ? in.reference : "";
+    rg.haplotypes.clear();
+    if (in.haplotypes) {                                     // white-space separated (realigner.cpp:788-794)
+        const char* p = in.haplotypes;
+        while (*p) {
+            while (*p == ' ' || *p == '\t' || *p == '\n' || *p == '\r' || *p == '\v' || *p == '\f') ++p;
+            const char* q = p;
+            while (*q && !(*q == ' ' || *q == '\t' || *q == '\n' || *q == '\r' || *q == '\v' || *q == '\f')) ++q;
+            if (q > p) rg.haplotypes.emplace_back(p, q);
+            p = q;
+        }
+    }
+    rg.reads.resize((size_t)in.read_size); rg.in_pos.resize((size_t)in.read_size); rg.in_cigar.resize((size_t)in.read_size);
+    for (int i = 0; i < in.read_size; ++i) { rg.reads[i] = in.seqs[i]; rg.in_pos[i] = in.positions[i]; rg.in_cigar[i] = in.cigars[i]; }
+    rg.ref_start = in.ref_start; rg.prefix = in.ref_prefix; rg.suffix = in.ref_suffix;
+}
+
+int realign_many(const mpn_region* regions, int nregions, struct_str_arr** out)
+{
+    std::vector<Region> rgs((size_t)nregions);
+    Stats st;
+    double t0 = now_s();
+    // ---- 1. host: k-mer fast pass, then the list of Smith-Waterman pairs of every region
+    std::vector<PairView> pairs;
+    for (int r = 0; r < nregions; ++r) {
+        Region& rg = rgs[r];
+        load_region(rg, regions[r]);
+        fast_pass(rg);
+        plan_read_pairs(rg);
+        rg.first_pair = pairs.size();
+        for (const HapRecord& h : rg.haps) {
+            const std::string& hap = rg.haplotypes[h.index];
+            pairs.push_back(PairView{hap.c_str(), (int)strlen(hap.c_str()), rg.reference.c_str(), (int)rg.reference.length()});
+        }
+        for (const auto& rh : rg.read_hap_pairs) {
+            const std::string& read = rg.reads[rh.first];
+            const std::string& hap = rg.haplotypes[rg.haps[rh.second].index];
+            pairs.push_back(PairView{read.c_str(), (int)strlen(read.c_str()), hap.c_str(), (int)hap.length()});
+        }
+    }
+    for (const PairView& p : pairs) { st.pairs++; st.cells += (long long)p.query_len * p.ref_len; }
+    double t1 = now_s();
+    // ---- 2. GPU: one batch (flag 0x0f, no filters, maskLen = query length: StripedSmithWaterman defaults, ssw_cpp.cpp:343-346)
+    std::vector<Alignment> aln;
+    {
+        StripedSmithWaterman::Aligner aligner(kMatch, kMismatch, kGapOpen, kGapExtend);
+        StripedSmithWaterman::Filter filter;
+        // a zero-length reference makes Aligner::Align return false in the reference (ssw_cpp.cpp:330); those pairs stay cleared
+        std::vector<PairView> live;
+        std::vector<size_t> where;
+        for (size_t i = 0; i < pairs.size(); ++i) if (pairs[i].ref_len > 0 && pairs[i].query_len > 0) { live.push_back(pairs[i]); where.push_back(i); }
+        std::vector<Alignment> got;
+        aligner.AlignPairs(live, filter, &got);
+        aln.assign(pairs.size(), Alignment());
+        for (size_t k = 0; k < where.size(); ++k) aln[where[k]] = std::move(got[k]);
+    }
+    double t2 = now_s();
+    // ---- 3. host: consume
+    const int threshold = ssw_score_threshold();
+    for (int r = 0; r < nregions; ++r) {
+        Region& rg = rgs[r];
+        size_t k = rg.first_pair;
+        for (HapRecord& h : rg.haps) {                                   // realigner.cpp:336-348
+            const Alignment& a = aln[k++];
+            if (a.sw_score > 0) {
+                h.is_reference = a.cigar_string == std::to_string(rg.haplotypes[h.index].size()) + "=";
+                h.cigar = a.cigar_string;
+                h.ops = parse_ops(h.cigar);
+                h.ref_pos = a.ref_begin;
+            }
+            build_shift_map(h, (int)rg.haplotypes[h.index].size());
+        }
+        for (const auto& rh : rg.read_hap_pairs) {                       // realigner.cpp:369-379
+            const Alignment& a = aln[k++];
+            Placement& pl = rg.haps[rh.second].reads[rh.first];
+            if (a.sw_score > 0 && a.sw_score >= threshold && pl.score < a.sw_score) {
+                pl.score = a.sw_score; pl.cigar = a.cigar_string; pl.pos = a.ref_begin;
+            }
+        }
+        std::sort(rg.haps.begin(), rg.haps.end());                       // realigner.cpp:105-106 (same comparator, same algorithm)
+        struct_str_arr* res = new struct_str_arr();
+        memset(res, 0, sizeof *res);
+        for (int i = 0; i < (int)rg.reads.size(); ++i) {
+            int pos = rg.in_pos[i];
+            std::string cigar = rg.in_cigar[i];
+            int best = -1;
+            if (best_haplotype(rg, i, &best)) {
+                const HapRecord& h = rg.haps[best];
+                const Placement& pl = h.reads[i];
+                if (pl.pos >= 0 && pl.pos < (int)h.shift.size()) {
+                    const int new_pos = rg.ref_start + h.ref_pos + pl.pos + h.shift[pl.pos];
+                    const std::vector<Op> ops = compose((int)rg.reads[i].length(), pl, h.ops);
+                    if (!ops.empty()) { cigar = ops_to_string(ops); pos = new_pos; }
+                }
+            }
+            if (i < 1000) {
+                res->cigar_string[i] = new char[cigar.size() + 1];
+                memcpy(res->cigar_string[i], cigar.c_str(), cigar.size() + 1);
+                res->position[i] = pos;
+            }
+        }
+        out[r] = res;
+    }
+    double t3 = now_s();
+    st.t_fast = t1 - t0; st.t_gpu = t2 - t1; st.t_compose = t3 - t2;
+    g_last = st;
+    return 0;
+}
+
+}  // namespace
+
+extern "C" struct_str_arr* realign_reads(char* seqs[], int* positions, char* cigars[], char* reference, char* haplotypes,
+                                         int ref_start, int ref_prefix, int ref_suffix, int read_size)
+{
+    mpn_region rg{seqs, positions, cigars, read_size, reference, haplotypes, ref_start, ref_prefix, ref_suffix};
+    struct_str_arr* out = nullptr;
+    realign_many(&rg, 1, &out);
+    return out;
+}
+
+extern "C" int mpn_realign_regions(const mpn_region* regions, int nregions, struct_str_arr** out)
+{
+    if (nregions < 0 || (nregions > 0 && (!regions || !out))) return -1;
+    for (int r = 0; r < nregions; ++r) if (regions[r].read_size < 0 || regions[r].read_size > 1000) return -1;
+    return realign_many(regions, nregions, out);
+}
+
+extern "C" void free_memory(struct_str_arr* pointer, int size)
+{
+    if (!pointer) return;
+    for (int i = 0; i < size && i < 1000; ++i) delete[] pointer->cigar_string[i];
+    delete pointer;
+}
+
+extern "C" int mpn_realign_last_stats(long long* pairs, long long* cells, double* seconds3)
+{
+    if (pairs) *pairs = g_last.pairs;
+    if (cells) *cells = g_last.cells;
+    if (seconds3) { seconds3[0] = g_last.t_fast; seconds3[1] = g_last.t_gpu; seconds3[2] = g_last.t_compose; }
+    return 0;
+}

@@ -4,7 +4,8 @@
 #include "../../include/ssw.h"
 #include "../../include/mpn_ssw_batch.h"
 #include <cstdlib>
-#include <mutex>
+#include "host_shared.h"
+#include <cstdio>
 
 struct _profile {
     const int8_t* read;       // borrowed (reference ssw.c:749)
@@ -14,22 +15,21 @@ struct _profile {
     int8_t score_size;
 };
 
-namespace {
-std::mutex g_mu;
-mpn_engine* g_engine = nullptr;
-
-mpn_engine* engine_locked()
+namespace mpn {
+std::mutex& shared_engine_mutex() { static std::mutex mu; return mu; }
+mpn_engine* shared_engine_locked()
 {
-    if (!g_engine) {
-        g_engine = mpn_engine_create(-1);
-        if (!g_engine) {
-            fprintf(stderr, "[libssw] cannot create the GPU engine: this libssw.so has no CPU fallback\n");
+    static mpn_engine* engine = nullptr;
+    if (!engine) {
+        engine = mpn_engine_create(-1);
+        if (!engine) {
+            fprintf(stderr, "[libssw] cannot create the GPU engine: this library has no CPU fallback\n");
             abort();
         }
     }
-    return g_engine;
+    return engine;
 }
-}  // namespace
+}  // namespace mpn
 
 extern "C" s_profile* ssw_init(const int8_t* read, const int32_t readLen, const int8_t* mat, const int32_t n, const int8_t score_size)
 {
@@ -59,8 +59,8 @@ extern "C" s_align* ssw_align(const s_profile* prof, const int8_t* ref, int32_t 
     uint32_t* cig = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)cap);
     int rc;
     {
-        std::lock_guard<std::mutex> lk(g_mu);
-        rc = mpn_align_batch(engine_locked(), &pr, prof->read, read_off, ref, ref_off, mask, 1, &res, cig, cap);
+        mpn::SharedEngineLock lk;
+        rc = mpn_align_batch(lk.engine(), &pr, prof->read, read_off, ref, ref_off, mask, 1, &res, cig, cap);
     }
     if (rc != 0) {
         fprintf(stderr, "[libssw] GPU alignment failed (code %d); no CPU fallback\n", rc);

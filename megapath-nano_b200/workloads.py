@@ -232,3 +232,90 @@ def fuzz_pairs(npairs, seed, max_read=700, max_ref=500, alphabet=4, flag=1, rand
     ml = np.maximum(15, rng.integers(15, 40, size=npairs) if rng.random() < 0.3 else (rl // 2 + rng.integers(0, 6, size=npairs))).astype(np.int32)
     return PairBatch(np.concatenate(reads_l), ro, np.concatenate(refs_l), fo, ml, mat=mat.reshape(-1).astype(np.int8), gapO=gapO, gapE=gapE,
                      flag=flag, name=f"fuzz seed {seed}")
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# BASELINE configs[2]: the realigner's amplicon workload (SURVEY.md section 8d "Config 3").  One region = what
+# realign_illumina_reads.py:567-605 hands to realign_reads: a reference window with prefix/suffix flanks, the candidate
+# haplotypes (flank + consensus + flank, space separated) and the reads overlapping the window with their current
+# position and CIGAR.  The de Bruijn assembly that proposes haplotypes is out of scope, so haplotypes are the window with
+# 1-3 planted SNVs / small indels; reads are sampled from a few "true" haplotypes with 0.5 % error.
+@dataclass
+class RegionWorkload:
+    reference: str
+    haplotypes: list
+    reads: list
+    positions: list
+    cigars: list
+    ref_start: int
+    ref_prefix: int
+    ref_suffix: int
+
+
+def _rand_dna(rng, n):
+    return "".join("ACGT"[i] for i in rng.integers(0, 4, size=n))
+
+
+def _plant_variants(rng, center, k):
+    s = list(center)
+    for _ in range(k):
+        if len(s) < 40:
+            break
+        p = int(rng.integers(10, len(s) - 10))
+        u = rng.random()
+        if u < 0.5:
+            s[p] = "ACGT"[("ACGT".index(s[p]) + 1 + int(rng.integers(0, 3))) % 4]
+        elif u < 0.75:
+            s[p:p] = list(_rand_dna(rng, int(rng.integers(1, 11))))
+        else:
+            del s[p:p + int(rng.integers(1, 11))]
+    return "".join(s)
+
+
+def _noisy_copy(rng, s, err):
+    out = []
+    for ch in s:
+        u = rng.random()
+        if u < err / 3:
+            out.append("ACGT"[("ACGT".index(ch) + 1 + int(rng.integers(0, 3))) % 4])
+        elif u < 2 * err / 3:
+            out.append("ACGT"[int(rng.integers(0, 4))]); out.append(ch)
+        elif u < err:
+            continue
+        else:
+            out.append(ch)
+    return "".join(out)
+
+
+def config3(nregions=64, seed=13, max_reads=1000, max_haps=32, err=0.005, n_frac=0.0):
+    """list of RegionWorkload (seeded)."""
+    rng = np.random.default_rng(seed)
+    regions = []
+    for _ in range(nregions):
+        wlen = int(rng.integers(160, 1001)); pre = int(rng.integers(20, 271)); suf = int(rng.integers(20, 271))
+        prefix, center, suffix = _rand_dna(rng, pre), _rand_dna(rng, wlen), _rand_dna(rng, suf)
+        reference = prefix + center + suffix
+        nh = int(rng.integers(2, max_haps + 1))
+        haps = [reference]
+        while len(haps) < nh:
+            h = prefix + _plant_variants(rng, center, int(rng.integers(1, 4))) + suffix
+            if h not in haps:
+                haps.append(h)
+        order = rng.permutation(nh)
+        haps = [haps[i] for i in order]
+        truth = [haps[i] for i in rng.choice(nh, size=min(nh, int(rng.integers(1, 4))), replace=False)]
+        nr = int(rng.integers(50, max_reads + 1))
+        reads, positions, cigars = [], [], []
+        ref_start = int(rng.integers(1000, 5_000_000))
+        for _ in range(nr):
+            h = truth[int(rng.integers(0, len(truth)))]
+            rl = int(rng.integers(100, 251)); rl = min(rl, len(h) - 1)
+            st = int(rng.integers(0, len(h) - rl + 1))
+            r = _noisy_copy(rng, h[st:st + rl], err)
+            if n_frac > 0:
+                r = "".join("N" if rng.random() < n_frac else c for c in r)
+            if not r:
+                r = "A"
+            reads.append(r); positions.append(ref_start + st); cigars.append(f"{len(r)}M")
+        regions.append(RegionWorkload(reference, haps, reads, positions, cigars, ref_start, pre, suf))
+    return regions

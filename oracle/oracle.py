@@ -31,6 +31,20 @@ def build(force=False):
         subprocess.run(["make", "-C", HERE, "ref"], check=True, capture_output=True)
 
 
+_HOSTTEST_SO = os.path.join(HERE, "_hosttest", "realigner_hosttest.so")
+
+
+def build_hosttest(force=False):
+    """the product's host-side realigner sources linked against the CPU checkers (oracle/host_shim.cpp); returns the path"""
+    build()
+    srcs = [os.path.join(HERE, "host_shim.cpp"), os.path.join(HERE, "ssw_oracle.c"), os.path.join(HERE, "batch_driver.c")]
+    pkg = os.path.join(HERE, "..", "megapath-nano_b200", "csrc")
+    srcs += [os.path.join(pkg, f) for f in ("realign_region.cpp", "ssw_cpp_layer.cpp", "host_shared.h")]
+    if force or not os.path.exists(_HOSTTEST_SO) or os.path.getmtime(_HOSTTEST_SO) < max(os.path.getmtime(f) for f in srcs):
+        subprocess.run(["make", "-C", HERE, "hosttest"], check=True, capture_output=True)
+    return _HOSTTEST_SO
+
+
 _port = None
 _ref = None
 

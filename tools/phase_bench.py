@@ -6,15 +6,18 @@ w = importlib.import_module("megapath-nano_b200.workloads")
 B = importlib.import_module("megapath-nano_b200.batch")
 pairs = int(sys.argv[1]) if len(sys.argv) > 1 else 300000
 cfg = int(sys.argv[2]) if len(sys.argv) > 2 else 2
-b = {1: w.config1, 2: w.config2}[cfg](pairs, seed=1000)
+flag = int(sys.argv[3]) if len(sys.argv) > 3 else None
+b = {1: w.config1, 2: w.config2, 4: w.config4, 5: w.config5}[cfg](pairs, seed=1000)
+if flag is not None:
+    b.flag = flag
 eng = B.Engine(0)
 eng.set_profile(True)
 h = eng.upload(b)
 best = None
-for it in range(5):
+for it in range(5 if cfg < 4 else 3):
     eng.run(h)
     ph = eng.phase_ms()
-    if it >= 2 and (best is None or ph["forward"] < best["forward"]):
+    if it >= (2 if cfg < 4 else 1) and (best is None or ph["forward"] < best["forward"]):
         best = ph
 tot = sum(best.values())
 print(f"{os.environ.get('MPN_SSW_LIB', 'default'):28s} pairs {pairs} fwd {best['forward']:.3f} fin {best['finish']:.3f} rev {best['reverse']:.3f} tr {best['trace']:.3f} total {tot:.3f} ms"

@@ -1,0 +1,37 @@
+"""BASELINE configs[2] (realigner amplicon workload) timing: python tools/realign_bench.py [regions] [seed]
+Per-region realign_reads latency and whole-set mpn_realign_regions throughput on the GPU, the compiled reference realigner
+(oracle/_ref/realigner_ref, clean subprocess, one core) beside it."""
+import dataclasses, importlib, json, os, subprocess, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+w = importlib.import_module("megapath-nano_b200.workloads")
+R = importlib.import_module("megapath-nano_b200.realigner")
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 200
+seed = int(sys.argv[2]) if len(sys.argv) > 2 else 13
+regions = w.config3(n, seed=seed)
+reads = sum(len(r.reads) for r in regions)
+R.realign_reads(regions[0])                      # context + engine creation
+t0 = time.perf_counter()
+lat = []
+single = []
+for rg in regions:
+    t = time.perf_counter(); single.append(R.realign_reads(rg)); lat.append(time.perf_counter() - t)
+t_single = time.perf_counter() - t0
+t0 = time.perf_counter(); many = R.realign_regions(regions); t_many = time.perf_counter() - t0
+st = R.last_stats()
+assert many == single
+lat.sort()
+out = {"regions": n, "reads": reads, "ssw_pairs": st["pairs"], "ssw_cells": st["cells"],
+       "per_region_ms": {"p50": 1e3 * lat[len(lat) // 2], "p95": 1e3 * lat[int(len(lat) * 0.95)], "sum_s": t_single},
+       "batched_s": t_many, "batched_split_s": {k: st[k] for k in ("fast_pass_s", "gpu_s", "compose_s")},
+       "batched_gcups_ssw_only": st["cells"] / max(st["gpu_s"], 1e-9) / 1e9, "batched_reads_per_s": reads / t_many}
+ref = os.path.join(ROOT, "oracle", "_ref", "realigner_ref")
+if os.path.exists(ref):
+    t0 = time.perf_counter()
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "ref_realigner_runner.py"), ref], input=json.dumps([dataclasses.asdict(r) for r in regions]).encode(), capture_output=True, check=True)
+    t_ref = time.perf_counter() - t0
+    want = [(a[0], a[1]) for a in json.loads(p.stdout)]
+    out["reference_cpu_s"] = t_ref
+    out["reference_reads_per_s"] = reads / t_ref
+    out["identical_to_reference"] = want == many
+print(json.dumps(out))
