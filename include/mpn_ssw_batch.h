@@ -78,6 +78,15 @@ int mpn_align_batch(mpn_engine* e, const mpn_params* p, const int8_t* reads, con
                     const int64_t* ref_off, const int32_t* masklen, int64_t npairs, mpn_result* out, uint32_t* cigar, int64_t cigar_cap);
 
 /*
+ * Same call for pairs that SHARE sequences (one haplotype against many reads, realigner.cpp:351-384): one arena of int8
+ * codes plus, per pair, the start and length of its read and of its target inside the arena.  Spans may overlap or repeat;
+ * every distinct sequence is uploaded once.
+ */
+int mpn_align_batch_spans(mpn_engine* e, const mpn_params* p, const int8_t* seq, int64_t seq_bytes, const int64_t* rd_start, const int32_t* rd_len,
+                          const int64_t* rf_start, const int32_t* rf_len, const int32_t* masklen, int64_t npairs,
+                          mpn_result* out, uint32_t* cigar, int64_t cigar_cap);
+
+/*
  * The same work split into phases, so that inputs can stay resident in HBM across repeated runs:
  *   upload : host -> device copies + scheduling (length binning, task lists)
  *   run    : enqueue every kernel of the batch on the engine's stream (no host synchronisation)
@@ -85,6 +94,8 @@ int mpn_align_batch(mpn_engine* e, const mpn_params* p, const int8_t* reads, con
  */
 mpn_batch* mpn_batch_upload(mpn_engine* e, const mpn_params* p, const int8_t* reads, const int64_t* read_off, const int8_t* refs,
                             const int64_t* ref_off, const int32_t* masklen, int64_t npairs);
+mpn_batch* mpn_batch_upload_spans(mpn_engine* e, const mpn_params* p, const int8_t* seq, int64_t seq_bytes, const int64_t* rd_start, const int32_t* rd_len,
+                                  const int64_t* rf_start, const int32_t* rf_len, const int32_t* masklen, int64_t npairs);
 int mpn_batch_run(mpn_batch* b);
 int mpn_batch_fetch(mpn_batch* b, mpn_result* out, uint32_t* cigar, int64_t cigar_cap);
 /* bytes copied host->device by upload and device->host by fetch for this batch */

@@ -84,6 +84,7 @@ void build_strip_table()
     for (int p = 0; p < 4; ++p)
         for (int k = 0; k < counts[p]; ++k) {
             const StripEntry& e = parts[p][k];
+            if (getenv("MPN_EXP_SKIP_G") && e.G == atoi(getenv("MPN_EXP_SKIP_G")) && e.KR >= 10) continue;   // A/B experiments on the bin table
             g_strips.push_back(StripCfg{e.G, e.KR, 2 * e.G * e.KR, e.fn, e.smem, 1});
         }
     std::stable_sort(g_strips.begin(), g_strips.end(), [](const StripCfg& a, const StripCfg& b) { return a.cap < b.cap; });
@@ -242,11 +243,45 @@ extern "C" void mpn_batch_free(mpn_batch* b)
     delete b;
 }
 
-static mpn_batch* upload_impl(mpn_engine* e, int slot_id, const mpn_params* p, const int8_t* reads, const int64_t* read_off, const int8_t* refs,
-                              const int64_t* ref_off, const int32_t* masklen, int64_t npairs)
+// Where the sequences of a batch come from.  Both forms end up as one device arena plus (start, length) spans per pair.
+//   CsrPairs   reads / refs as two CSR arrays (mpn_batch_upload): arena = [reads | refs], copied straight from the caller's buffers
+//   SpanPairs  one caller arena + explicit spans (mpn_batch_upload_spans): pairs may share sequences (a haplotype aligned to many reads)
+struct CsrPairs {
+    const int8_t* reads; const int64_t* read_off; const int8_t* refs; const int64_t* ref_off; int64_t npairs;
+    int64_t reads_total() const { return npairs ? read_off[npairs] - read_off[0] : 0; }
+    int64_t refs_total() const { return npairs ? ref_off[npairs] - ref_off[0] : 0; }
+    int64_t rl(int64_t i) const { return read_off[i + 1] - read_off[i]; }
+    int64_t fl(int64_t i) const { return ref_off[i + 1] - ref_off[i]; }
+    int64_t rd_base(int64_t i) const { return read_off[i] - read_off[0]; }
+    int64_t rf_base(int64_t i) const { return reads_total() + (ref_off[i] - ref_off[0]); }
+    bool valid() const { return npairs == 0 || (reads && read_off && refs && ref_off); }
+    bool span_ok(int64_t) const { return true; }
+    size_t arena_bytes() const { return (size_t)(reads_total() + refs_total()); }
+    void copy_arena(int8_t* dst, cudaStream_t st) const {
+        if (!npairs) return;
+        if (reads_total()) cudaMemcpyAsync(dst, reads + read_off[0], (size_t)reads_total(), cudaMemcpyHostToDevice, st);
+        if (refs_total()) cudaMemcpyAsync(dst + reads_total(), refs + ref_off[0], (size_t)refs_total(), cudaMemcpyHostToDevice, st);
+    }
+    int64_t read_bases() const { return reads_total(); }
+};
+struct SpanPairs {
+    const int8_t* seq; int64_t seq_bytes; const int64_t* rd_start; const int32_t* rd_len; const int64_t* rf_start; const int32_t* rf_len; int64_t npairs;
+    int64_t rl(int64_t i) const { return rd_len[i]; }
+    int64_t fl(int64_t i) const { return rf_len[i]; }
+    int64_t rd_base(int64_t i) const { return rd_start[i]; }
+    int64_t rf_base(int64_t i) const { return rf_start[i]; }
+    bool valid() const { return seq_bytes >= 0 && (npairs == 0 || (seq && rd_start && rd_len && rf_start && rf_len)); }
+    bool span_ok(int64_t i) const { return rd_start[i] >= 0 && rf_start[i] >= 0 && rd_start[i] + rd_len[i] <= seq_bytes && rf_start[i] + rf_len[i] <= seq_bytes; }
+    size_t arena_bytes() const { return (size_t)seq_bytes; }
+    void copy_arena(int8_t* dst, cudaStream_t st) const { if (seq_bytes) cudaMemcpyAsync(dst, seq, (size_t)seq_bytes, cudaMemcpyHostToDevice, st); }
+    int64_t read_bases() const { int64_t t = 0; for (int64_t i = 0; i < npairs; ++i) t += rd_len[i]; return t; }
+};
+
+template <class Pairs>
+static mpn_batch* upload_impl(mpn_engine* e, int slot_id, const mpn_params* p, const Pairs& src, const int32_t* masklen, int64_t npairs)
 {
     if (!e || !p || !p->mat || p->n < 1 || p->n > 127 || npairs < 0 || npairs > 0x7fffffff) return nullptr;
-    if (npairs > 0 && (!reads || !read_off || !refs || !ref_off || !masklen)) return nullptr;
+    if (!src.valid() || (npairs > 0 && !masklen)) return nullptr;
     CK(cudaSetDevice(e->device));
     mpn_batch* b = new mpn_batch();
     b->e = e; b->p = *p; b->npairs = npairs;
@@ -286,8 +321,8 @@ static mpn_batch* upload_impl(mpn_engine* e, int slot_id, const mpn_params* p, c
     const bool packed_ok = n <= 8;
     const int64_t maxpos = std::max(maxv, 0);
     for (int64_t i = 0; i < npairs; ++i) {
-        const int64_t rl = read_off[i + 1] - read_off[i], fl = ref_off[i + 1] - ref_off[i];
-        if (rl < 0 || fl < 0 || rl > 0x3fffffff || fl > 0x3fffffff) { delete b; return nullptr; }
+        const int64_t rl = src.rl(i), fl = src.fl(i);
+        if (rl < 0 || fl < 0 || rl > 0x3fffffff || fl > 0x3fffffff || !src.span_ok(i)) { delete b; return nullptr; }
         cells += rl * fl;
         max_rd = std::max<int>(max_rd, (int)rl); max_rf = std::max<int>(max_rf, (int)fl); min_rf = std::min<int>(min_rf, (int)fl);
         cm_total += fl;
@@ -332,19 +367,18 @@ static mpn_batch* upload_impl(mpn_engine* e, int slot_id, const mpn_params* p, c
         } else {
             std::vector<int64_t>& cnt = e->h_cnt; std::vector<int64_t>& idx = e->h_idx;
             cnt.assign((size_t)max_rf + 2, 0); idx.resize(npairs);
-            for (int64_t i = 0; i < npairs; ++i) cnt[max_rf - (ref_off[i + 1] - ref_off[i]) + 1]++;
+            for (int64_t i = 0; i < npairs; ++i) cnt[max_rf - src.fl(i) + 1]++;
             for (int v = 0; v <= max_rf; ++v) cnt[v + 1] += cnt[v];
-            for (int64_t i = 0; i < npairs; ++i) idx[cnt[max_rf - (ref_off[i + 1] - ref_off[i])]++] = i;     // descending target length, stable
+            for (int64_t i = 0; i < npairs; ++i) idx[cnt[max_rf - src.fl(i)]++] = i;     // descending target length, stable
             for (int64_t k = 0; k < npairs; ++k) { const int64_t i = idx[k]; order[cursor[bin[i]]++] = i; }
         }
-        const int64_t reads_total = npairs ? read_off[npairs] - read_off[0] : 0;
         int64_t cm = 0;
         for (int64_t k = 0; k < npairs; ++k) {
             const int64_t i = order[k];
             SwTask& t = h_tasks[k];
-            t.rd_base = read_off[i] - read_off[0];
-            t.rf_base = reads_total + (ref_off[i] - ref_off[0]);
-            t.rd_len = (int32_t)(read_off[i + 1] - read_off[i]); t.rf_len = (int32_t)(ref_off[i + 1] - ref_off[i]);
+            t.rd_base = src.rd_base(i);
+            t.rf_base = src.rf_base(i);
+            t.rd_len = (int32_t)src.rl(i); t.rf_len = (int32_t)src.fl(i);
             t.cm_off = cm; cm += t.rf_len;            // column records are laid out in task order
             t.dir = 1; t.out = (int32_t)i; t.stop = 0; t.pad_ = 0;
         }
@@ -353,9 +387,8 @@ static mpn_batch* upload_impl(mpn_engine* e, int slot_id, const mpn_params* p, c
 
     // ---- device buffers + uploads (straight from the caller's buffers: pinned caller memory gives full PCIe rate)
     DevPool& pool = e->pool;
-    const size_t reads_bytes = npairs ? (size_t)(read_off[npairs] - read_off[0]) : 0;
-    const size_t refs_bytes = npairs ? (size_t)(ref_off[npairs] - ref_off[0]) : 0;
-    b->seq_reads_bytes = reads_bytes; b->seq_bytes = reads_bytes + refs_bytes;
+    const size_t reads_bytes = (size_t)src.read_bases();          // bases the traceback arenas are budgeted on
+    b->seq_reads_bytes = reads_bytes; b->seq_bytes = src.arena_bytes();
     pool.take(b->seq, b->seq_bytes + 16);
     pool.take(b->mask, sizeof(int32_t) * (size_t)(npairs + 1));
     pool.take(b->tasks_fwd, sizeof(SwTask) * (size_t)(npairs + 1)); pool.take(b->tasks_rev, sizeof(SwTask) * (size_t)(npairs + 1));
@@ -365,15 +398,15 @@ static mpn_batch* upload_impl(mpn_engine* e, int slot_id, const mpn_params* p, c
     pool.take(b->counters, 512 * sizeof(unsigned long long));   // [0,128) misc (arena cursors at 64/65, task cursors at 100..104), [128,256) forward bins, [256,384) reverse bins
     pool.take(b->dmat, (size_t)n * n + 16);
     if (npairs) {
-        CK(cudaMemcpyAsync(b->seq.p, reads + read_off[0], reads_bytes, cudaMemcpyHostToDevice, st));
-        CK(cudaMemcpyAsync(b->seq.as<int8_t>() + reads_bytes, refs + ref_off[0], refs_bytes, cudaMemcpyHostToDevice, st));
+        src.copy_arena(b->seq.as<int8_t>(), st);
+        CK(cudaGetLastError());
         CK(cudaMemcpyAsync(b->mask.p, masklen, sizeof(int32_t) * npairs, cudaMemcpyHostToDevice, st));
         CK(cudaMemcpyAsync(b->tasks_fwd.p, h_tasks, sizeof(SwTask) * npairs, cudaMemcpyHostToDevice, st));
     }
     sl.pin_misc.reserve(4096 + (size_t)n * n);
     memcpy(sl.pin_misc.as<char>() + 4096, b->mat.data(), (size_t)n * n);
     CK(cudaMemcpyAsync(b->dmat.p, sl.pin_misc.as<char>() + 4096, (size_t)n * n, cudaMemcpyHostToDevice, st));
-    b->h2d_bytes = reads_bytes + refs_bytes + (sizeof(int32_t) + sizeof(SwTask)) * (size_t)npairs + (size_t)n * n;
+    b->h2d_bytes = b->seq_bytes + (sizeof(int32_t) + sizeof(SwTask)) * (size_t)npairs + (size_t)n * n;
 
     // ---- boundary rows of the 32-bit kernel (one slot per resident warp)
     b->wide_blocks = e->sm_count * 3;
@@ -400,7 +433,26 @@ static mpn_batch* upload_impl(mpn_engine* e, int slot_id, const mpn_params* p, c
 extern "C" mpn_batch* mpn_batch_upload(mpn_engine* e, const mpn_params* p, const int8_t* reads, const int64_t* read_off, const int8_t* refs,
                                         const int64_t* ref_off, const int32_t* masklen, int64_t npairs)
 {
-    return upload_impl(e, 0, p, reads, read_off, refs, ref_off, masklen, npairs);
+    return upload_impl(e, 0, p, CsrPairs{reads, read_off, refs, ref_off, npairs}, masklen, npairs);
+}
+
+extern "C" mpn_batch* mpn_batch_upload_spans(mpn_engine* e, const mpn_params* p, const int8_t* seq, int64_t seq_bytes, const int64_t* rd_start, const int32_t* rd_len,
+                                              const int64_t* rf_start, const int32_t* rf_len, const int32_t* masklen, int64_t npairs)
+{
+    return upload_impl(e, 0, p, SpanPairs{seq, seq_bytes, rd_start, rd_len, rf_start, rf_len, npairs}, masklen, npairs);
+}
+
+extern "C" int mpn_align_batch_spans(mpn_engine* e, const mpn_params* p, const int8_t* seq, int64_t seq_bytes, const int64_t* rd_start, const int32_t* rd_len,
+                                     const int64_t* rf_start, const int32_t* rf_len, const int32_t* masklen, int64_t npairs,
+                                     mpn_result* out, uint32_t* cigar, int64_t cigar_cap)
+{
+    if (!e || npairs < 0) return MPN_E_ARG;
+    mpn_batch* b = mpn_batch_upload_spans(e, p, seq, seq_bytes, rd_start, rd_len, rf_start, rf_len, masklen, npairs);
+    if (!b) return MPN_E_ARG;
+    int rc = mpn_batch_run(b);
+    if (rc == 0) rc = mpn_batch_fetch(b, out, cigar, cigar_cap);
+    mpn_batch_free(b);
+    return rc;
 }
 
 static void launch_strips(mpn_batch* b, const SwTask* tasks, bool forward, SwEnds* ends, int counter_base)
@@ -631,7 +683,7 @@ extern "C" int mpn_align_batch(mpn_engine* e, const mpn_params* p, const int8_t*
         drain(s);
         const int64_t c0 = c * per, n_c = std::min(per, npairs - c0);
         if (n_c <= 0) break;
-        mpn_batch* b = upload_impl(e, 1 + s, p, reads, read_off + c0, refs, ref_off + c0, masklen + c0, n_c);
+        mpn_batch* b = upload_impl(e, 1 + s, p, CsrPairs{reads, read_off + c0, refs, ref_off + c0, n_c}, masklen + c0, n_c);
         if (!b) { rc = MPN_E_ARG; break; }
         mpn_batch_run(b);
         inflight[s] = b; start_of[s] = c0;

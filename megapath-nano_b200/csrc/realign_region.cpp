@@ -11,6 +11,7 @@
 // Steps 1 and 3 are plain host code written against flat vectors (no std::list / std::regex); step 2 never runs on the CPU.
 #include "../../include/realigner.h"
 #include "../../include/ssw_cpp.h"
+#include "host_shared.h"
 
 #include <algorithm>
 #include <chrono>
@@ -207,6 +208,10 @@ void fast_pass_one(const Region& rg, const KmerIndex& index, const std::string& 
     std::vector<int> coverage(hap.size(), 0);
     if (hap.length() < (size_t)kKmer) return;            // the reference's unsigned loop bound wraps here and throws; nothing sensible to reproduce
     const int last = (int)hap.length() - kKmer;
+    // Consecutive k-mers of a read point at the same start on the haplotype, and repeating the comparison there can change nothing
+    // (a failed one has no effect, a passed one only re-increments coverage that is tested against zero and cannot raise the
+    // read's score again): remember the last start compared per read and skip exact repeats.
+    std::vector<int> last_start(rg.reads.size(), -2);
     uint64_t key = 0; int valid = 0;
     for (int i = 0; i < kKmer - 1; ++i) {
         const int b = base2(hap[i]);
@@ -224,6 +229,8 @@ void fast_pass_one(const Region& rg, const KmerIndex& index, const std::string& 
             if ((size_t)start + (size_t)rlen > hap.length()) continue;
             Placement& pl = (*placed)[oc->read];
             if (pl.pos != kNotPlaced && pl.pos == start) continue;
+            if (last_start[oc->read] == start) continue;
+            last_start[oc->read] = start;
             int mism = 0;
             const int sc = fast_compare(hap.data() + start, read.data(), rlen, kMaxMismatches + 1, &mism);
             if (mism <= kMaxMismatches) {
@@ -244,22 +251,20 @@ void fast_pass_one(const Region& rg, const KmerIndex& index, const std::string& 
     }
 }
 
-void fast_pass(Region& rg)
+void fast_pass(Region& rg, bool threads)
 {
     KmerIndex index;
     index.build(rg.reads);
-    std::vector<Placement> placed(rg.reads.size());
-    rg.haps.clear();
-    rg.haps.reserve(rg.haplotypes.size());
-    for (int h = 0; h < (int)rg.haplotypes.size(); ++h) {
-        for (Placement& p : placed) p.reset();
-        int score = 0;
-        fast_pass_one(rg, index, rg.haplotypes[h], &score, &placed);
-        if (score == 0) for (Placement& p : placed) p.reset();
-        HapRecord rec;
-        rec.index = h; rec.score = score; rec.reads = placed;
-        rg.haps.push_back(std::move(rec));
-    }
+    const int nh = (int)rg.haplotypes.size();
+    rg.haps.assign((size_t)nh, HapRecord());
+    auto one = [&](int64_t h) {                       // haplotypes are independent of each other (realigner.cpp:146-168)
+        HapRecord& rec = rg.haps[(size_t)h];
+        rec.index = (int)h; rec.score = 0;
+        rec.reads.assign(rg.reads.size(), Placement());
+        fast_pass_one(rg, index, rg.haplotypes[(size_t)h], &rec.score, &rec.reads);
+        if (rec.score == 0) for (Placement& p : rec.reads) p.reset();
+    };
+    if (threads) mpn::parallel_for(nh, 1, one); else for (int h = 0; h < nh; ++h) one(h);
 }
 
 // which (read, haplotype) pairs need Smith-Waterman (realigner.cpp:351-366)
@@ -425,11 +430,12 @@ int realign_many(const mpn_region* regions, int nregions, struct_str_arr** out)
     double t0 = now_s();
     // ---- 1. host: k-mer fast pass, then the list of Smith-Waterman pairs of every region
     std::vector<PairView> pairs;
+    for (int r = 0; r < nregions; ++r) load_region(rgs[r], regions[r]);
+    // regions are independent: one host thread each when there are several, else threads over the haplotypes of the one region
+    if (nregions > 1) mpn::parallel_for(nregions, 1, [&](int64_t r) { fast_pass(rgs[(size_t)r], false); plan_read_pairs(rgs[(size_t)r]); });
+    else if (nregions == 1) { fast_pass(rgs[0], rgs[0].reads.size() * rgs[0].haplotypes.size() >= 2048); plan_read_pairs(rgs[0]); }
     for (int r = 0; r < nregions; ++r) {
         Region& rg = rgs[r];
-        load_region(rg, regions[r]);
-        fast_pass(rg);
-        plan_read_pairs(rg);
         rg.first_pair = pairs.size();
         for (const HapRecord& h : rg.haps) {
             const std::string& hap = rg.haplotypes[h.index];
@@ -460,7 +466,7 @@ int realign_many(const mpn_region* regions, int nregions, struct_str_arr** out)
     double t2 = now_s();
     // ---- 3. host: consume
     const int threshold = ssw_score_threshold();
-    for (int r = 0; r < nregions; ++r) {
+    mpn::parallel_for(nregions, 1, [&](int64_t r) {
         Region& rg = rgs[r];
         size_t k = rg.first_pair;
         for (HapRecord& h : rg.haps) {                                   // realigner.cpp:336-348
@@ -503,7 +509,7 @@ int realign_many(const mpn_region* regions, int nregions, struct_str_arr** out)
             }
         }
         out[r] = res;
-    }
+    });
     double t3 = now_s();
     st.t_fast = t1 - t0; st.t_gpu = t2 - t1; st.t_compose = t3 - t2;
     g_last = st;

@@ -9,6 +9,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
+#include <unordered_map>
 
 namespace StripedSmithWaterman {
 
@@ -131,25 +133,44 @@ bool Aligner::AlignPairs(const std::vector<PairView>& pairs, const Filter& filte
     if (translate_.empty() || !out) return false;
     const size_t np = pairs.size();
     out->assign(np, Alignment());
-    // pack: skip empty queries (Align returns false for them) but keep their slot
-    std::vector<int64_t> qoff(1, 0), toff(1, 0);
-    std::vector<int32_t> mask; std::vector<size_t> slot;
-    size_t qbytes = 0, tbytes = 0;
-    for (const PairView& p : pairs) if (p.query_len > 0) { qbytes += (size_t)p.query_len; tbytes += (size_t)p.ref_len; }
-    std::vector<int8_t> q(qbytes + 1), t(tbytes + 1);
+    // ---- pack: every DISTINCT sequence (by address and length) is translated and uploaded once -- in the realigner one haplotype
+    //      meets hundreds of reads and one read meets every haplotype (realigner.cpp:351-384).  Empty queries keep a cleared slot.
+    struct Key { const void* p; int len; bool operator==(const Key& o) const { return p == o.p && len == o.len; } };
+    struct KeyHash { size_t operator()(const Key& k) const { return std::hash<const void*>()(k.p) * 31u + (size_t)k.len; } };
+    std::unordered_map<Key, int64_t, KeyHash> where;
+    std::vector<std::pair<const char*, int>> distinct;     // (text or nullptr = the stored reference, length)
+    std::vector<int64_t> start;                            // arena offset of each distinct sequence
+    int64_t arena_bytes = 0;
+    auto intern = [&](const char* p, int len) -> int64_t {
+        const Key k{p ? (const void*)p : (const void*)reference_.data(), len};
+        auto it = where.find(k);
+        if (it != where.end()) return it->second;
+        const int64_t at = arena_bytes;
+        where.emplace(k, at);
+        distinct.push_back({p, len}); start.push_back(at);
+        arena_bytes += len;
+        return at;
+    };
+    std::vector<int64_t> rd_start, rf_start;
+    std::vector<int32_t> rd_len, rf_len, mask;
+    std::vector<size_t> slot;
+    int64_t qbytes = 0, tbytes = 0;
     for (size_t i = 0; i < np; ++i) {
         const PairView& p = pairs[i];
         if (p.query_len <= 0) continue;
-        translate_into(translate_, p.query, p.query_len, q.data() + qoff.back());
-        // a target that is the aligner's stored reference is already translated
-        if (p.ref == nullptr) memcpy(t.data() + toff.back(), reference_.data(), (size_t)p.ref_len);
-        else translate_into(translate_, p.ref, p.ref_len, t.data() + toff.back());
-        qoff.push_back(qoff.back() + p.query_len); toff.push_back(toff.back() + p.ref_len);
+        rd_start.push_back(intern(p.query, p.query_len)); rd_len.push_back(p.query_len);
+        rf_start.push_back(intern(p.ref, p.ref_len)); rf_len.push_back(p.ref_len);
         mask.push_back(p.query_len);                       // maskLen = query_len (ssw_cpp.cpp:346)
         slot.push_back(i);
+        qbytes += p.query_len; tbytes += p.ref_len;
     }
     const int64_t n = (int64_t)slot.size();
     if (n == 0) return true;
+    std::vector<int8_t> arena((size_t)arena_bytes + 1);
+    mpn::parallel_for((int64_t)distinct.size(), 64, [&](int64_t d) {
+        if (distinct[d].first == nullptr) memcpy(arena.data() + start[d], reference_.data(), (size_t)distinct[d].second);
+        else translate_into(translate_, distinct[d].first, distinct[d].second, arena.data() + start[d]);
+    });
     uint8_t flag = 0;                                      // SetFlag, ssw_cpp.cpp:209-212
     if (filter.report_begin_position) flag |= 0x08;
     if (filter.report_cigar) flag |= 0x0f;
@@ -157,26 +178,28 @@ bool Aligner::AlignPairs(const std::vector<PairView>& pairs, const Filter& filte
     pr.mat = matrix_.data(); pr.n = n_; pr.gapO = gap_open_; pr.gapE = gap_extend_; pr.score_size = 2;
     pr.flag = flag; pr.filters = filter.score_filter; pr.filterd = filter.distance_filter;
     std::vector<mpn_result> res((size_t)n);
-    std::vector<uint32_t> arena((size_t)(n * 24 + (int64_t)qbytes / 4 + 4096));
+    std::vector<uint32_t> cig((size_t)(n * 24 + qbytes / 4 + 4096));
     int rc;
     for (int attempt = 0;; ++attempt) {
         mpn::SharedEngineLock lk;
-        rc = mpn_align_batch(lk.engine(), &pr, q.data(), qoff.data(), t.data(), toff.data(), mask.data(), n, res.data(), arena.data(), (int64_t)arena.size());
+        rc = mpn_align_batch_spans(lk.engine(), &pr, arena.data(), arena_bytes, rd_start.data(), rd_len.data(), rf_start.data(), rf_len.data(), mask.data(), n,
+                                   res.data(), cig.data(), (int64_t)cig.size());
         if (rc != MPN_E_CIGAR_SPACE || attempt == 1) break;
-        arena.resize((size_t)(2 * ((int64_t)qbytes + (int64_t)tbytes) + 16 * n));        // always enough: a CIGAR has at most read + target runs
+        cig.resize((size_t)(2 * (qbytes + tbytes) + 16 * n));          // always enough: a CIGAR has at most read + target runs
     }
     if (rc != 0) {
         fprintf(stderr, "[ssw_cpp] GPU alignment failed (code %d); this library has no CPU fallback\n", rc);
         abort();
     }
-    for (int64_t k = 0; k < n; ++k) {
-        const PairView& p = pairs[slot[k]];
+    for (int64_t k = 0; k < n; ++k)
         if (res[k].status != MPN_ST_OK) {                  // the reference dereferences a NULL s_align here; fail loudly instead
             fprintf(stderr, "[ssw_cpp] ssw_align returned no result for pair %lld\n", (long long)slot[k]);
             abort();
         }
-        finish_alignment(res[k], arena.data(), t.data() + toff[k], q.data() + qoff[k], p.query_len, &(*out)[slot[k]]);
-    }
+    // ---- '=' / 'X' CIGAR + mismatch count per pair (independent: host threads)
+    mpn::parallel_for(n, 256, [&](int64_t k) {
+        finish_alignment(res[k], cig.data(), arena.data() + rf_start[k], arena.data() + rd_start[k], rd_len[k], &(*out)[slot[k]]);
+    });
     return true;
 }
 

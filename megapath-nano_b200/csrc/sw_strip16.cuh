@@ -203,10 +203,24 @@ sw_strip16_kernel(const SwTask* __restrict__ tasks, int ntasks, int* __restrict_
                 uint32_t hnext = 0;
                 if (j + 1 < KR) hnext = add2(H[j], prmt(a, b, sel[j + 1]));   // uses H(j) of the previous column: diagonal of row j+1
                 else Hdtop = H[j];                                            // bottom H of the previous column: diagonal for the next stage
+#ifdef MPN_EXP_SPLITCHAIN                                                          // timing experiment (wrong results): two independent F chains per step
+                if (j == KR / 2) F = Ftop ^ cmin;
+#endif
+#ifdef MPN_EXP_FCHAIN
+                // short F chain: F' = max(F - e, max(h, E) - o) needs only F of the row above (valid for gapO >= gapE)
+                uint32_t Hp;
+                asm("max.s16x2.relu %0, %1, %2;" : "=r"(Hp) : "r"(h), "r"(E[j]));
+                const uint32_t Gp = add2(Hp, sc.mgapO2);
+                const uint32_t Hn = max2(Hp, F);
+                F = addmax_relu(F, sc.mgapE2, Gp);
+                const uint32_t Hg = add2(Hn, sc.mgapO2);
+                E[j] = addmax_relu(E[j], sc.mgapE2, Hg);
+#else
                 const uint32_t Hn = max3_relu(h, E[j], F);
                 const uint32_t Hg = add2(Hn, sc.mgapO2);
                 E[j] = addmax_relu(E[j], sc.mgapE2, Hg);
                 F = addmax_relu(F, sc.mgapE2, Hg);
+#endif
                 H[j] = Hn;
                 if (j & 1) m = max3(m, H[j - 1], Hn);
                 else if (j == KR - 1) m = max2(m, Hn);                        // odd KR: the last row has no partner

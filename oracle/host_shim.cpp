@@ -28,6 +28,26 @@ mpn_engine* shared_engine_locked() { return reinterpret_cast<mpn_engine*>(0x1); 
 }
 
 extern "C" int mpn_align_batch(mpn_engine*, const mpn_params* p, const int8_t* reads, const int64_t* read_off, const int8_t* refs,
+                               const int64_t* ref_off, const int32_t* masklen, int64_t npairs, mpn_result* out, uint32_t* cigar, int64_t cigar_cap);
+
+// spans -> CSR (the checkers take one pair per call anyway)
+extern "C" int mpn_align_batch_spans(mpn_engine* e, const mpn_params* p, const int8_t* seq, int64_t seq_bytes, const int64_t* rd_start, const int32_t* rd_len,
+                                     const int64_t* rf_start, const int32_t* rf_len, const int32_t* masklen, int64_t npairs,
+                                     mpn_result* out, uint32_t* cigar, int64_t cigar_cap)
+{
+    std::vector<int64_t> ro(1, 0), fo(1, 0);
+    std::vector<int8_t> reads, refs;
+    for (int64_t i = 0; i < npairs; ++i) {
+        if (rd_start[i] < 0 || rf_start[i] < 0 || rd_start[i] + rd_len[i] > seq_bytes || rf_start[i] + rf_len[i] > seq_bytes) return MPN_E_ARG;
+        reads.insert(reads.end(), seq + rd_start[i], seq + rd_start[i] + rd_len[i]);
+        refs.insert(refs.end(), seq + rf_start[i], seq + rf_start[i] + rf_len[i]);
+        ro.push_back((int64_t)reads.size()); fo.push_back((int64_t)refs.size());
+    }
+    reads.push_back(0); refs.push_back(0);
+    return mpn_align_batch(e, p, reads.data(), ro.data(), refs.data(), fo.data(), masklen, npairs, out, cigar, cigar_cap);
+}
+
+extern "C" int mpn_align_batch(mpn_engine*, const mpn_params* p, const int8_t* reads, const int64_t* read_off, const int8_t* refs,
                                const int64_t* ref_off, const int32_t* masklen, int64_t npairs, mpn_result* out, uint32_t* cigar, int64_t cigar_cap)
 {
     const int cap = 2048;
