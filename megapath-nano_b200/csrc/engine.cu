@@ -114,7 +114,7 @@ struct mpn_engine {
     int ev_valid = 0;
     DevPool pool;
     struct Slot { cudaStream_t st = nullptr; PinBuf pin_tasks, pin_fwd, pin_fin, pin_misc; };
-    static constexpr int NSLOT = 3;                  // slot 0 serves the phased API on the engine stream; 1..2 are the pipeline of mpn_align_batch
+    static constexpr int NSLOT = 5;                  // slot 0 serves the phased API on the engine stream; 1..4 are the pipeline of mpn_align_batch
     Slot slot[NSLOT];
     std::vector<int32_t> h_bin;
     std::vector<int64_t> h_order, h_idx, h_cnt;
@@ -654,7 +654,7 @@ extern "C" int mpn_align_batch(mpn_engine* e, const mpn_params* p, const int8_t*
     // Small batches: one chunk on the engine stream.  Large batches: chunks of ~128 k pairs alternate between two pipeline slots
     // (own stream + own pinned staging each), so the H2D copies and host-side scheduling of chunk k+1 overlap the kernels of chunk k
     // and the D2H of chunk k-1.
-    const int64_t CHUNK = 131072;
+    static const int64_t CHUNK = []() { const char* v = getenv("MPN_CHUNK_PAIRS"); const long long c = v ? atoll(v) : 0; return c >= 1024 ? (int64_t)c : (int64_t)131072; }();
     if (npairs <= CHUNK + CHUNK / 2) {
         mpn_batch* b = mpn_batch_upload(e, p, reads, read_off, refs, ref_off, masklen, npairs);
         if (!b) return MPN_E_ARG;
@@ -665,8 +665,12 @@ extern "C" int mpn_align_batch(mpn_engine* e, const mpn_params* p, const int8_t*
     }
     const int64_t nchunks = (npairs + CHUNK - 1) / CHUNK;
     const int64_t per = (npairs + nchunks - 1) / nchunks;
-    mpn_batch* inflight[2] = {nullptr, nullptr};
-    int64_t start_of[2] = {0, 0};
+    // ring of in-flight chunks, one pipeline slot each (own stream + own pinned staging).  Several chunks are queued on the GPU at any
+    // time, so the persistent grids of chunk k+1 fill the SMs that the tail of chunk k leaves idle, and the host work of a chunk
+    // (scheduling, H2D enqueue, D2H + record conversion) hides behind the kernels of the others.  Fetch order = chunk order (CIGAR offsets).
+    constexpr int DEPTH = mpn_engine::NSLOT - 1;
+    mpn_batch* inflight[DEPTH] = {};
+    int64_t start_of[DEPTH] = {};
     int64_t cig_base = 0;
     int rc = 0;
     auto drain = [&](int s) {
@@ -678,9 +682,10 @@ extern "C" int mpn_align_batch(mpn_engine* e, const mpn_params* p, const int8_t*
         mpn_batch_free(inflight[s]);
         inflight[s] = nullptr;
     };
-    for (int64_t c = 0; c < nchunks; ++c) {
-        const int s = (int)(c & 1);
-        drain(s);
+    int64_t issued = 0;
+    for (int64_t c = 0; c < nchunks; ++c, ++issued) {
+        const int s = (int)(c % DEPTH);
+        drain(s);                                   // the oldest chunk (c - DEPTH) used this slot
         const int64_t c0 = c * per, n_c = std::min(per, npairs - c0);
         if (n_c <= 0) break;
         mpn_batch* b = upload_impl(e, 1 + s, p, CsrPairs{reads, read_off + c0, refs, ref_off + c0, n_c}, masklen + c0, n_c);
@@ -688,8 +693,7 @@ extern "C" int mpn_align_batch(mpn_engine* e, const mpn_params* p, const int8_t*
         mpn_batch_run(b);
         inflight[s] = b; start_of[s] = c0;
     }
-    // results must come back in chunk order for the CIGAR offsets: the older in-flight chunk first
-    const int first = (inflight[0] && inflight[1]) ? (start_of[0] < start_of[1] ? 0 : 1) : 0;
-    drain(first); drain(1 - first);
+    // the remaining chunks, oldest first
+    for (int64_t c = std::max<int64_t>(0, issued - DEPTH); c < issued + DEPTH; ++c) drain((int)(c % DEPTH));
     return rc;
 }
