@@ -250,6 +250,15 @@ def main():
             "hbm": {"achieved_gbs": algo_bytes / (fwd_ms * 1e-3) / 1e9 if fwd_ms > 0 else None, "peak_gbs": hbm_peak,
                     "frac": (algo_bytes / (fwd_ms * 1e-3) / 1e9 / hbm_peak) if fwd_ms > 0 else None, "algorithmic_bytes_per_launch": algo_bytes},
             "traffic": None}
+    # DRAM bytes of the same forward pass from one `ncu --set full` capture (profiles/r01e_strip16_traffic.json, sum over the length bins
+    # of one pass = one "launch" of the dominant kernel); only quoted when the capture was taken on this workload size
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r01e_strip16_traffic.json")))
+        if args.config == 2 and b.npairs == 1_000_000:
+            roof["traffic"] = tr["forward_dram_bytes"]
+            roof["traffic_note"] = "dram__bytes_read.sum + dram__bytes_write.sum over the forward launches of one step; algorithmic bytes %.3g" % algo_bytes
+    except Exception:
+        pass
     if clocks and clocks.get("sm_mhz"):
         roof["frac_at_observed_clock"] = fwd_gcups / (peak_gcups * clocks["sm_mhz"] / sm_max) if fwd_gcups else None
 
