@@ -5,6 +5,7 @@
 #include "sw_common.cuh"
 #include "strip_table.h"
 #include "sw_wide32.cuh"
+#include "sw_long16.cuh"
 #include "sw_finish.cuh"
 #include "sw_trace.cuh"
 #include "sw_trace_narrow.cuh"
@@ -74,7 +75,9 @@ struct StripCfg { int G, KR, cap; StripFn fn; size_t smem; int blocks_per_sm; };
 std::vector<StripCfg> g_strips;
 std::vector<int16_t> g_bin_of_len;       // read length -> index into g_strips (smallest strip that fits)
 int N_STRIPS = 0;
+int LONG_BIN = 0;                        // pseudo-bin of the multi-strip clamped 16-bit kernel (sw_long16.cuh)
 int WIDE_BIN = 0;                        // pseudo-bin of the 32-bit kernel
+constexpr int LONG_KR = 16;
 
 void build_strip_table()
 {
@@ -89,7 +92,8 @@ void build_strip_table()
         }
     std::stable_sort(g_strips.begin(), g_strips.end(), [](const StripCfg& a, const StripCfg& b) { return a.cap < b.cap; });
     N_STRIPS = (int)g_strips.size();
-    WIDE_BIN = N_STRIPS;
+    LONG_BIN = N_STRIPS;
+    WIDE_BIN = N_STRIPS + 1;
     g_bin_of_len.assign((size_t)g_strips.back().cap + 1, 0);
     int k = 0;
     for (int len = 0; len <= g_strips.back().cap; ++len) {
@@ -134,7 +138,7 @@ struct mpn_batch {
     Score16 sc16{};
     FinishParams fin{};
     // device
-    DevBuf seq, mask, tasks_fwd, tasks_rev, ends_fwd, ends_rev, colrec, fwdres, finalres, counters, dmat, scratch, cig, wide_boundary, bandrec, flaglist;
+    DevBuf seq, mask, tasks_fwd, tasks_rev, ends_fwd, ends_rev, colrec, fwdres, finalres, counters, dmat, scratch, cig, wide_boundary, long_boundary, bandrec, flaglist;
     size_t seq_reads_bytes = 0, seq_bytes = 0;
     int64_t colrec_words = 0;
     unsigned long long scratch_bytes = 0, cig_cap = 0;
@@ -238,7 +242,7 @@ extern "C" void mpn_batch_free(mpn_batch* b)
     if (!b) return;
     cudaSetDevice(b->e->device);
     DevBuf* bufs[] = {&b->seq, &b->mask, &b->tasks_fwd, &b->tasks_rev, &b->ends_fwd, &b->ends_rev,
-                      &b->colrec, &b->fwdres, &b->finalres, &b->counters, &b->dmat, &b->scratch, &b->cig, &b->wide_boundary, &b->bandrec, &b->flaglist};
+                      &b->colrec, &b->fwdres, &b->finalres, &b->counters, &b->dmat, &b->scratch, &b->cig, &b->wide_boundary, &b->long_boundary, &b->bandrec, &b->flaglist};
     for (DevBuf* d : bufs) b->e->pool.give(*d);
     delete b;
 }
@@ -315,10 +319,11 @@ static mpn_batch* upload_impl(mpn_engine* e, int slot_id, const mpn_params* p, c
     // ---- per-pair lengths, binning
     std::vector<int32_t>& bin = e->h_bin;
     bin.resize(npairs);
-    std::vector<int64_t> bin_count(N_STRIPS + 1, 0);
+    std::vector<int64_t> bin_count(N_STRIPS + 2, 0);
     int64_t cm_total = 0, cells = 0;
     int max_rd = 0, max_rf = 0, min_rf = 0x7fffffff;
     const bool packed_ok = n <= 8;
+    static const bool no_long16 = getenv("MPN_NO_LONG16") != nullptr;      // A/B switch: send long / saturating pairs to the 32-bit kernel
     const int64_t maxpos = std::max(maxv, 0);
     for (int64_t i = 0; i < npairs; ++i) {
         const int64_t rl = src.rl(i), fl = src.fl(i);
@@ -326,18 +331,20 @@ static mpn_batch* upload_impl(mpn_engine* e, int slot_id, const mpn_params* p, c
         cells += rl * fl;
         max_rd = std::max<int>(max_rd, (int)rl); max_rf = std::max<int>(max_rf, (int)fl); min_rf = std::min<int>(min_rf, (int)fl);
         cm_total += fl;
-        int c = WIDE_BIN;
-        // the packed kernel is exact as long as no H can reach the int16 clamp of ssw.c:425 (and the add cannot wrap)
+        int c = packed_ok ? LONG_BIN : WIDE_BIN;
+        // the short-read packed kernel is exact as long as no H can reach the int16 clamp of ssw.c:425 (and the add cannot wrap);
+        // longer reads and pairs that can saturate go to the multi-strip kernel, which carries the clamp
         if (packed_ok && (std::min(rl, fl) + 1) * maxpos <= 32767 && rl < (int64_t)g_bin_of_len.size()) c = g_bin_of_len[rl];
+        if (no_long16 && c == LONG_BIN) c = WIDE_BIN;
         bin[i] = c; bin_count[c]++;
     }
     b->total_cells = cells; b->max_rd = max_rd; b->colrec_words = cm_total;
-    b->n_wide_pre = bin_count[WIDE_BIN];
+    b->n_wide_pre = bin_count[WIDE_BIN] + bin_count[LONG_BIN];
     {   // a launch with too few tasks cannot fill the GPU and the launches of a batch run back to back: fold thin bins into the next
         // larger strip (a few more dead rows, far better occupancy).  The largest packed bin keeps whatever it has.
         const int64_t thin = (int64_t)e->sm_count * 64;
-        std::vector<int> remap(N_STRIPS + 1);
-        for (int c = 0; c <= N_STRIPS; ++c) remap[c] = c;
+        std::vector<int> remap(N_STRIPS + 2);
+        for (int c = 0; c <= N_STRIPS + 1; ++c) remap[c] = c;
         bool any = false;
         for (int c = 0; c + 1 < N_STRIPS; ++c) {
             if (bin_count[c] == 0 || bin_count[c] >= thin) continue;
@@ -354,8 +361,8 @@ static mpn_batch* upload_impl(mpn_engine* e, int slot_id, const mpn_params* p, c
 
     // ---- task lists in pinned staging: per bin, longest targets first (counting sort on target length) so that the groups of
     //      a warp run in step and the tail of a launch is made of short tasks
-    std::vector<int64_t> bin_first(N_STRIPS + 2, 0);
-    for (int c = 0; c <= N_STRIPS; ++c) bin_first[c + 1] = bin_first[c] + bin_count[c];
+    std::vector<int64_t> bin_first(N_STRIPS + 3, 0);
+    for (int c = 0; c <= N_STRIPS + 1; ++c) bin_first[c + 1] = bin_first[c] + bin_count[c];
     sl.pin_tasks.reserve(sizeof(SwTask) * (size_t)(npairs + 1));
     SwTask* h_tasks = sl.pin_tasks.as<SwTask>();
     {
@@ -383,7 +390,7 @@ static mpn_batch* upload_impl(mpn_engine* e, int slot_id, const mpn_params* p, c
             t.dir = 1; t.out = (int32_t)i; t.stop = 0; t.pad_ = 0;
         }
     }
-    for (int c = 0; c <= N_STRIPS; ++c) if (bin_count[c] > 0) b->bins.push_back(BinLaunch{c, bin_first[c], bin_count[c]});
+    for (int c = 0; c <= N_STRIPS + 1; ++c) if (bin_count[c] > 0) b->bins.push_back(BinLaunch{c, bin_first[c], bin_count[c]});
 
     // ---- device buffers + uploads (straight from the caller's buffers: pinned caller memory gives full PCIe rate)
     DevPool& pool = e->pool;
@@ -412,6 +419,8 @@ static mpn_batch* upload_impl(mpn_engine* e, int slot_id, const mpn_params* p, c
     b->wide_blocks = e->sm_count * 3;
     b->wide_stride = ((long long)max_rf + 63) & ~63ll;
     pool.take(b->wide_boundary, sizeof(int) * (size_t)b->wide_blocks * (WIDE_BLOCK / 32) * 2 * (size_t)b->wide_stride + 256);
+    // the multi-strip 16-bit kernel may run concurrently with the 32-bit one (bins of a pass are launched on side streams): own buffer
+    if (bin_count[LONG_BIN] > 0) pool.take(b->long_boundary, sizeof(uint32_t) * (size_t)b->wide_blocks * (LONG_BLOCK / 32) * 2 * (size_t)b->wide_stride + 256);
 
     // ---- traceback arenas.  Direction bytes: (2*band+1) per read row; the first attempt has band |dlen|+1 and most pairs
     // stop there.  Budget 16 band cells per read base (+ slack); pairs that do not fit are reported (status 5) and re-run by fetch.
@@ -471,7 +480,12 @@ static void launch_strips(mpn_batch* b, const SwTask* tasks, bool forward, SwEnd
         const BinLaunch& bl = b->bins[bi];
         cudaStream_t st = fork ? e->aux[turn++ % mpn_engine::NAUX] : main_st;
         int* counter = reinterpret_cast<int*>(b->counters.as<unsigned long long>() + slot++);
-        if (bl.cfg == WIDE_BIN) {
+        if (bl.cfg == LONG_BIN) {
+            const int blocks = (int)std::min<int64_t>((bl.count + LONG_BLOCK / 32 - 1) / (LONG_BLOCK / 32), b->wide_blocks);
+            sw_long16_kernel<LONG_KR><<<blocks, LONG_BLOCK, long16_smem_bytes<LONG_KR>(), st>>>(tasks + bl.first, (int)bl.count, counter, b->seq.as<int8_t>(), b->sc16,
+                forward ? b->colrec.as<uint32_t>() : nullptr, ends, b->long_boundary.as<uint32_t>(), b->wide_stride);
+            e->wide_pairs += forward ? bl.count : 0;
+        } else if (bl.cfg == WIDE_BIN) {
             launch_wide32_impl(tasks + bl.first, (int)bl.count, counter, b->seq.as<int8_t>(), b->dmat.as<int8_t>(), b->p.n, b->fin.gapO, b->fin.gapE,
                                forward ? b->colrec.as<uint32_t>() : nullptr, ends, b->wide_boundary.as<int>(), b->wide_stride, b->wide_blocks, 0, st);
             e->wide_pairs += forward ? bl.count : 0;
