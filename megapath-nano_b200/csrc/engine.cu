@@ -138,7 +138,7 @@ struct mpn_batch {
     Score16 sc16{};
     FinishParams fin{};
     // device
-    DevBuf seq, mask, tasks_fwd, tasks_rev, ends_fwd, ends_rev, colrec, fwdres, finalres, counters, dmat, scratch, cig, wide_boundary, long_boundary, bandrec, flaglist;
+    DevBuf seq, mask, tasks_fwd, tasks_rev, ends_fwd, ends_rev, colrec, fwdres, finalres, counters, dmat, scratch, cig, wide_boundary, long_boundary, warp_dir, bandrec, flaglist;
     size_t seq_reads_bytes = 0, seq_bytes = 0;
     int64_t colrec_words = 0;
     unsigned long long scratch_bytes = 0, cig_cap = 0;
@@ -148,6 +148,7 @@ struct mpn_batch {
     bool pipelined = false;               // owned by mpn_align_batch's chunk pipeline: no host synchronisation inside upload
     size_t h2d_bytes = 0, d2h_bytes = 0;
     long long wide_stride = 0; int wide_blocks = 0;
+    unsigned long long warp_dir_stride = 0; int warp_trace_blocks = 1;
 };
 
 extern "C" mpn_engine* mpn_engine_create(int device)
@@ -242,7 +243,7 @@ extern "C" void mpn_batch_free(mpn_batch* b)
     if (!b) return;
     cudaSetDevice(b->e->device);
     DevBuf* bufs[] = {&b->seq, &b->mask, &b->tasks_fwd, &b->tasks_rev, &b->ends_fwd, &b->ends_rev,
-                      &b->colrec, &b->fwdres, &b->finalres, &b->counters, &b->dmat, &b->scratch, &b->cig, &b->wide_boundary, &b->long_boundary, &b->bandrec, &b->flaglist};
+                      &b->colrec, &b->fwdres, &b->finalres, &b->counters, &b->dmat, &b->scratch, &b->cig, &b->wide_boundary, &b->long_boundary, &b->warp_dir, &b->bandrec, &b->flaglist};
     for (DevBuf* d : bufs) b->e->pool.give(*d);
     delete b;
 }
@@ -431,6 +432,14 @@ static mpn_batch* upload_impl(mpn_engine* e, int slot_id, const mpn_params* p, c
         b->scratch_bytes = (unsigned long long)read_bases * 24ull + (unsigned long long)npairs * 512ull + (64ull << 20);
         b->cig_cap = (unsigned long long)npairs * 24ull + (unsigned long long)read_bases / 4ull + 4096ull;
         pool.take(b->scratch, b->scratch_bytes);
+        // wide-band traceback: a direction region per resident warp (band cells x longest read), reused for every attempt and pair;
+        // with ONT-scale reads the grid shrinks so that the regions stay within a few GB
+        b->warp_dir_stride = warptr_region_bytes(std::max(max_rd, 1));
+        const unsigned long long budget = 6ull << 30;
+        long long wb = (long long)(budget / (b->warp_dir_stride * WARPTR_WARPS));
+        wb = std::min<long long>(wb, (npairs + WARPTR_WARPS - 1) / WARPTR_WARPS);
+        b->warp_trace_blocks = (int)std::max<long long>(std::min<long long>(wb, (long long)e->sm_count * 4), 1);
+        pool.take(b->warp_dir, (size_t)b->warp_dir_stride * WARPTR_WARPS * (size_t)b->warp_trace_blocks + 256);
         pool.take(b->cig, b->cig_cap * sizeof(uint32_t));
     }
     // the task list sits in slot-owned pinned staging that the next upload on this slot overwrites: the phased API waits for
@@ -567,9 +576,9 @@ extern "C" int mpn_batch_run(mpn_batch* b)
                 b->cig.as<uint32_t>(), b->cig_cap, b->counters.as<unsigned long long>() + 65, b->finalres.as<FinalResult>());
             CK(cudaGetLastError());
             // wide bands: one warp per flagged pair
-            sw_trace_warp_kernel<<<e->sm_count * 4, 32 * WARPTR_WARPS, warptr_smem_bytes(b->p.n), st>>>(b->tasks_fwd.as<SwTask>(), b->flaglist.as<int>(),
+            sw_trace_warp_kernel<<<b->warp_trace_blocks, 32 * WARPTR_WARPS, warptr_smem_bytes(b->p.n), st>>>(b->tasks_fwd.as<SwTask>(), b->flaglist.as<int>(),
                 reinterpret_cast<int*>(b->counters.as<unsigned long long>() + 103), reinterpret_cast<int*>(b->counters.as<unsigned long long>() + 104), b->seq.as<int8_t>(),
-                b->fwdres.as<FwdResult>(), tp, ar, b->cig.as<uint32_t>(), b->cig_cap, b->counters.as<unsigned long long>() + 65, b->finalres.as<FinalResult>(), b->bandrec.as<BandRec>());
+                b->fwdres.as<FwdResult>(), tp, b->warp_dir.as<uint8_t>(), b->warp_dir_stride, b->cig.as<uint32_t>(), b->cig_cap, b->counters.as<unsigned long long>() + 65, b->finalres.as<FinalResult>(), b->bandrec.as<BandRec>());
             CK(cudaGetLastError());
             e->launches += 3;
         }

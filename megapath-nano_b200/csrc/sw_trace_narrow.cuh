@@ -21,6 +21,8 @@ constexpr int NARROW_BLOCK = 64;
 inline size_t narrow_smem_bytes() { return 3ull * NARROW_W * NARROW_BLOCK * sizeof(int) + 8 * sizeof(unsigned long long); }
 
 // per-pair hand-over from the DP kernel to the traceback kernel
+constexpr int NARROW_MAX_ROWS = 1536;       // longer reads go to the warp-parallel kernel whatever their band
+
 struct BandRec {
     unsigned long long dir_off;   // byte offset of the pair's direction words in the scratch arena
     int32_t bw;                   // band half-width of the successful attempt
@@ -93,7 +95,10 @@ sw_band_dp_kernel(const SwTask* __restrict__ order, int ntasks, int* __restrict_
                             unsigned long long o = atomicAdd(cig_used, 1ull);          // "1M" (ssw.c:625,680-687)
                             if (o + 1 > cig_cap) r.status = 6;
                             else { cig[o] = 1u << 4; r.cigar_off = (int64_t)o; r.cigar_len = 1; }
-                        } else if (n > 8 || bw > NARROW_BW) { r.status = 7; br.bw = bw; flag_list[atomicAdd(nflag, 1)] = k; }
+                        } else if (n > 8 || bw > NARROW_BW || sub_read > NARROW_MAX_ROWS) {
+                            // wide bands, and reads so long that one lane would serialise millions of cells: one warp per pair instead
+                            r.status = 7; br.bw = bw; flag_list[atomicAdd(nflag, 1)] = k;
+                        }
                         else {
                             ref = useq + tk.rf_base + r.ref_begin1;
                             read = useq + tk.rd_base + r.read_begin1;
