@@ -10,7 +10,7 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PKG = os.path.join(ROOT, "megapath-nano_b200")
-LIBS = [os.path.join(PKG, "libmpn_ssw.so"), os.path.join(PKG, "realign", "libssw.so")]
+LIBS = [os.path.join(PKG, "libmpn_ssw.so"), os.path.join(PKG, "realign", "libssw.so"), os.path.join(PKG, "realign", "realigner")]
 
 
 def declared_functions(header):
@@ -29,11 +29,13 @@ def built():
 
 def test_headers_declare_the_reference_entry_points():
     assert set(declared_functions("ssw.h")) >= {"ssw_init", "init_destroy", "ssw_align", "align_destroy"}
-    assert set(declared_functions("mpn_ssw_batch.h")) >= {"mpn_engine_create", "mpn_align_batch", "mpn_batch_upload", "mpn_batch_run", "mpn_batch_fetch", "mpn_batch_free"}
+    assert set(declared_functions("mpn_ssw_batch.h")) >= {"mpn_engine_create", "mpn_align_batch", "mpn_align_batch_spans", "mpn_batch_upload", "mpn_batch_upload_spans",
+                                                          "mpn_batch_run", "mpn_batch_fetch", "mpn_batch_free"}
+    assert set(declared_functions("realigner.h")) >= {"realign_reads", "free_memory", "mpn_realign_regions"}
 
 
 def test_libraries_export_every_declared_symbol(built):
-    want = declared_functions("ssw.h") + declared_functions("mpn_ssw_batch.h")
+    want = declared_functions("ssw.h") + declared_functions("mpn_ssw_batch.h") + declared_functions("realigner.h")
     for path in built:
         lib = ct.CDLL(path)
         for name in want:
@@ -52,6 +54,26 @@ def test_s_align_layout_is_the_reference_layout(tmp_path):
     assert got == [40, 0, 2, 4, 8, 12, 16, 20, 24, 32]
     pyssw = importlib.import_module("megapath-nano_b200.pyssw")
     assert ct.sizeof(pyssw.CAlignRes) == 40 and pyssw.CAlignRes.sCigar.offset == 24 and pyssw.CAlignRes.nCigarLen.offset == 32
+
+
+def test_struct_str_arr_layout_and_cpp_front_end_symbols(built, tmp_path):
+    """struct_str_arr is what realign_illumina_reads.py:40-43 mirrors (1000 ints, 1000 pointers), and the C++ front end of
+    include/ssw_cpp.h links: a translation unit that uses the class compiles and resolves against libmpn_ssw.so"""
+    R = importlib.import_module("megapath-nano_b200.realigner")
+    assert ct.sizeof(R.StructPointer) == 1000 * 4 + 1000 * 8 and R.StructPointer.cigar_string.offset == 4000
+    src = tmp_path / "lay2.c"
+    src.write_text('#include <stddef.h>\n#include <stdio.h>\n#include "realigner.h"\nint main(void){printf("%zu %zu %zu\\n", sizeof(struct_str_arr), offsetof(struct_str_arr, cigar_string), sizeof(mpn_region)); return 0;}\n')
+    exe = tmp_path / "lay2"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)], check=True)
+    got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    assert got == [12000, 4000, ct.sizeof(R.MpnRegion)]
+    cpp = tmp_path / "use.cpp"
+    cpp.write_text('#include "ssw_cpp.h"\nint probe(){ StripedSmithWaterman::Aligner a(4, 6, 8, 2); StripedSmithWaterman::Filter f; StripedSmithWaterman::Alignment al;'
+                   ' std::vector<StripedSmithWaterman::PairView> pv; std::vector<StripedSmithWaterman::Alignment> out; a.SetReferenceSequence("ACGT", 4);'
+                   ' return (int)a.AlignPairs(pv, f, &out) + (int)sizeof(al); }\n')
+    so = tmp_path / "use.so"
+    subprocess.run(["g++", "-std=c++17", "-shared", "-fPIC", "-I", os.path.join(ROOT, "include"), "-o", str(so), str(cpp), built[0], "-Wl,-z,defs",
+                    "-Wl,-rpath," + PKG], check=True)
 
 
 def test_cigar_helpers_match_reference_encoding(tmp_path):
