@@ -149,6 +149,8 @@ struct mpn_batch {
     size_t h2d_bytes = 0, d2h_bytes = 0;
     long long wide_stride = 0; int wide_blocks = 0;
     unsigned long long warp_dir_stride = 0; int warp_trace_blocks = 1;
+    int64_t sum_rd = 0, sum_rf = 0;       // over pairs (worst-case CIGAR words = sum_rd + sum_rf)
+    int arena_retries = 0;
 };
 
 extern "C" mpn_engine* mpn_engine_create(int device)
@@ -340,6 +342,7 @@ static mpn_batch* upload_impl(mpn_engine* e, int slot_id, const mpn_params* p, c
         bin[i] = c; bin_count[c]++;
     }
     b->total_cells = cells; b->max_rd = max_rd; b->colrec_words = cm_total;
+    b->sum_rf = cm_total; b->sum_rd = src.read_bases();
     b->n_wide_pre = bin_count[WIDE_BIN] + bin_count[LONG_BIN];
     {   // a launch with too few tasks cannot fill the GPU and the launches of a batch run back to back: fold thin bins into the next
         // larger strip (a few more dead rows, far better occupancy).  The largest packed bin keeps whatever it has.
@@ -646,12 +649,27 @@ static int fetch_impl(mpn_batch* b, mpn_result* out, uint32_t* cigar, int64_t ci
             r.cigar_len = g.cigar_len; r.cigar_off = g.cigar_len > 0 ? g.cigar_off + cigar_base : 0;
             if (g.status == 3) r.status = MPN_ST_NULL;
             else if (g.status != 0) {
-                if (rc == 0) fprintf(stderr, "[mpn_ssw] traceback could not complete (first at pair %lld, status %d: 5/6 = arena exhausted, 7/8 = band beyond kernel limits)\n", (long long)i, g.status);
+                if (rc == 0 && (b->arena_retries > 0 || (g.status != 5 && g.status != 6))) fprintf(stderr, "[mpn_ssw] traceback could not complete (first at pair %lld, status %d: 5/6 = arena exhausted, 7/8 = band beyond kernel limits)\n", (long long)i, g.status);
                 rc = MPN_E_UNSUPPORTED;
             }
         }
     }
     CK(cudaStreamSynchronize(st));      // CIGAR arena copy
+    if (rc == MPN_E_UNSUPPORTED && b->arena_retries == 0) {
+        // An arena of the traceback ran out (statuses 5 / 6: direction words or CIGAR words beyond the typical-case budget, e.g.
+        // reads made of alternating indels).  Size both for the worst case and run the batch once more; results are deterministic.
+        bool arena = false;
+        for (int64_t i = 0; i < n && !arena; ++i) arena = h_fwd[i].status == 0 && (h_fin[i].status == 5 || h_fin[i].status == 6);
+        if (arena) {
+            b->arena_retries = 1;
+            b->scratch_bytes = b->scratch_bytes * 8ull + (unsigned long long)b->sum_rd * 64ull;
+            b->cig_cap = (unsigned long long)(b->sum_rd + b->sum_rf) + 2ull * (unsigned long long)n + 4096ull;
+            e->pool.take(b->scratch, b->scratch_bytes);
+            e->pool.take(b->cig, b->cig_cap * sizeof(uint32_t));
+            mpn_batch_run(b);
+            return fetch_impl(b, out, cigar, cigar_cap, cigar_base, cigar_words);
+        }
+    }
     return rc;
 }
 

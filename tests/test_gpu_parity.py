@@ -207,3 +207,24 @@ def test_config5_mixed_lengths_sample(eng):
     r, c = oracle_table(sub, cap=cap, threads=os.cpu_count() or 8)
     bad = diff(g, gc, r, c)
     assert len(bad) == 0, (bad[:5], g[bad[:2]], r[bad[:2]], sub.read_len[bad[:5]])
+
+
+def test_cigar_dense_pairs_exceed_the_typical_arena(eng):
+    """reads that delete every third target base, cheap gaps: about one CIGAR word per read base, far beyond the typical-case
+    arena budget (24 words per pair + 1 per 4 read bases) -> the engine must size for the worst case and re-run, not fail"""
+    rng = np.random.default_rng(21)
+    reads, refs = [], []
+    for _ in range(96):
+        t = rng.integers(0, 4, size=int(rng.integers(400, 700))).astype(np.int8)
+        keep = np.ones(len(t), bool); keep[2::3] = False
+        reads.append(t[keep][:300]); refs.append(t)
+    ro = np.concatenate([[0], np.cumsum([len(x) for x in reads])]).astype(np.int64)
+    fo = np.concatenate([[0], np.cumsum([len(x) for x in refs])]).astype(np.int64)
+    mat = w.dna_matrix(5, 6)
+    b = w.PairBatch(np.concatenate(reads), ro, np.concatenate(refs), fo, np.full(len(reads), 40, np.int32), mat=mat, gapO=2, gapE=1, flag=1)
+    cap = 1024
+    rec, cig = eng.align(b, cigar_cap=int(b.read_len.sum() + b.ref_len.sum()))
+    g, gc = B.as_table(rec, cig, cap)
+    r, c = oracle_table(b, cap=cap)
+    assert len(diff(g, gc, r, c)) == 0
+    assert int(rec["cigar_len"].sum()) > b.npairs * 24 + int(b.read_len.sum()) // 4 + 4096
