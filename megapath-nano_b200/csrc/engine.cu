@@ -10,6 +10,7 @@
 #include "sw_trace.cuh"
 #include "sw_trace_narrow.cuh"
 #include "sw_trace_warp.cuh"
+#include "sw_trace_rows.cuh"
 
 #include <algorithm>
 #include <cstdio>
@@ -138,7 +139,7 @@ struct mpn_batch {
     Score16 sc16{};
     FinishParams fin{};
     // device
-    DevBuf seq, mask, tasks_fwd, tasks_rev, ends_fwd, ends_rev, colrec, fwdres, finalres, counters, dmat, scratch, cig, wide_boundary, long_boundary, warp_dir, bandrec, flaglist;
+    DevBuf seq, mask, tasks_fwd, tasks_rev, ends_fwd, ends_rev, colrec, fwdres, finalres, counters, dmat, scratch, cig, wide_boundary, long_boundary, warp_dir, bandrec, flaglist, bandq_items, bandq_meta;
     size_t seq_reads_bytes = 0, seq_bytes = 0;
     int64_t colrec_words = 0;
     unsigned long long scratch_bytes = 0, cig_cap = 0;
@@ -245,7 +246,7 @@ extern "C" void mpn_batch_free(mpn_batch* b)
     if (!b) return;
     cudaSetDevice(b->e->device);
     DevBuf* bufs[] = {&b->seq, &b->mask, &b->tasks_fwd, &b->tasks_rev, &b->ends_fwd, &b->ends_rev,
-                      &b->colrec, &b->fwdres, &b->finalres, &b->counters, &b->dmat, &b->scratch, &b->cig, &b->wide_boundary, &b->long_boundary, &b->warp_dir, &b->bandrec, &b->flaglist};
+                      &b->colrec, &b->fwdres, &b->finalres, &b->counters, &b->dmat, &b->scratch, &b->cig, &b->wide_boundary, &b->long_boundary, &b->warp_dir, &b->bandrec, &b->flaglist, &b->bandq_items, &b->bandq_meta};
     for (DevBuf* d : bufs) b->e->pool.give(*d);
     delete b;
 }
@@ -429,7 +430,11 @@ static mpn_batch* upload_impl(mpn_engine* e, int slot_id, const mpn_params* p, c
     // ---- traceback arenas.  Direction bytes: (2*band+1) per read row; the first attempt has band |dlen|+1 and most pairs
     // stop there.  Budget 16 band cells per read base (+ slack); pairs that do not fit are reported (status 5) and re-run by fetch.
     const bool want_cigar = (p->flag & 7) != 0;
-    if ((p->flag & 0xff) != 0) { pool.take(b->bandrec, sizeof(BandRec) * (size_t)(npairs + 1)); pool.take(b->flaglist, sizeof(int) * (size_t)(npairs + 1)); }
+    if ((p->flag & 0xff) != 0) {
+        pool.take(b->bandrec, sizeof(BandRec) * (size_t)(npairs + 1)); pool.take(b->flaglist, sizeof(int) * (size_t)(npairs + 1));
+        pool.take(b->bandq_items, sizeof(int2) * (size_t)ROWS_CLASSES * (size_t)(npairs + 1));     // one work queue per band-width class
+        pool.take(b->bandq_meta, 64 * sizeof(int));
+    }
     if (want_cigar) {
         int64_t read_bases = (int64_t)reads_bytes;
         b->scratch_bytes = (unsigned long long)read_bases * 24ull + (unsigned long long)npairs * 512ull + (64ull << 20);
@@ -563,18 +568,24 @@ extern "C" int mpn_batch_run(mpn_batch* b)
         TraceParams tp{b->fin.flag, b->fin.filters, b->p.filterd, b->fin.gapO, b->fin.gapE, b->p.n, b->dmat.as<int8_t>()};
         Arena ar{b->scratch.as<uint8_t>(), b->scratch_bytes, b->counters.as<unsigned long long>() + 64};
         {
-            // narrow bands: lane-persistent DP kernel, then one-thread-per-pair traceback
-            int nb = 0;
-            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, sw_band_dp_kernel, NARROW_BLOCK, narrow_smem_bytes()));
-            // lanes are persistent workers: give each about 6 pairs (load balance across unequal bands) while keeping >= 4 blocks per SM
-            int64_t want = (n + NARROW_BLOCK * 6 - 1) / (NARROW_BLOCK * 6);
-            want = std::max<int64_t>(want, std::min<int64_t>((n + NARROW_BLOCK - 1) / NARROW_BLOCK, (int64_t)e->sm_count * 4));
-            const unsigned blocks = (unsigned)std::min<int64_t>(want, (int64_t)e->sm_count * std::max(nb, 1));
-            sw_band_dp_kernel<<<blocks, NARROW_BLOCK, narrow_smem_bytes(), st>>>(b->tasks_fwd.as<SwTask>(), (int)n, reinterpret_cast<int*>(b->counters.as<unsigned long long>() + 102),
-                b->seq.as<int8_t>(), b->fwdres.as<FwdResult>(), b->ends_rev.as<SwEnds>(), tp, ar, b->cig.as<uint32_t>(), b->cig_cap,
-                b->counters.as<unsigned long long>() + 65, b->finalres.as<FinalResult>(), b->bandrec.as<BandRec>(), b->flaglist.as<int>(),
-                reinterpret_cast<int*>(b->counters.as<unsigned long long>() + 103));
+            // narrow bands: setup (begin positions, filters, one queue per band-width class), then one lane-persistent row kernel per
+            // class in increasing order (a failed attempt re-queues the pair for the doubled band = a later class), then one-thread-per-pair traceback
+            CK(cudaMemsetAsync(b->bandq_meta.p, 0, 64 * sizeof(int), st));
+            BandQueues bq{b->bandq_items.as<int2>(), b->bandq_meta.as<int>(), b->bandq_meta.as<int>() + 16, (int)n};
+            sw_band_setup_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(b->tasks_fwd.as<SwTask>(), (int)n, b->fwdres.as<FwdResult>(), b->ends_rev.as<SwEnds>(), tp,
+                b->cig.as<uint32_t>(), b->cig_cap, b->counters.as<unsigned long long>() + 65, b->finalres.as<FinalResult>(), b->bandrec.as<BandRec>(), b->flaglist.as<int>(),
+                reinterpret_cast<int*>(b->counters.as<unsigned long long>() + 103), bq);
             CK(cudaGetLastError());
+            {
+                const unsigned rows_blocks = (unsigned)std::max<int64_t>(1, std::min<int64_t>((n + ROWS_BLOCK - 1) / ROWS_BLOCK, (int64_t)e->sm_count * 8));
+                int* const nflag = reinterpret_cast<int*>(b->counters.as<unsigned long long>() + 103);
+#define MPN_ROWS_LAUNCH(CLS) sw_band_rows_kernel<CLS><<<rows_blocks, ROWS_BLOCK, 0, st>>>(b->tasks_fwd.as<SwTask>(), b->seq.as<int8_t>(), b->fwdres.as<FwdResult>(), tp, ar, \
+                    b->finalres.as<FinalResult>(), b->bandrec.as<BandRec>(), b->flaglist.as<int>(), nflag, bq)
+                MPN_ROWS_LAUNCH(0); MPN_ROWS_LAUNCH(1); MPN_ROWS_LAUNCH(2); MPN_ROWS_LAUNCH(3);
+#undef MPN_ROWS_LAUNCH
+                CK(cudaGetLastError());
+                e->launches += 5;
+            }
             sw_band_trace_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(b->tasks_fwd.as<SwTask>(), (int)n, b->fwdres.as<FwdResult>(), b->bandrec.as<BandRec>(), ar,
                 b->cig.as<uint32_t>(), b->cig_cap, b->counters.as<unsigned long long>() + 65, b->finalres.as<FinalResult>());
             CK(cudaGetLastError());

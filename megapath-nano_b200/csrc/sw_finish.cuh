@@ -54,6 +54,7 @@ __global__ void __launch_bounds__(128)
 sw_finish_kernel(const SwTask* __restrict__ fwd_tasks, int ntasks, const SwEnds* __restrict__ ends, const uint32_t* __restrict__ colrec,
                  PairArrays pa, FinishParams fp, FwdResult* __restrict__ res, SwTask* __restrict__ rev_tasks)
 {
+    __shared__ int fsm[4 * 128];                  // per warp: ring of B (64) + ring of prefix maxima (64)
     const int lane = threadIdx.x & 31;
     const int k = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
     if (k >= ntasks) return;
@@ -82,38 +83,41 @@ sw_finish_kernel(const SwTask* __restrict__ fwd_tasks, int ntasks, const SwEnds*
         const int e1 = max(end_ref - masklen, 0);
         const int e2 = min(end_ref + masklen, rf_len) + (byte_mode ? 1 : 0);
         const uint32_t* rec = colrec + tk.cm_off;
-        // running state across chunks of 32 columns
-        int prevB = 0;                 // B of the previous chunk, per lane
-        int prevPM = INT_MIN / 2;      // inclusive prefix max of (B[j] + j*gapE) of the previous chunk, per lane
-        int carryPM = INT_MIN / 2;     // prefix max over all earlier chunks
+        // Two 64-entry rings in shared memory (this warp's slice) hold B and the prefix maximum of the last two chunks, so "the value
+        // d columns back" is one LDS instead of a two-shuffle select.  Entries of columns < 0 are the zero / -inf the formulas expect.
+        int* ringB = fsm + (threadIdx.x >> 5) * 128;
+        int* ringX = ringB + 64;
+        const int NEGV = INT_MIN / 2;
+        ringB[lane] = 0; ringB[32 + lane] = 0; ringX[lane] = NEGV; ringX[32 + lane] = NEGV;
+        __syncwarp();
+        int carryPM = NEGV;            // prefix max of (B[j] + j*gapE) over all earlier chunks
         int bestL = 0, idxL = 0, bestR = 0, idxR = 0;     // strict-greater-first maxima of the two ranges (per lane, merged at the end)
         bool anyL = false, anyR = false;
         for (int c0 = 0; c0 < rf_len; c0 += 32) {
             const int c = c0 + lane;
-            uint32_t w = c < rf_len ? rec[c] : 0u;
-            int cm = (int)(w & 0xffffu), B = (int)(w >> 16);
+            const uint32_t w = c < rf_len ? rec[c] : 0u;
+            const int cm = (int)(w & 0xffffu), B = (int)(w >> 16);
             int v = cm;
             if (P > 0) {
-                // window maximum of B over the previous P (<= 15) columns
-                int win = 0;
-                for (int d = 1; d <= P; ++d) {
-                    int bv = shift_back(B, prevB, d, lane);
-                    if (c - d >= 0) win = max(win, bv);
-                }
-                v = max(v, win);
+                ringB[c & 63] = B;
                 // eroded contribution: PM[c-P-1] - gapO - (c-P-1)*gapE with PM the inclusive prefix max of B[j] + j*gapE
-                int x = c < rf_len ? B + c * fp.gapE : INT_MIN / 2;
+                int x = c < rf_len ? B + c * fp.gapE : NEGV;
 #pragma unroll
                 for (int off = 1; off < 32; off <<= 1) {
-                    int o = __shfl_up_sync(0xffffffffu, x, off);
+                    const int o = __shfl_up_sync(0xffffffffu, x, off);
                     if (lane >= off) x = max(x, o);
                 }
                 x = max(x, carryPM);
-                int pm = shift_back(x, prevPM, P + 1, lane);
-                if (c - P - 1 >= 0) v = max(v, pm - fp.gapO - (c - P - 1) * fp.gapE);
+                ringX[c & 63] = x;
                 carryPM = __shfl_sync(0xffffffffu, x, 31);
-                prevPM = x;
-                prevB = B;
+                __syncwarp();
+                // window maximum of B over the previous P (<= 15) columns
+                int win = 0;
+                for (int d = 1; d <= P; ++d) win = max(win, ringB[(c - d) & 63]);
+                v = max(v, win);
+                const int pm = ringX[(c - P - 1) & 63];
+                v = max(v, pm - fp.gapO - (c - P - 1) * fp.gapE);       // columns < 0 hold -inf
+                __syncwarp();
             }
             if (c < rf_len) {
                 if (c < e1) { if (!anyL || v > bestL) { bestL = v; idxL = c; anyL = true; } }

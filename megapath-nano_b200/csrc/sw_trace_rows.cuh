@@ -1,0 +1,216 @@
+// Narrow-band traceback DP with the band row held in registers (sm_100a): replaces banded_sw (ssw.c:532-616) for bands of up to
+// 15 cells on reads of up to NARROW_MAX_ROWS rows -- every pair of BASELINE configs[1].
+//
+//   sw_band_setup_kernel     one thread per pair: begin positions from the reverse pass (ssw.c:820-832), the CIGAR filters of
+//                            ssw.c:833, the trivial "1M" case, and the first band |sub_ref - sub_read| + 1 (ssw.c:838); pairs are
+//                            appended to the work queue of their band half-width (1..7) or handed to the warp kernel (wider, longer).
+//   sw_band_rows_kernel<BW>  lane-persistent workers for ONE band half-width: a lane pulls a pair from the queue and then does a
+//                            whole read row per loop iteration, the 2*BW+1 cells unrolled with H / E of the previous row in registers
+//                            (updated in place, band coordinates of the reference), the target window in a 128-bit register pair and
+//                            the 4-bit direction cells of the row packed into one 64-bit store.  A failed attempt (banded maximum
+//                            below the score, ssw.c:614-616) re-queues the pair in the queue of the doubled band, which is launched later.
+// Band-coordinate quirks (`edge` zeroing, ssw.c:580) and tie rules as in sw_trace_warp.cuh; direction words as sw_band_trace_kernel reads them.
+#pragma once
+#include "sw_trace_narrow.cuh"
+
+namespace mpn {
+
+constexpr int ROWS_BLOCK = 128;
+constexpr int ROWS_MAXBW = NARROW_BW;                 // 7
+constexpr int ROWS_CLASSES = 4;                       // register rows of 3, 5, 9 and 15 band cells
+__host__ __device__ constexpr int rows_class_of(int bw) { return bw <= 1 ? 0 : (bw == 2 ? 1 : (bw <= 4 ? 2 : 3)); }
+__host__ __device__ constexpr int rows_class_cells(int cls) { return cls == 0 ? 3 : (cls == 1 ? 5 : (cls == 2 ? 9 : 15)); }
+
+struct BandQueues {
+    int2* items;             // [ROWS_CLASSES][capacity] (task index in the sorted task list, band half-width)
+    int* count;              // [ROWS_CLASSES] filled entries per queue
+    int* head;               // [ROWS_CLASSES] consumed entries per queue
+    int capacity;
+};
+
+__device__ __forceinline__ void band_enqueue(const BandQueues& q, int k, int bw)
+{
+    const int cls = rows_class_of(bw);
+    q.items[(size_t)cls * q.capacity + atomicAdd(q.count + cls, 1)] = make_int2(k, bw);
+}
+
+__global__ void __launch_bounds__(128)
+sw_band_setup_kernel(const SwTask* __restrict__ order, int ntasks, const FwdResult* __restrict__ fr, const SwEnds* __restrict__ rev, TraceParams tp,
+                     uint32_t* __restrict__ cig, unsigned long long cig_cap, unsigned long long* __restrict__ cig_used, FinalResult* __restrict__ out,
+                     BandRec* __restrict__ recs, int* __restrict__ flag_list, int* __restrict__ nflag, BandQueues q)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= ntasks) return;
+    const SwTask tk = order[k];
+    const int i = tk.out;
+    const FwdResult f = fr[i];
+    FinalResult r;
+    r.ref_begin1 = -1; r.read_begin1 = -1; r.cigar_len = 0; r.status = 0; r.cigar_off = 0;
+    BandRec br; br.dir_off = 0; br.bw = 0; br.kind = 0;
+    if (f.want_rev) {
+        if (f.score1 > 0) {
+            const SwEnds e = rev[i];
+            r.ref_begin1 = f.ref_end1 - e.col;
+            r.read_begin1 = f.read_end1 - e.row;
+        } else {
+            r.ref_begin1 = f.word_mode ? 0 : -1;       // empty / 1x1 reverse matrix (ssw.c:820-831)
+            r.read_begin1 = 0;
+        }
+        const bool no_cigar = (7 & tp.flag) == 0 || ((2 & tp.flag) != 0 && f.score1 < tp.filters) ||
+            ((4 & tp.flag) != 0 && (f.ref_end1 - r.ref_begin1 > tp.filterd || f.read_end1 - r.read_begin1 > tp.filterd));   // ssw.c:833
+        if (!no_cigar) {
+            const int sub_ref = f.ref_end1 - r.ref_begin1 + 1, sub_read = f.read_end1 - r.read_begin1 + 1;
+            const int bw = abs(sub_ref - sub_read) + 1;
+            if (f.score1 <= 0) {
+                unsigned long long o = atomicAdd(cig_used, 1ull);          // "1M" (ssw.c:625,680-687)
+                if (o + 1 > cig_cap) r.status = 6;
+                else { cig[o] = 1u << 4; r.cigar_off = (int64_t)o; r.cigar_len = 1; }
+            } else if (tp.n > 8 || bw > ROWS_MAXBW || sub_read > NARROW_MAX_ROWS) {
+                // wide bands, and reads so long that one lane would serialise millions of cells: one warp per pair instead
+                r.status = 7; br.bw = bw; flag_list[atomicAdd(nflag, 1)] = k;
+            } else {
+                band_enqueue(q, k, bw);
+            }
+        }
+    }
+    out[i] = r;
+    recs[i] = br;
+}
+
+// eight consecutive sequence bytes starting at p[from], zero beyond `len` (byte loads: the sequences are not aligned)
+__device__ __forceinline__ unsigned long long load8(const uint8_t* __restrict__ p, int from, int len)
+{
+    unsigned long long v = 0;
+#pragma unroll
+    for (int x = 0; x < 8; ++x) {
+        const unsigned long long c = from + x < len ? (unsigned long long)p[from + x] : 0ull;
+        v |= c << (8 * x);
+    }
+    return v;
+}
+
+template <int CLS>
+__global__ void __launch_bounds__(ROWS_BLOCK)
+sw_band_rows_kernel(const SwTask* __restrict__ order, const int8_t* __restrict__ seq, const FwdResult* __restrict__ fr, TraceParams tp, Arena scratch,
+                    FinalResult* __restrict__ out, BandRec* __restrict__ recs, int* __restrict__ flag_list, int* __restrict__ nflag, BandQueues q)
+{
+    constexpr int W = rows_class_cells(CLS);           // band cells held per row (>= 2 * bw + 1 of every pair of this class)
+    __shared__ unsigned long long srow[8];             // srow[q] = bytes mat[t*n+q], t = 0..7: scores of read code q against the target codes
+    const int n = tp.n, gapO = tp.gapO, gapE = tp.gapE;
+    if (threadIdx.x < 8) {
+        unsigned long long v = 0;
+        if ((int)threadIdx.x < n && n <= 8)
+            for (int t = 0; t < n; ++t) v |= (unsigned long long)(uint8_t)tp.mat[t * n + threadIdx.x] << (8 * t);
+        srow[threadIdx.x] = v;
+    }
+    __syncthreads();
+    const int total = q.count[CLS];                    // complete: every producer of this queue ran in an earlier launch
+    const int2* items = q.items + (size_t)CLS * q.capacity;
+    const uint8_t* useq = reinterpret_cast<const uint8_t*>(seq);
+
+    bool busy = false, drained = false;
+    int kcur = 0, i = 0, sub_ref = 1, sub_read = 1, score = 0, maxv = 0, ii = 0, wbase = 0, bw = 1;
+    const uint8_t* ref = useq; const uint8_t* read = useq;
+    unsigned long long* dirrow = nullptr; unsigned long long dir_off = 0;
+    unsigned long long win_lo = 0, win_hi = 0;         // target bases wbase .. wbase + 15
+    unsigned long long tq_cur = 0, tq_nxt = 0;         // the 8 + 8 target bases that enter the window next (loaded 8 slides ahead)
+    unsigned long long rq_cur = 0, rq_nxt = 0;         // read bases of rows ii .. (octet end) and of the next octet (loaded 8 rows ahead)
+    int H[W + 3], E[W + 3];                            // previous row in band coordinates: index 0 = left boundary, cell p lives at p + 1
+
+    for (;;) {
+        if (!busy && !drained) {
+            const int qi = atomicAdd(q.head + CLS, 1);
+            if (qi >= total) drained = true;
+            else {
+                const int2 it = items[qi];
+                kcur = it.x; bw = it.y;
+                const SwTask tk = order[kcur];
+                i = tk.out;
+                const FwdResult f = fr[i];
+                const FinalResult r = out[i];
+                sub_ref = f.ref_end1 - r.ref_begin1 + 1; sub_read = f.read_end1 - r.read_begin1 + 1; score = f.score1;
+                ref = useq + tk.rf_base + r.ref_begin1; read = useq + tk.rd_base + r.read_begin1;
+                const unsigned long long need = (unsigned long long)sub_read * 8ull;
+                const unsigned long long o = atomicAdd(scratch.used, (need + 15ull) & ~15ull);
+                if (o + need > scratch.bytes) { out[i].status = 5; }
+                else {
+                    dir_off = o; dirrow = reinterpret_cast<unsigned long long*>(scratch.base + o);
+#pragma unroll
+                    for (int x = 0; x < W + 3; ++x) { H[x] = 0; E[x] = 0; }
+                    win_lo = load8(ref, 0, sub_ref); win_hi = load8(ref, 8, sub_ref);
+                    tq_cur = load8(ref, 16, sub_ref); tq_nxt = load8(ref, 24, sub_ref);
+                    rq_cur = load8(read, 0, sub_read); rq_nxt = load8(read, 8, sub_read);
+                    wbase = 0; ii = 0; maxv = 0;
+                    busy = true;
+                }
+            }
+        }
+        // lanes leave together, once every lane has seen the queue empty (the queue of this class only shrinks while the kernel runs)
+        if (!__any_sync(0xffffffffu, busy || !drained)) break;
+        if (!busy) continue;
+
+        // ------------------------------------------------------------------ one read row
+        const int xi = max(ii - bw, 0);
+        const int end = min(sub_ref - 1, ii + bw);
+        const int edge = min(end + 1, 2 * bw + 2);     // `width - 1` of ssw.c:557,580
+        const bool sh = ii > bw;                       // band start moved by one column against the previous row
+        if (xi > wbase) {                              // slide the target window by one base
+            win_lo = (win_lo >> 8) | (win_hi << 56);
+            win_hi = (win_hi >> 8) | (tq_cur << 56);
+            tq_cur >>= 8;
+            wbase = xi;
+            if ((wbase & 7) == 0) { tq_cur = tq_nxt; tq_nxt = load8(ref, wbase + 24, sub_ref); }      // 8 slides consumed one word
+        }
+        const unsigned long long rscore = srow[(unsigned)rq_cur & 7u];
+        rq_cur >>= 8;
+        if ((ii & 7) == 7) { rq_cur = rq_nxt; rq_nxt = load8(read, ii + 9, sub_read); }
+        const bool row0 = ii == 0;
+        unsigned long long dirword = 0;
+        int hleft = 0, fv = 0;
+        int hdg = sh ? H[1] : 0;                       // H(ii-1, xi-1); band coordinate 0 is the matrix edge
+#pragma unroll
+        for (int p = 0; p < W; ++p) {
+            const bool valid = xi + p <= end;
+            const int e_idx = p + 1 + (sh ? 1 : 0);    // previous-row band coordinate of (ii-1, xi+p)
+            int hup = sh ? H[p + 2] : H[p + 1];
+            int eup = sh ? E[p + 2] : E[p + 1];
+            if (e_idx == edge) { hup = 0; eup = 0; }   // the slot the reference zeroes before every row (ssw.c:580)
+            const unsigned code = (unsigned)((p < 8 ? win_lo >> (8 * p) : win_hi >> (8 * (p - 8))) & 7ull);
+            const int sc = (int)(int8_t)(rscore >> (8 * code));
+            int open = row0 ? -gapO : hup - gapO;
+            int ext = row0 ? -gapE : eup - gapE;
+            const int ev = open > ext ? open : ext;
+            const unsigned de3 = open > ext ? 1u : 0u;                                        // ties extend (ssw.c:593-594)
+            open = hleft - gapO; ext = fv - gapE;
+            fv = open > ext ? open : ext;
+            const unsigned df5 = open > ext ? 1u : 0u;                                        // ssw.c:596-599
+            const int e1 = ev > 0 ? ev : 0, f1 = fv > 0 ? fv : 0;
+            const int t1 = e1 > f1 ? e1 : f1;
+            const int t2 = hdg + sc;
+            const int hv = t1 > t2 ? t1 : t2;
+            const unsigned src = t1 <= t2 ? 1u : (e1 > f1 ? 2u : 3u);                         // 1 diagonal, 2 from E, 3 from F (ssw.c:609-610)
+            hdg = hup;                                 // the next cell's diagonal (zeroed together with the slot)
+            H[p + 1] = valid ? hv : 0;
+            E[p + 1] = valid ? ev : 0;
+            if (valid) {
+                maxv = max(maxv, hv);
+                dirword |= (unsigned long long)(de3 | (df5 << 1) | (src << 2)) << (4 * p);
+            }
+            hleft = hv;
+        }
+        dirrow[ii] = dirword;
+        if (++ii >= sub_read) {
+            busy = false;
+            if (maxv >= score) {                                                              // ssw.c:614-615
+                BandRec br; br.dir_off = dir_off; br.bw = bw; br.kind = 2; recs[i] = br;
+            } else if (2 * bw <= ROWS_MAXBW) {
+                band_enqueue(q, kcur, 2 * bw);         // always a later class: the launches go through the classes in increasing order
+            } else {
+                out[i].status = 7; BandRec br; br.dir_off = 0; br.bw = 2 * bw; br.kind = 0; recs[i] = br;
+                flag_list[atomicAdd(nflag, 1)] = kcur;
+            }
+        }
+    }
+}
+
+}  // namespace mpn

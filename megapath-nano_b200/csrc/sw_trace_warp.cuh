@@ -52,7 +52,7 @@ __device__ __forceinline__ int warp_band_row(const WarpRowCtx& c, int ii, uint8_
         const int e_idx = min(p + shift + 1, WARPTR_CELLS + 1);        // previous-row band coordinate of (ii-1, j)
         int hup = c.Hp[e_idx], eup = c.Ep[e_idx];
         if (e_idx == edge) { hup = 0; eup = 0; }                       // the slot the reference zeroes before every row
-        const int hdg = (e_idx - 1 == 0) ? 0 : c.Hp[e_idx - 1];        // h_b[0] = 0
+        const int hdg = (e_idx - 1 == 0 || e_idx - 1 == edge) ? 0 : c.Hp[e_idx - 1];   // h_b[0] = 0, and the diagonal sees the zeroed slot too
         const int open = ii == 0 ? -c.gapO : hup - c.gapO, ext = ii == 0 ? -c.gapE : eup - c.gapE;
         const int ev = open > ext ? open : ext;
         de3s |= (open > ext ? 1u : 0u) << k;
