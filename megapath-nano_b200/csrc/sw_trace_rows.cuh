@@ -77,15 +77,18 @@ sw_band_setup_kernel(const SwTask* __restrict__ order, int ntasks, const FwdResu
     recs[i] = br;
 }
 
-// eight consecutive sequence bytes starting at p[from], zero beyond `len` (byte loads: the sequences are not aligned)
+// eight consecutive sequence bytes starting at p[from], zero beyond `len`.  Two aligned 64-bit loads + a funnel shift instead of eight
+// byte loads: the arena starts 256-byte aligned and is padded by 16 bytes (engine.cu), so the aligned words around any base are readable.
 __device__ __forceinline__ unsigned long long load8(const uint8_t* __restrict__ p, int from, int len)
 {
-    unsigned long long v = 0;
-#pragma unroll
-    for (int x = 0; x < 8; ++x) {
-        const unsigned long long c = from + x < len ? (unsigned long long)p[from + x] : 0ull;
-        v |= c << (8 * x);
-    }
+    const int left = len - from;
+    if (left <= 0) return 0ull;
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p + from);
+    const unsigned long long* w = reinterpret_cast<const unsigned long long*>(a & ~(uintptr_t)7);
+    const unsigned sh = (unsigned)(a & 7u) * 8u;
+    const unsigned long long lo = w[0], hi = w[1];
+    unsigned long long v = sh ? ((lo >> sh) | (hi << (64u - sh))) : lo;
+    if (left < 8) v &= (1ull << (8 * left)) - 1ull;
     return v;
 }
 
