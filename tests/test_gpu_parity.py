@@ -228,3 +228,32 @@ def test_cigar_dense_pairs_exceed_the_typical_arena(eng):
     r, c = oracle_table(b, cap=cap)
     assert len(diff(g, gc, r, c)) == 0
     assert int(rec["cigar_len"].sum()) > b.npairs * 24 + int(b.read_len.sum()) // 4 + 4096
+
+
+def test_large_alphabet_goes_through_the_int32_kernels(eng):
+    """the ABI is generic in n (ssw.h:77, any n x n matrix): a 20-letter protein-like matrix takes the 32-bit score kernel and the
+    warp traceback (the packed kernels assume n <= 8)"""
+    rng = np.random.default_rng(33)
+    n = 20
+    mat = rng.integers(-4, 3, size=(n, n)).astype(np.int8)
+    mat = np.minimum(mat, mat.T)
+    for i in range(n):
+        mat[i, i] = int(rng.integers(4, 10))
+    reads, refs = [], []
+    for _ in range(150):
+        t = rng.integers(0, n, size=int(rng.integers(30, 400))).astype(np.int8)
+        s = int(rng.integers(0, max(1, len(t) - 20)))
+        r = t[s:s + int(rng.integers(10, 250))].copy()
+        r[rng.random(len(r)) < 0.1] = rng.integers(0, n)
+        if len(r) > 40 and rng.random() < 0.5:
+            r = np.delete(r, slice(20, 20 + int(rng.integers(1, 6))))
+        reads.append(r); refs.append(t)
+    ro = np.concatenate([[0], np.cumsum([len(x) for x in reads])]).astype(np.int64)
+    fo = np.concatenate([[0], np.cumsum([len(x) for x in refs])]).astype(np.int64)
+    for flag, gapO, gapE in ((1, 11, 1), (0, 5, 2)):
+        b = w.PairBatch(np.concatenate(reads), ro, np.concatenate(refs), fo, np.maximum(15, np.diff(ro) // 2).astype(np.int32), mat=mat.reshape(-1), n=n,
+                        gapO=gapO, gapE=gapE, flag=flag)
+        g, gc, _, _ = gpu_table(eng, b)
+        r, c = oracle_table(b)
+        bad = diff(g, gc, r, c)
+        assert len(bad) == 0, (flag, bad[:5], g[bad[:1]], r[bad[:1]])
