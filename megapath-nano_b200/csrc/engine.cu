@@ -88,7 +88,6 @@ void build_strip_table()
     for (int p = 0; p < 4; ++p)
         for (int k = 0; k < counts[p]; ++k) {
             const StripEntry& e = parts[p][k];
-            if (getenv("MPN_EXP_SKIP_G") && e.G == atoi(getenv("MPN_EXP_SKIP_G")) && e.KR >= 10) continue;   // A/B experiments on the bin table
             g_strips.push_back(StripCfg{e.G, e.KR, 2 * e.G * e.KR, e.fn, e.smem, 1});
         }
     std::stable_sort(g_strips.begin(), g_strips.end(), [](const StripCfg& a, const StripCfg& b) { return a.cap < b.cap; });

@@ -6,10 +6,6 @@ const StripEntry g_strip_part_a[] = {
     MPN_STRIP_ENTRY(4, 4), MPN_STRIP_ENTRY(8, 4),
     MPN_STRIP_ENTRY(6, 8), MPN_STRIP_ENTRY(7, 8), MPN_STRIP_ENTRY(8, 8), MPN_STRIP_ENTRY(9, 8), MPN_STRIP_ENTRY(10, 8),
     MPN_STRIP_ENTRY(11, 8), MPN_STRIP_ENTRY(12, 8), MPN_STRIP_ENTRY(13, 8),
-#ifdef MPN_EXP_FATG4                                                                 // timing experiment: 4-thread groups with 20 .. 38 rows per stage
-    MPN_STRIP_ENTRY(20, 4), MPN_STRIP_ENTRY(22, 4), MPN_STRIP_ENTRY(24, 4), MPN_STRIP_ENTRY(26, 4), MPN_STRIP_ENTRY(28, 4), MPN_STRIP_ENTRY(30, 4),
-    MPN_STRIP_ENTRY(32, 4), MPN_STRIP_ENTRY(34, 4), MPN_STRIP_ENTRY(36, 4), MPN_STRIP_ENTRY(38, 4),
-#endif
 };
 const int g_strip_part_a_n = sizeof(g_strip_part_a) / sizeof(g_strip_part_a[0]);
 }

@@ -127,9 +127,6 @@ sw_strip16_kernel(const SwTask* __restrict__ tasks, int ntasks, int* __restrict_
                     e.col = wscore > 0 ? wcol : -1;
                     e.row = wscore > 0 ? row : 0;
                     e.flags = anywide ? SW_FLAG_NEEDS_WIDE : 0;
-#ifdef MPN_EXP_CLAMP                                                              // timing experiments with deliberately wrong kernels: keep later passes in bounds
-                    if (wscore > 0) { e.col = min(max(e.col, 0), rf_len - 1); e.row = min(max(e.row, 0), CAP - dead - 1); }
-#endif
                     out[tout] = e;
                 }
             }
@@ -203,24 +200,10 @@ sw_strip16_kernel(const SwTask* __restrict__ tasks, int ntasks, int* __restrict_
                 uint32_t hnext = 0;
                 if (j + 1 < KR) hnext = add2(H[j], prmt(a, b, sel[j + 1]));   // uses H(j) of the previous column: diagonal of row j+1
                 else Hdtop = H[j];                                            // bottom H of the previous column: diagonal for the next stage
-#ifdef MPN_EXP_SPLITCHAIN                                                          // timing experiment (wrong results): two independent F chains per step
-                if (j == KR / 2) F = Ftop ^ cmin;
-#endif
-#ifdef MPN_EXP_FCHAIN
-                // short F chain: F' = max(F - e, max(h, E) - o) needs only F of the row above (valid for gapO >= gapE)
-                uint32_t Hp;
-                asm("max.s16x2.relu %0, %1, %2;" : "=r"(Hp) : "r"(h), "r"(E[j]));
-                const uint32_t Gp = add2(Hp, sc.mgapO2);
-                const uint32_t Hn = max2(Hp, F);
-                F = addmax_relu(F, sc.mgapE2, Gp);
-                const uint32_t Hg = add2(Hn, sc.mgapO2);
-                E[j] = addmax_relu(E[j], sc.mgapE2, Hg);
-#else
                 const uint32_t Hn = max3_relu(h, E[j], F);
                 const uint32_t Hg = add2(Hn, sc.mgapO2);
                 E[j] = addmax_relu(E[j], sc.mgapE2, Hg);
                 F = addmax_relu(F, sc.mgapE2, Hg);
-#endif
                 H[j] = Hn;
                 if (j & 1) m = max3(m, H[j - 1], Hn);
                 else if (j == KR - 1) m = max2(m, Hn);                        // odd KR: the last row has no partner
@@ -231,33 +214,23 @@ sw_strip16_kernel(const SwTask* __restrict__ tasks, int ntasks, int* __restrict_
             best = max2_track(best, m, ge_hi, ge_lo);
             if (!ge_lo) {
                 cvlo = (uint32_t)s;
-#ifndef MPN_EXP_NOSNAP
 #pragma unroll
                 for (int k = 0; k < KRQ; ++k) snap[(size_t)k * STRIP_BLOCK + tid] = make_uint4(H[4 * k], H[min(4 * k + 1, KR - 1)], H[min(4 * k + 2, KR - 1)], H[min(4 * k + 3, KR - 1)]);
-#endif
             }
             if (!ge_hi) {
                 cvhi = (uint32_t)s;
-#ifndef MPN_EXP_NOSNAP
 #pragma unroll
                 for (int k = 0; k < KRQ; ++k) snap[(size_t)(KRQ + k) * STRIP_BLOCK + tid] = make_uint4(H[4 * k], H[min(4 * k + 1, KR - 1)], H[min(4 * k + 2, KR - 1)], H[min(4 * k + 3, KR - 1)]);
-#endif
             }
             const uint32_t cmout = max2(cmin, m);
             // ---- (column maximum, bottom-row H) of this step: staged in shared memory by every thread, only the last stage's
             //      entry is a finished column (s - (2G-1)); the group writes G of them to global memory after the loop
-#ifndef MPN_EXP_NOCROW
             crow[u * STRIP_BLOCK + tid] = prmt(cmout, H[KR - 1], 0x7632u);
-#endif
             // ---- hand the boundary to the next stage
-#ifdef MPN_EXP_NOSHFL
-            const uint32_t rF = F ^ 1u, rH = Hdtop, rC = cmout, rA = b;
-#else
             const uint32_t rF = __shfl_up_sync(0xffffffffu, F, 1, G);
             const uint32_t rH = __shfl_up_sync(0xffffffffu, Hdtop, 1, G);
             const uint32_t rC = __shfl_up_sync(0xffffffffu, cmout, 1, G);
             const uint32_t rA = __shfl_up_sync(0xffffffffu, b, 1, G);
-#endif
             Ftop = prmt(rF, F, mergeSel);
             Hdtop = prmt(rH, Hdtop, mergeSel);
             cmin = prmt(rC, cmout, mergeSel);
