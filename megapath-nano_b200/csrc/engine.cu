@@ -714,8 +714,16 @@ extern "C" int mpn_align_batch(mpn_engine* e, const mpn_params* p, const int8_t*
         mpn_batch_free(b);
         return rc;
     }
-    const int64_t nchunks = (npairs + CHUNK - 1) / CHUNK;
-    const int64_t per = (npairs + nchunks - 1) / nchunks;
+    // chunk boundaries: equal chunks of about CHUNK pairs, except that the first two are a quarter and a half of that, so the GPU starts
+    // after a short upload instead of waiting for a full chunk to be scheduled and copied
+    std::vector<int64_t> bounds(1, 0);
+    {
+        int64_t at = 0;
+        for (int64_t want : {CHUNK / 4, CHUNK / 2}) if (npairs - at > 2 * CHUNK) { at += want; bounds.push_back(at); }
+        const int64_t rest = npairs - at, nrest = (rest + CHUNK - 1) / CHUNK, per = (rest + nrest - 1) / nrest;
+        while (at < npairs) { at = std::min(npairs, at + per); bounds.push_back(at); }
+    }
+    const int64_t nchunks = (int64_t)bounds.size() - 1;
     // ring of in-flight chunks, one pipeline slot each (own stream + own pinned staging).  Several chunks are queued on the GPU at any
     // time, so the persistent grids of chunk k+1 fill the SMs that the tail of chunk k leaves idle, and the host work of a chunk
     // (scheduling, H2D enqueue, D2H + record conversion) hides behind the kernels of the others.  Fetch order = chunk order (CIGAR offsets).
@@ -737,7 +745,7 @@ extern "C" int mpn_align_batch(mpn_engine* e, const mpn_params* p, const int8_t*
     for (int64_t c = 0; c < nchunks; ++c, ++issued) {
         const int s = (int)(c % DEPTH);
         drain(s);                                   // the oldest chunk (c - DEPTH) used this slot
-        const int64_t c0 = c * per, n_c = std::min(per, npairs - c0);
+        const int64_t c0 = bounds[c], n_c = bounds[c + 1] - c0;
         if (n_c <= 0) break;
         mpn_batch* b = upload_impl(e, 1 + s, p, CsrPairs{reads, read_off + c0, refs, ref_off + c0, n_c}, masklen + c0, n_c);
         if (!b) { rc = MPN_E_ARG; break; }
