@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(128)
 sw_finish_kernel(const SwTask* __restrict__ fwd_tasks, int ntasks, const SwEnds* __restrict__ ends, const uint32_t* __restrict__ colrec,
                  PairArrays pa, FinishParams fp, FwdResult* __restrict__ res, SwTask* __restrict__ rev_tasks)
 {
-    __shared__ int fsm[4 * 128];                  // per warp: ring of B (64) + ring of prefix maxima (64)
+    __shared__ int fsm[4 * 512];                  // per warp: ring of B (256) + ring of prefix maxima (256)
     const int lane = threadIdx.x & 31;
     const int k = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
     if (k >= ntasks) return;
@@ -83,45 +83,72 @@ sw_finish_kernel(const SwTask* __restrict__ fwd_tasks, int ntasks, const SwEnds*
         const int e1 = max(end_ref - masklen, 0);
         const int e2 = min(end_ref + masklen, rf_len) + (byte_mode ? 1 : 0);
         const uint32_t* rec = colrec + tk.cm_off;
-        // Two 64-entry rings in shared memory (this warp's slice) hold B and the prefix maximum of the last two chunks, so "the value
-        // d columns back" is one LDS instead of a two-shuffle select.  Entries of columns < 0 are the zero / -inf the formulas expect.
-        int* ringB = fsm + (threadIdx.x >> 5) * 128;
-        int* ringX = ringB + 64;
+        // 128 columns per iteration, 4 consecutive columns per lane.  Two 256-entry rings in shared memory (this warp's slice) hold B and
+        // the prefix maximum of the last two iterations, so "the value d columns back" is one LDS.  Entries of columns < 0 are the
+        // zero / -inf the formulas expect.
+        int* ringB = fsm + (threadIdx.x >> 5) * 512;
+        int* ringX = ringB + 256;
         const int NEGV = INT_MIN / 2;
-        ringB[lane] = 0; ringB[32 + lane] = 0; ringX[lane] = NEGV; ringX[32 + lane] = NEGV;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { ringB[q * 32 + lane] = 0; ringX[q * 32 + lane] = NEGV; }
         __syncwarp();
-        int carryPM = NEGV;            // prefix max of (B[j] + j*gapE) over all earlier chunks
+        int carryPM = NEGV;            // prefix max of (B[j] + j*gapE) over all earlier iterations
         int bestL = 0, idxL = 0, bestR = 0, idxR = 0;     // strict-greater-first maxima of the two ranges (per lane, merged at the end)
         bool anyL = false, anyR = false;
-        for (int c0 = 0; c0 < rf_len; c0 += 32) {
-            const int c = c0 + lane;
-            const uint32_t w = c < rf_len ? rec[c] : 0u;
-            const int cm = (int)(w & 0xffffu), B = (int)(w >> 16);
-            int v = cm;
+        for (int c0 = 0; c0 < rf_len; c0 += 128) {
+            const int cb = c0 + 4 * lane;
+            int cm[4], B[4], v[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const uint32_t w = cb + q < rf_len ? rec[cb + q] : 0u;
+                cm[q] = (int)(w & 0xffffu); B[q] = (int)(w >> 16); v[q] = cm[q];
+            }
             if (P > 0) {
-                ringB[c & 63] = B;
-                // eroded contribution: PM[c-P-1] - gapO - (c-P-1)*gapE with PM the inclusive prefix max of B[j] + j*gapE
-                int x = c < rf_len ? B + c * fp.gapE : NEGV;
+                // inclusive prefix max of x = B[j] + j*gapE: serial inside the lane, one warp scan of the lane aggregates
+                int x[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    x[q] = cb + q < rf_len ? B[q] + (cb + q) * fp.gapE : NEGV;
+                    if (q) x[q] = max(x[q], x[q - 1]);
+                    ringB[(cb + q) & 255] = B[q];
+                }
+                int inc = x[3];
 #pragma unroll
                 for (int off = 1; off < 32; off <<= 1) {
-                    const int o = __shfl_up_sync(0xffffffffu, x, off);
-                    if (lane >= off) x = max(x, o);
+                    const int o = __shfl_up_sync(0xffffffffu, inc, off);
+                    if (lane >= off) inc = max(inc, o);
                 }
-                x = max(x, carryPM);
-                ringX[c & 63] = x;
-                carryPM = __shfl_sync(0xffffffffu, x, 31);
+                int pre = __shfl_up_sync(0xffffffffu, inc, 1);
+                if (lane == 0) pre = NEGV;
+                pre = max(pre, carryPM);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) ringX[(cb + q) & 255] = max(x[q], pre);
+                carryPM = max(carryPM, __shfl_sync(0xffffffffu, inc, 31));
                 __syncwarp();
-                // window maximum of B over the previous P (<= 15) columns
-                int win = 0;
-                for (int d = 1; d <= P; ++d) win = max(win, ringB[(c - d) & 63]);
-                v = max(v, win);
-                const int pm = ringX[(c - P - 1) & 63];
-                v = max(v, pm - fp.gapO - (c - P - 1) * fp.gapE);       // columns < 0 hold -inf
+                // window maximum of B over the previous P (<= 15) columns: s0..s3 = running max over the d = 1.. columns before this
+                // lane's block, captured at depths P, P-1, P-2, P-3 (what columns 0..3 of the block still see of it) ...
+                int s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+                for (int d = 1; d <= P; ++d) { s3 = s2; s2 = s1; s1 = s0; s0 = max(s0, ringB[(cb - d) & 255]); }
+                // ... plus the columns of the block itself that lie inside the window
+                v[0] = max(v[0], s0);
+                v[1] = max(v[1], max(s1, B[0]));
+                v[2] = max(v[2], max(s2, P >= 2 ? max(B[1], B[0]) : B[1]));
+                v[3] = max(v[3], max(s3, P >= 3 ? max(B[2], max(B[1], B[0])) : (P >= 2 ? max(B[2], B[1]) : B[2])));
+                // eroded contribution: PM[c-P-1] - gapO - (c-P-1)*gapE with PM the inclusive prefix max of B[j] + j*gapE (-inf for columns < 0)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int cc = cb + q - P - 1;
+                    v[q] = max(v[q], ringX[cc & 255] - fp.gapO - cc * fp.gapE);
+                }
                 __syncwarp();
             }
-            if (c < rf_len) {
-                if (c < e1) { if (!anyL || v > bestL) { bestL = v; idxL = c; anyL = true; } }
-                else if (c >= e2) { if (!anyR || v > bestR) { bestR = v; idxR = c; anyR = true; } }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int c = cb + q;
+                if (c < rf_len) {
+                    if (c < e1) { if (!anyL || v[q] > bestL) { bestL = v[q]; idxL = c; anyL = true; } }
+                    else if (c >= e2) { if (!anyR || v[q] > bestR) { bestR = v[q]; idxR = c; anyR = true; } }
+                }
             }
         }
         // merge lanes: larger value wins, ties -> smaller column
