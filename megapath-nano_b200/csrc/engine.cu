@@ -70,7 +70,7 @@ struct PinBuf {
 };
 
 constexpr int STRIP_BLOCK_THREADS = 128;   // = STRIP_BLOCK of sw_strip16.cuh (the kernels are compiled in strip_inst_*.cu)
-struct StripCfg { int G, KR, cap; StripFn fn; size_t smem; int blocks_per_sm; };
+struct StripCfg { int G, KR, cap; StripFn fn; StripFn fn_rev; size_t smem; int blocks_per_sm; };
 
 // all instantiations of the packed kernel, sorted by the number of read rows one strip covers (cap = 2 * G * KR)
 std::vector<StripCfg> g_strips;
@@ -88,7 +88,7 @@ void build_strip_table()
     for (int p = 0; p < 4; ++p)
         for (int k = 0; k < counts[p]; ++k) {
             const StripEntry& e = parts[p][k];
-            g_strips.push_back(StripCfg{e.G, e.KR, 2 * e.G * e.KR, e.fn, e.smem, 1});
+            g_strips.push_back(StripCfg{e.G, e.KR, 2 * e.G * e.KR, e.fn, e.fn_rev, e.smem, 1});
         }
     std::stable_sort(g_strips.begin(), g_strips.end(), [](const StripCfg& a, const StripCfg& b) { return a.cap < b.cap; });
     N_STRIPS = (int)g_strips.size();
@@ -510,7 +510,7 @@ static void launch_strips(mpn_batch* b, const SwTask* tasks, bool forward, SwEnd
             const int groups_per_block = STRIP_BLOCK_THREADS / c.G;
             int64_t blocks = (bl.count + groups_per_block - 1) / groups_per_block;
             blocks = std::min<int64_t>(blocks, (int64_t)e->sm_count * c.blocks_per_sm);
-            c.fn<<<(unsigned)blocks, STRIP_BLOCK_THREADS, c.smem, st>>>(tasks + bl.first, (int)bl.count, counter, b->seq.as<int8_t>(), b->sc16,
+            (forward ? c.fn : c.fn_rev)<<<(unsigned)blocks, STRIP_BLOCK_THREADS, c.smem, st>>>(tasks + bl.first, (int)bl.count, counter, b->seq.as<int8_t>(), b->sc16,
                                                                   forward ? b->colrec.as<uint32_t>() : nullptr, ends);
         }
         CK(cudaGetLastError());

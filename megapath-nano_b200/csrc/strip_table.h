@@ -7,13 +7,13 @@
 namespace mpn {
 
 typedef void (*StripFn)(const SwTask*, int, int*, const int8_t*, const Score16, uint32_t*, SwEnds*);
-struct StripEntry { int G, KR; StripFn fn; size_t smem; };
+struct StripEntry { int G, KR; StripFn fn; StripFn fn_rev; size_t smem; };      // forward / reverse instantiation of the same strip
 
 extern const StripEntry g_strip_part_a[]; extern const int g_strip_part_a_n;
 extern const StripEntry g_strip_part_b[]; extern const int g_strip_part_b_n;
 extern const StripEntry g_strip_part_c[]; extern const int g_strip_part_c_n;
 extern const StripEntry g_strip_part_d[]; extern const int g_strip_part_d_n;
 
-#define MPN_STRIP_ENTRY(KR, G) { G, KR, sw_strip16_kernel<KR, G>, strip16_smem_bytes<KR, G>() }
+#define MPN_STRIP_ENTRY(KR, G) { G, KR, sw_strip16_kernel<KR, G, false>, sw_strip16_kernel<KR, G, true>, strip16_smem_bytes<KR, G>() }
 
 }  // namespace mpn

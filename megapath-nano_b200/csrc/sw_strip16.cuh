@@ -41,7 +41,10 @@ constexpr int STRIP_UNROLL = MPN_STRIP_UNROLL;
 template <int KR, int G>
 __host__ __device__ constexpr size_t strip16_smem_bytes() { return (size_t)2 * ((KR + 3) / 4) * STRIP_BLOCK * sizeof(uint4) + (size_t)G * STRIP_BLOCK * sizeof(uint32_t); }
 
-template <int KR, int G>
+// REV = false: forward passes (column records written, no early end).  REV = true: reverse passes (ssw.c:820-832): no column records, the
+// pass ends once the terminating score has been seen, and only a stage that REACHES that score can be the winner, so the H-column
+// snapshots sit behind a warp-uniform branch that is taken a handful of times per pair instead of being issued (predicated off) every step.
+template <int KR, int G, bool REV>
 __global__ void __launch_bounds__(STRIP_BLOCK, MPN_STRIP_MINB)
 sw_strip16_kernel(const SwTask* __restrict__ tasks, int ntasks, int* __restrict__ counter, const int8_t* __restrict__ seq,
                   const Score16 sc, uint32_t* __restrict__ colrec, SwEnds* __restrict__ out)
@@ -78,7 +81,7 @@ sw_strip16_kernel(const SwTask* __restrict__ tasks, int ntasks, int* __restrict_
 
     for (;;) {
         // ------------------------------------------------------------------ task boundary (every G steps) -------------
-        {   // early end of a reverse pass (ssw.c:281 / :483): once some stage has seen the terminating score in column c, every
+        if (REV) {   // early end of a reverse pass (ssw.c:281 / :483): once some stage has seen the terminating score in column c, every
             // stage has passed column c after at most 2G-1 further steps; the usual first-column / first-row selection then applies.
             const uint32_t x = best ^ stop2;
             const bool hit = stop2 != 0u && ((x & 0xffffu) == 0u || (x >> 16) == 0u);
@@ -127,6 +130,9 @@ sw_strip16_kernel(const SwTask* __restrict__ tasks, int ntasks, int* __restrict_
                     e.col = wscore > 0 ? wcol : -1;
                     e.row = wscore > 0 ? row : 0;
                     e.flags = anywide ? SW_FLAG_NEEDS_WIDE : 0;
+                    // a reverse pass that did not reach its terminating score has no snapshot to read the row from (cannot happen for a
+                    // symmetric recurrence; kept as a guard): redo the pair in the 32-bit kernel
+                    if (REV && stop2 != 0u && (uint32_t)wscore != (stop2 & 0xffffu)) e.flags = SW_FLAG_NEEDS_WIDE;
                     out[tout] = e;
                 }
             }
@@ -212,39 +218,63 @@ sw_strip16_kernel(const SwTask* __restrict__ tasks, int ntasks, int* __restrict_
             // ---- per-stage best tracking: strict improvement keeps the first column (ssw.c:269 / :474)
             bool ge_hi, ge_lo;
             best = max2_track(best, m, ge_hi, ge_lo);
-            if (!ge_lo) {
-                cvlo = (uint32_t)s;
+            if (!REV) {
+                if (!ge_lo) {
+                    cvlo = (uint32_t)s;
 #pragma unroll
-                for (int k = 0; k < KRQ; ++k) snap[(size_t)k * STRIP_BLOCK + tid] = make_uint4(H[4 * k], H[min(4 * k + 1, KR - 1)], H[min(4 * k + 2, KR - 1)], H[min(4 * k + 3, KR - 1)]);
-            }
-            if (!ge_hi) {
-                cvhi = (uint32_t)s;
+                    for (int k = 0; k < KRQ; ++k) snap[(size_t)k * STRIP_BLOCK + tid] = make_uint4(H[4 * k], H[min(4 * k + 1, KR - 1)], H[min(4 * k + 2, KR - 1)], H[min(4 * k + 3, KR - 1)]);
+                }
+                if (!ge_hi) {
+                    cvhi = (uint32_t)s;
 #pragma unroll
-                for (int k = 0; k < KRQ; ++k) snap[(size_t)(KRQ + k) * STRIP_BLOCK + tid] = make_uint4(H[4 * k], H[min(4 * k + 1, KR - 1)], H[min(4 * k + 2, KR - 1)], H[min(4 * k + 3, KR - 1)]);
+                    for (int k = 0; k < KRQ; ++k) snap[(size_t)(KRQ + k) * STRIP_BLOCK + tid] = make_uint4(H[4 * k], H[min(4 * k + 1, KR - 1)], H[min(4 * k + 2, KR - 1)], H[min(4 * k + 3, KR - 1)]);
+                }
+            } else {
+                if (!ge_lo) cvlo = (uint32_t)s;
+                if (!ge_hi) cvhi = (uint32_t)s;
+                const uint32_t x = best ^ stop2;
+                const bool win_lo = !ge_lo && (x & 0xffffu) == 0u, win_hi = !ge_hi && (x >> 16) == 0u;
+                if (__any_sync(0xffffffffu, win_lo || win_hi)) {
+                    if (win_lo) {
+#pragma unroll
+                        for (int k = 0; k < KRQ; ++k) snap[(size_t)k * STRIP_BLOCK + tid] = make_uint4(H[4 * k], H[min(4 * k + 1, KR - 1)], H[min(4 * k + 2, KR - 1)], H[min(4 * k + 3, KR - 1)]);
+                    }
+                    if (win_hi) {
+#pragma unroll
+                        for (int k = 0; k < KRQ; ++k) snap[(size_t)(KRQ + k) * STRIP_BLOCK + tid] = make_uint4(H[4 * k], H[min(4 * k + 1, KR - 1)], H[min(4 * k + 2, KR - 1)], H[min(4 * k + 3, KR - 1)]);
+                    }
+                }
             }
-            const uint32_t cmout = max2(cmin, m);
-            // ---- (column maximum, bottom-row H) of this step: staged in shared memory by every thread, only the last stage's
-            //      entry is a finished column (s - (2G-1)); the group writes G of them to global memory after the loop
-            crow[u * STRIP_BLOCK + tid] = prmt(cmout, H[KR - 1], 0x7632u);
+            uint32_t cmout = 0;
+            if (!REV) {
+                cmout = max2(cmin, m);
+                // ---- (column maximum, bottom-row H) of this step: staged in shared memory by every thread, only the last stage's
+                //      entry is a finished column (s - (2G-1)); the group writes G of them to global memory after the loop
+                crow[u * STRIP_BLOCK + tid] = prmt(cmout, H[KR - 1], 0x7632u);
+            }
             // ---- hand the boundary to the next stage
             const uint32_t rF = __shfl_up_sync(0xffffffffu, F, 1, G);
             const uint32_t rH = __shfl_up_sync(0xffffffffu, Hdtop, 1, G);
-            const uint32_t rC = __shfl_up_sync(0xffffffffu, cmout, 1, G);
             const uint32_t rA = __shfl_up_sync(0xffffffffu, b, 1, G);
             Ftop = prmt(rF, F, mergeSel);
             Hdtop = prmt(rH, Hdtop, mergeSel);
-            cmin = prmt(rC, cmout, mergeSel);
+            if (!REV) {
+                const uint32_t rC = __shfl_up_sync(0xffffffffu, cmout, 1, G);
+                cmin = prmt(rC, cmout, mergeSel);
+            }
             b = a;
             a = rA;
         }
         // ---- column records of the G steps just done: thread t of the group stores the one of step s - G + t (one 4*G-byte run per group)
-        __syncwarp();
-        if (cm_off >= 0) {
-            const int c = s - G + t - (2 * G - 1);
-            const uint32_t v = crow[t * STRIP_BLOCK + tid - t + (G - 1)];
-            if (c >= 0 && c < rf_len) colrec[cm_off + c] = v;
+        if (!REV) {
+            __syncwarp();
+            if (cm_off >= 0) {
+                const int c = s - G + t - (2 * G - 1);
+                const uint32_t v = crow[t * STRIP_BLOCK + tid - t + (G - 1)];
+                if (c >= 0 && c < rf_len) colrec[cm_off + c] = v;
+            }
+            __syncwarp();
         }
-        __syncwarp();
     }
 }
 
