@@ -13,6 +13,7 @@
 #include "sw_trace_rows.cuh"
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -472,11 +473,20 @@ extern "C" int mpn_align_batch_spans(mpn_engine* e, const mpn_params* p, const i
                                      mpn_result* out, uint32_t* cigar, int64_t cigar_cap)
 {
     if (!e || npairs < 0) return MPN_E_ARG;
+    static const bool timing = getenv("MPN_TIMING") != nullptr;
+    auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t0 = now();
     mpn_batch* b = mpn_batch_upload_spans(e, p, seq, seq_bytes, rd_start, rd_len, rf_start, rf_len, masklen, npairs);
     if (!b) return MPN_E_ARG;
+    const double t1 = now();
     int rc = mpn_batch_run(b);
+    const double t2 = now();
+    if (timing) CK(cudaStreamSynchronize(b->st));
+    const double t3 = now();
     if (rc == 0) rc = mpn_batch_fetch(b, out, cigar, cigar_cap);
+    const double t4 = now();
     mpn_batch_free(b);
+    if (timing) fprintf(stderr, "[mpn_ssw] spans batch %lld pairs: upload %.3f ms, enqueue %.3f ms, kernels %.3f ms, fetch %.3f ms\n", (long long)npairs, t1 - t0, t2 - t1, t3 - t2, t4 - t3);
     return rc;
 }
 

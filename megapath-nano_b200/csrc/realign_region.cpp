@@ -120,7 +120,7 @@ std::string ops_to_string(const std::vector<Op>& ops)      // CigarVectorToStrin
 
 // ------------------------------------------------------------------------------------------------ k-mer index
 // The reference keys an unordered_map by the 32-character substring.  Here: k-mers made only of A/C/G/T pack into one
-// 64-bit word (sorted array + binary search, occurrences kept in insertion order = (read, offset) ascending); k-mers with
+// 64-bit word (flat hash table, occurrences grouped per k-mer in insertion order = (read, offset) ascending); k-mers with
 // any other character (N, lower case) go to a small string-keyed map so that equality stays exact string equality.
 struct Occurrence { uint64_t key; int read; int offset; };
 
@@ -130,14 +130,22 @@ inline int base2(char c)
 }
 
 struct KmerIndex {
-    std::vector<Occurrence> packed;
+    // packed k-mers: open-addressing table key -> (first, count) into `occ`, where the occurrences of one k-mer are contiguous and
+    // keep their insertion order = (read, offset) ascending (the order the reference's vectors have, realigner.cpp:425-427)
+    struct Slot { uint64_t key; int first; int count; };
+    std::vector<Slot> table;
+    std::vector<Occurrence> occ;
+    uint64_t mask = 0;
     std::unordered_map<std::string, std::vector<Occurrence>> odd;
+
+    static inline uint64_t mix(uint64_t k) { k ^= k >> 33; k *= 0xff51afd7ed558ccdULL; k ^= k >> 33; return k; }
 
     void build(const std::vector<std::string>& reads)
     {
         size_t total = 0;
         for (const std::string& r : reads) if ((int)r.size() > kKmer) total += r.size() - kKmer + 1;
-        packed.reserve(total);
+        std::vector<Occurrence> raw;
+        raw.reserve(total);
         for (int id = 0; id < (int)reads.size(); ++id) {
             const std::string& r = reads[id];
             if (r.length() <= (size_t)kKmer) continue;                      // AddReadToIndex, realigner.cpp:436-438
@@ -147,21 +155,38 @@ struct KmerIndex {
                 if (b < 0) { valid = 0; key = 0; } else { key = (key << 2) | (uint64_t)b; ++valid; }
                 const int start = i - kKmer + 1;
                 if (start < 0) continue;
-                if (valid >= kKmer) packed.push_back(Occurrence{key, id, start});
+                if (valid >= kKmer) raw.push_back(Occurrence{key, id, start});
                 else odd[r.substr((size_t)start, kKmer)].push_back(Occurrence{0, id, start});
             }
         }
-        std::stable_sort(packed.begin(), packed.end(), [](const Occurrence& a, const Occurrence& b) { return a.key < b.key; });
+        size_t cap = 64;
+        while (cap < raw.size() * 2 + 2) cap <<= 1;
+        mask = cap - 1;
+        table.assign(cap, Slot{0, -1, 0});
+        // pass 1: count per key; pass 2: prefix offsets; pass 3: scatter in insertion order
+        std::vector<int> slot_of(raw.size());
+        for (size_t q = 0; q < raw.size(); ++q) {
+            uint64_t h = mix(raw[q].key) & mask;
+            while (table[h].first != -1 && table[h].key != raw[q].key) h = (h + 1) & mask;
+            if (table[h].first == -1) { table[h].key = raw[q].key; table[h].first = 0; }
+            table[h].count++;
+            slot_of[q] = (int)h;
+        }
+        int at = 0;
+        for (Slot& sl : table) if (sl.first != -1) { sl.first = at; at += sl.count; sl.count = 0; }
+        occ.resize(raw.size());
+        for (size_t q = 0; q < raw.size(); ++q) { Slot& sl = table[(size_t)slot_of[q]]; occ[(size_t)(sl.first + sl.count++)] = raw[q]; }
     }
 
     // occurrences of the k-mer starting at hap[i]; `key`/`valid` are the caller's rolling state for that window
     std::pair<const Occurrence*, const Occurrence*> find(const std::string& hap, int i, uint64_t key, bool valid) const
     {
         if (valid) {
-            auto lo = std::lower_bound(packed.begin(), packed.end(), key, [](const Occurrence& a, uint64_t k) { return a.key < k; });
-            auto hi = lo;
-            while (hi != packed.end() && hi->key == key) ++hi;
-            return {packed.data() + (lo - packed.begin()), packed.data() + (hi - packed.begin())};
+            if (table.empty()) return {nullptr, nullptr};
+            uint64_t h = mix(key) & mask;
+            while (table[h].first != -1 && table[h].key != key) h = (h + 1) & mask;
+            if (table[h].first == -1) return {nullptr, nullptr};
+            return {occ.data() + table[h].first, occ.data() + table[h].first + table[h].count};
         }
         if (odd.empty()) return {nullptr, nullptr};
         auto it = odd.find(hap.substr((size_t)i, kKmer));

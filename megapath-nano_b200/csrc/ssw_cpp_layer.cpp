@@ -8,6 +8,7 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
 #include <functional>
 #include <unordered_map>
@@ -131,6 +132,9 @@ void Aligner::CleanReferenceSequence(void) { reference_.clear(); }
 bool Aligner::AlignPairs(const std::vector<PairView>& pairs, const Filter& filter, std::vector<Alignment>* out) const
 {
     if (translate_.empty() || !out) return false;
+    static const bool timing = getenv("MPN_TIMING") != nullptr;
+    auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_start = now();
     const size_t np = pairs.size();
     out->assign(np, Alignment());
     // ---- pack: every DISTINCT sequence (by address and length) is translated and uploaded once -- in the realigner one haplotype
@@ -180,6 +184,7 @@ bool Aligner::AlignPairs(const std::vector<PairView>& pairs, const Filter& filte
     std::vector<mpn_result> res((size_t)n);
     std::vector<uint32_t> cig((size_t)(n * 24 + qbytes / 4 + 4096));
     int rc;
+    const double t_packed = now();
     for (int attempt = 0;; ++attempt) {
         mpn::SharedEngineLock lk;
         rc = mpn_align_batch_spans(lk.engine(), &pr, arena.data(), arena_bytes, rd_start.data(), rd_len.data(), rf_start.data(), rf_len.data(), mask.data(), n,
@@ -197,9 +202,11 @@ bool Aligner::AlignPairs(const std::vector<PairView>& pairs, const Filter& filte
             abort();
         }
     // ---- '=' / 'X' CIGAR + mismatch count per pair (independent: host threads)
+    const double t_gpu = now();
     mpn::parallel_for(n, 256, [&](int64_t k) {
         finish_alignment(res[k], cig.data(), arena.data() + rf_start[k], arena.data() + rd_start[k], rd_len[k], &(*out)[slot[k]]);
     });
+    if (timing) fprintf(stderr, "[ssw_cpp] %lld pairs: pack %.3f ms, engine %.3f ms, post-process %.3f ms\n", (long long)n, t_packed - t_start, t_gpu - t_packed, now() - t_gpu);
     return true;
 }
 
