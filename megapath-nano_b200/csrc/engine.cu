@@ -43,8 +43,11 @@ struct DevPool {
         int best = -1;
         for (size_t i = 0; i < free_list.size(); ++i)
             if (free_list[i].cap >= bytes && (best < 0 || free_list[i].cap < free_list[best].cap)) best = (int)i;
-        if (best >= 0 && free_list[best].cap <= bytes * 2 + (1u << 20)) { d = free_list[best]; free_list.erase(free_list.begin() + best); return; }
+        if (best >= 0 && free_list[best].cap <= bytes * 4 + (1u << 20)) { d = free_list[best]; free_list.erase(free_list.begin() + best); return; }
+        // big blocks are rounded up to a power of two so that batches of varying size (one realigner region after the other) keep
+        // hitting the cache instead of alternating cudaMalloc / cudaFree
         size_t want = bytes + bytes / 16 + 256;
+        if (want > (1u << 20)) { size_t p2 = 1u << 20; while (p2 < want) p2 <<= 1; want = p2; }
         cudaError_t err = cudaMalloc(&d.p, want);
         if (err != cudaSuccess) {            // out of memory: drop the cache and retry once
             cudaGetLastError();
@@ -151,6 +154,7 @@ struct mpn_batch {
     long long wide_stride = 0; int wide_blocks = 0;
     unsigned long long warp_dir_stride = 0; int warp_trace_blocks = 1;
     int64_t sum_rd = 0, sum_rf = 0;       // over pairs (worst-case CIGAR words = sum_rd + sum_rf)
+    int64_t n_long_rows = 0;              // pairs whose read has more than 512 rows
     int arena_retries = 0;
 };
 
@@ -324,7 +328,7 @@ static mpn_batch* upload_impl(mpn_engine* e, int slot_id, const mpn_params* p, c
     std::vector<int32_t>& bin = e->h_bin;
     bin.resize(npairs);
     std::vector<int64_t> bin_count(N_STRIPS + 2, 0);
-    int64_t cm_total = 0, cells = 0;
+    int64_t cm_total = 0, cells = 0, n_long = 0;
     int max_rd = 0, max_rf = 0, min_rf = 0x7fffffff;
     const bool packed_ok = n <= 8;
     static const bool no_long16 = getenv("MPN_NO_LONG16") != nullptr;      // A/B switch: send long / saturating pairs to the 32-bit kernel
@@ -333,6 +337,7 @@ static mpn_batch* upload_impl(mpn_engine* e, int slot_id, const mpn_params* p, c
         const int64_t rl = src.rl(i), fl = src.fl(i);
         if (rl < 0 || fl < 0 || rl > 0x3fffffff || fl > 0x3fffffff || !src.span_ok(i)) { delete b; return nullptr; }
         cells += rl * fl;
+        n_long += rl > 512;
         max_rd = std::max<int>(max_rd, (int)rl); max_rf = std::max<int>(max_rf, (int)fl); min_rf = std::min<int>(min_rf, (int)fl);
         cm_total += fl;
         int c = packed_ok ? LONG_BIN : WIDE_BIN;
@@ -343,7 +348,7 @@ static mpn_batch* upload_impl(mpn_engine* e, int slot_id, const mpn_params* p, c
         bin[i] = c; bin_count[c]++;
     }
     b->total_cells = cells; b->max_rd = max_rd; b->colrec_words = cm_total;
-    b->sum_rf = cm_total; b->sum_rd = src.read_bases();
+    b->sum_rf = cm_total; b->sum_rd = src.read_bases(); b->n_long_rows = n_long;
     b->n_wide_pre = bin_count[WIDE_BIN] + bin_count[LONG_BIN];
     {   // a launch with too few tasks cannot fill the GPU and the launches of a batch run back to back: fold thin bins into the next
         // larger strip (a few more dead rows, far better occupancy).  The largest packed bin keeps whatever it has.
@@ -445,7 +450,8 @@ static mpn_batch* upload_impl(mpn_engine* e, int slot_id, const mpn_params* p, c
         b->warp_dir_stride = warptr_region_bytes(std::max(max_rd, 1));
         const unsigned long long budget = 6ull << 30;
         long long wb = (long long)(budget / (b->warp_dir_stride * WARPTR_WARPS));
-        wb = std::min<long long>(wb, (npairs + WARPTR_WARPS - 1) / WARPTR_WARPS);
+        // warps that can be busy at all: the long reads (always traced by this kernel in small batches) plus a share of wide bands
+        wb = std::min<long long>(wb, (n_long + npairs / 8 + 16 + WARPTR_WARPS - 1) / WARPTR_WARPS);
         b->warp_trace_blocks = (int)std::max<long long>(std::min<long long>(wb, (long long)e->sm_count * 4), 1);
         pool.take(b->warp_dir, (size_t)b->warp_dir_stride * WARPTR_WARPS * (size_t)b->warp_trace_blocks + 256);
         pool.take(b->cig, b->cig_cap * sizeof(uint32_t));
@@ -574,7 +580,10 @@ extern "C" int mpn_batch_run(mpn_batch* b)
         CK(cudaGetLastError());
         e->launches++;
         if (e->profile) { CK(cudaEventRecord(e->ev[3], st)); e->ev_valid = 4; }
-        TraceParams tp{b->fin.flag, b->fin.filters, b->p.filterd, b->fin.gapO, b->fin.gapE, b->p.n, b->dmat.as<int8_t>()};
+        // lane-per-pair traceback is the throughput path; a few long reads in a batch (the haplotype-vs-reference pairs of a realigner
+        // region) would serialise a thousand rows on single lanes, so they take the warp-per-pair kernel unless there are many of them
+        const int lane_max_rows = b->n_long_rows <= 4096 ? 512 : NARROW_MAX_ROWS;
+        TraceParams tp{b->fin.flag, b->fin.filters, b->p.filterd, b->fin.gapO, b->fin.gapE, b->p.n, b->dmat.as<int8_t>(), lane_max_rows};
         Arena ar{b->scratch.as<uint8_t>(), b->scratch_bytes, b->counters.as<unsigned long long>() + 64};
         {
             // narrow bands: setup (begin positions, filters, one queue per band-width class), then one lane-persistent row kernel per

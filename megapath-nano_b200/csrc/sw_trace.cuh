@@ -20,6 +20,7 @@ struct TraceParams {
     int32_t flag, filters, filterd;
     int32_t gapO, gapE, n;
     const int8_t* mat;            // n*n, device
+    int32_t lane_max_rows;        // narrow bands: reads with more rows go to the warp-per-pair kernel instead of the lane-per-pair one
 };
 
 struct FinalResult {              // second half of s_align (ssw.h:47-57)

@@ -1,5 +1,5 @@
 // Narrow-band traceback DP with the band row held in registers (sm_100a): replaces banded_sw (ssw.c:532-616) for bands of up to
-// 15 cells on reads of up to NARROW_MAX_ROWS rows -- every pair of BASELINE configs[1].
+// 15 cells on reads of up to NARROW_MAX_ROWS rows (fewer when the batch holds only a few long reads) -- every pair of BASELINE configs[1].
 //
 //   sw_band_setup_kernel     one thread per pair: begin positions from the reverse pass (ssw.c:820-832), the CIGAR filters of
 //                            ssw.c:833, the trivial "1M" case, and the first band |sub_ref - sub_read| + 1 (ssw.c:838); pairs are
@@ -65,7 +65,7 @@ sw_band_setup_kernel(const SwTask* __restrict__ order, int ntasks, const FwdResu
                 unsigned long long o = atomicAdd(cig_used, 1ull);          // "1M" (ssw.c:625,680-687)
                 if (o + 1 > cig_cap) r.status = 6;
                 else { cig[o] = 1u << 4; r.cigar_off = (int64_t)o; r.cigar_len = 1; }
-            } else if (tp.n > 8 || bw > ROWS_MAXBW || sub_read > NARROW_MAX_ROWS) {
+            } else if (tp.n > 8 || bw > ROWS_MAXBW || sub_read > tp.lane_max_rows) {
                 // wide bands, and reads so long that one lane would serialise millions of cells: one warp per pair instead
                 r.status = 7; br.bw = bw; flag_list[atomicAdd(nflag, 1)] = k;
             } else {
