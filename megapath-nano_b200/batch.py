@@ -42,6 +42,8 @@ def lib():
         L.mpn_batch_free.argtypes = [ct.c_void_p]
         L.mpn_align_batch.argtypes = [ct.c_void_p, ct.POINTER(MpnParams), ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_int64,
                                       ct.c_void_p, ct.c_void_p, ct.c_int64]
+        L.mpn_align_batch_spans.argtypes = [ct.c_void_p, ct.POINTER(MpnParams), ct.c_void_p, ct.c_int64, ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_void_p,
+                                            ct.c_void_p, ct.c_int64, ct.c_void_p, ct.c_void_p, ct.c_int64]
         assert ct.sizeof(MpnParams) == 40 and RESULT_DTYPE.itemsize == 40, (ct.sizeof(MpnParams), RESULT_DTYPE.itemsize)
         _lib = L
     return _lib
@@ -137,6 +139,32 @@ class Engine:
         if rc:
             raise RuntimeError(f"mpn_align_batch -> {rc}")
         return out, cig
+
+
+def _align_spans(self, b, seq, rd_start, rd_len, rf_start, rf_len, masklen, cigar_cap=None):
+    """Pairs that share sequences (mpn_align_batch_spans): `seq` is one int8 arena, pair i aligns seq[rd_start[i] : +rd_len[i]] to
+    seq[rf_start[i] : +rf_len[i]].  `b` carries the scoring / flag fields of a PairBatch.  Returns (records, cigar arena)."""
+    seq = np.ascontiguousarray(seq, dtype=np.int8)
+    rd_start = np.ascontiguousarray(rd_start, dtype=np.int64); rf_start = np.ascontiguousarray(rf_start, dtype=np.int64)
+    rd_len = np.ascontiguousarray(rd_len, dtype=np.int32); rf_len = np.ascontiguousarray(rf_len, dtype=np.int32)
+    masklen = np.ascontiguousarray(masklen, dtype=np.int32)
+    n = len(rd_start)
+    if cigar_cap is None:
+        cigar_cap = n * 24 + int(rd_len.sum()) // 4 + 4096
+    out = np.zeros(n, dtype=RESULT_DTYPE)
+    cig = np.zeros(max(cigar_cap, 1), dtype=np.uint32)
+    keep = []
+    p = self._params(b, keep)
+    rc = self.L.mpn_align_batch_spans(self.h, ct.byref(p), _ptr(seq), len(seq), _ptr(rd_start), _ptr(rd_len), _ptr(rf_start), _ptr(rf_len), _ptr(masklen), n,
+                                      _ptr(out), _ptr(cig), int(cigar_cap))
+    if rc == -3:                                       # MPN_E_CIGAR_SPACE: size for the worst case once
+        return _align_spans(self, b, seq, rd_start, rd_len, rf_start, rf_len, masklen, cigar_cap=int(rd_len.sum() + rf_len.sum()) + 16 * n)
+    if rc:
+        raise RuntimeError(f"mpn_align_batch_spans -> {rc}")
+    return out, cig
+
+
+Engine.align_spans = _align_spans
 
 
 def as_table(rec, cig, cigar_cap=64):

@@ -113,14 +113,13 @@ class SSW(object):
         if n == 0:
             return []
         rl = np.array([len(q) for q in qs], dtype=np.int64)
+        # one arena: the reference once, then the queries; every pair points at the same reference span
+        seq = np.concatenate([self.rNum] + qs)
+        rd_start = self.reference_len + np.concatenate([[0], np.cumsum(rl)[:-1]]).astype(np.int64)
         b = type("B", (), {})()
-        b.reads = np.concatenate(qs) if n else np.zeros(0, np.int8)
-        b.read_off = np.concatenate([[0], np.cumsum(rl)]).astype(np.int64)
-        b.refs = np.tile(self.rNum, n)
-        b.ref_off = (np.arange(n + 1, dtype=np.int64) * self.reference_len)
-        b.masklen = np.array([self._mask_len(int(l)) for l in rl], dtype=np.int32)
-        b.mat, b.n, b.gapO, b.gapE, b.score_size, b.flag, b.filters, b.filterd, b.npairs = self.mat_np, 5, self.gap_open, self.gap_extend, 2, 2, 0, 0, n
-        rec, cig = self._engine.align(b)
+        b.mat, b.n, b.gapO, b.gapE, b.score_size, b.flag, b.filters, b.filterd = self.mat_np, 5, self.gap_open, self.gap_extend, 2, 2, 0, 0
+        masklen = np.array([self._mask_len(int(l)) for l in rl], dtype=np.int32)
+        rec, cig = self._engine.align_spans(b, seq, rd_start, rl.astype(np.int32), np.zeros(n, np.int64), np.full(n, self.reference_len, np.int32), masklen)
         out = []
         for i in range(n):
             o, l = int(rec["cigar_off"][i]), int(rec["cigar_len"][i])
