@@ -40,15 +40,6 @@ struct FwdResult {                // per pair, forward half of s_align (ssw.h:47
     int32_t want_rev;             // reverse pass requested by the flag logic of ssw.c:817
 };
 
-// value of `cur` (this chunk) or `prev` (previous chunk of 32 columns) at column (lane - k), 1 <= k <= 31
-__device__ __forceinline__ int shift_back(int cur, int prev, int k, int lane)
-{
-    const int src = (lane - k) & 31;
-    const int vc = __shfl_sync(0xffffffffu, cur, src);
-    const int vp = __shfl_sync(0xffffffffu, prev, src);
-    return lane >= k ? vc : vp;
-}
-
 // one warp per forward task
 __global__ void __launch_bounds__(128)
 sw_finish_kernel(const SwTask* __restrict__ fwd_tasks, int ntasks, const SwEnds* __restrict__ ends, const uint32_t* __restrict__ colrec,

@@ -1,8 +1,9 @@
-// Banded traceback + CIGAR kernel (sm_100a): replaces banded_sw (ssw.c:532-718) and the begin-position / CIGAR part of
-// ssw_align (ssw.c:830-848).  One thread per pair; the band of a 150-300 bp read is 3-9 cells wide, so the work per pair
-// is a few thousand int32 cells, ~1 % of the score passes.  Direction bits live in a global scratch arena that the
-// kernel carves up with an atomic bump pointer (the band is doubled until the banded maximum reaches the score, so the
-// size is only known on the device); CIGAR words go to a second arena the same way.
+// Generic banded traceback + CIGAR kernel (sm_100a): banded_sw (ssw.c:532-718) and the begin-position / CIGAR part of
+// ssw_align (ssw.c:830-848) for ANY band width, one thread per pair.  It is the last stage of the traceback chain -- the
+// register-row kernels (sw_trace_rows.cuh) take bands of up to 15 cells, the warp kernel (sw_trace_warp.cuh) up to 544 -- and
+// only sees what those hand on (status 8).  This file also defines the types the whole chain shares.  Direction bytes live in a
+// global scratch arena carved up with an atomic bump pointer (the band is doubled until the banded maximum reaches the score, so
+// the size is only known on the device); CIGAR words go to a second arena the same way.
 //
 // banded_sw semantics kept:
 //   band attempt bw: row i covers columns max(0,i-bw) .. min(refLen-1,i+bw); E/F are NOT floored; ties prefer the

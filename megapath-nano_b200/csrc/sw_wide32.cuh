@@ -159,8 +159,6 @@ sw_wide32_kernel(const SwTask* __restrict__ tasks, int ntasks, int* __restrict__
 inline size_t wide32_smem_bytes(int n) { return sizeof(int) * (size_t)((((n + 1) * (n + 1) + 31) & ~31) + WIDE_KR * WIDE_BLOCK); }
 
 // host launchers.  `boundary` must hold 2 * stride ints per warp of the grid.
-struct WideGrid { int blocks; long long stride; };
-
 inline void launch_wide32_impl(const SwTask* tasks, int ntasks, int* counter, const int8_t* seq, const int8_t* mat, int n, int gapO, int gapE,
                                uint32_t* colrec, SwEnds* ends, int* boundary, long long stride, int blocks, int only_flagged, cudaStream_t st)
 {
