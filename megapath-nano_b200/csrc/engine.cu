@@ -136,7 +136,7 @@ struct mpn_batch {
     std::vector<int8_t> mat;
     int64_t npairs = 0;
     int64_t total_cells = 0;
-    int max_rd = 0;
+    int max_rd = 0, max_rf = 0;
     std::vector<BinLaunch> bins;
     int64_t n_wide_pre = 0;               // pairs routed to the 32-bit kernel by the host classifier
     Score16 sc16{};
@@ -347,7 +347,7 @@ static mpn_batch* upload_impl(mpn_engine* e, int slot_id, const mpn_params* p, c
         if (no_long16 && c == LONG_BIN) c = WIDE_BIN;
         bin[i] = c; bin_count[c]++;
     }
-    b->total_cells = cells; b->max_rd = max_rd; b->colrec_words = cm_total;
+    b->total_cells = cells; b->max_rd = max_rd; b->max_rf = max_rf; b->colrec_words = cm_total;
     b->sum_rf = cm_total; b->sum_rd = src.read_bases(); b->n_long_rows = n_long;
     b->n_wide_pre = bin_count[WIDE_BIN] + bin_count[LONG_BIN];
     {   // a launch with too few tasks cannot fill the GPU and the launches of a batch run back to back: fold thin bins into the next
@@ -513,8 +513,13 @@ static void launch_strips(mpn_batch* b, const SwTask* tasks, bool forward, SwEnd
         cudaStream_t st = fork ? e->aux[turn++ % mpn_engine::NAUX] : main_st;
         int* counter = reinterpret_cast<int*>(b->counters.as<unsigned long long>() + slot++);
         if (bl.cfg == LONG_BIN) {
-            const int blocks = (int)std::min<int64_t>((bl.count + LONG_BLOCK / 32 - 1) / (LONG_BLOCK / 32), b->wide_blocks);
-            sw_long16_kernel<LONG_KR><<<blocks, LONG_BLOCK, long16_smem_bytes<LONG_KR>(), st>>>(tasks + bl.first, (int)bl.count, counter, b->seq.as<int8_t>(), b->sc16,
+            // few long pairs: several warps per pair (strips pipelined across the warps of a block), else one warp per pair
+            const int64_t slots = (int64_t)b->wide_blocks * (LONG_BLOCK / 32);
+            const int nwp = (b->max_rf >= (1 << 20) || bl.count * 2 > slots) ? 1 : (bl.count * 4 <= slots ? 4 : 2);
+            const int ppb = (LONG_BLOCK / 32) / nwp;
+            const int blocks = (int)std::min<int64_t>((bl.count + ppb - 1) / ppb, b->wide_blocks);
+            auto fn = nwp == 1 ? sw_long16_kernel<LONG_KR, 1> : (nwp == 2 ? sw_long16_kernel<LONG_KR, 2> : sw_long16_kernel<LONG_KR, 4>);
+            fn<<<blocks, LONG_BLOCK, long16_smem_bytes<LONG_KR>(), st>>>(tasks + bl.first, (int)bl.count, counter, b->seq.as<int8_t>(), b->sc16,
                 forward ? b->colrec.as<uint32_t>() : nullptr, ends, b->long_boundary.as<uint32_t>(), b->wide_stride);
             e->wide_pairs += forward ? bl.count : 0;
         } else if (bl.cfg == WIDE_BIN) {

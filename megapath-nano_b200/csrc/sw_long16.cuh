@@ -15,6 +15,11 @@
 // Per packed cell: PRMT, VIADDMNMX.U16x2 (diagonal + score, clamped), VIMNMX3.U16x2, VIMNMX.U16x2 (floor), 2x VIADDMNMX.U16x2 (E, F),
 // 1/2 VIMNMX3.U16x2 (column maximum) on the alu pipe + one VIADD.16x2 on the fma pipe.
 //
+// NWP > 1 (small batches): NWP warps of a block share one pair.  Warp w takes strips w, w + NWP, ... and runs a few dozen columns behind
+// the warp that owns the strip above: the producer publishes "32-column blocks flushed" in shared memory after a __threadfence, the
+// consumer spins on it (bounded; a broken invariant traps instead of hanging) before it reads the boundary words with L2 loads.  The early
+// end of reverse passes is not used in this mode (it changes no result: no column after the terminating one can hold a higher score).
+//
 // Output contract identical to the other score kernels: SwEnds per task (+ the per-column records on forward passes).
 #pragma once
 #include "sw_common.cuh"
@@ -52,7 +57,7 @@ __device__ __forceinline__ uint32_t umax2_track(uint32_t a, uint32_t b, bool& a_
 template <int KR>
 __host__ __device__ constexpr size_t long16_smem_bytes() { return (size_t)2 * ((KR + 3) / 4) * LONG_BLOCK * sizeof(uint4) + (size_t)2 * 32 * (LONG_BLOCK / 32) * sizeof(uint32_t); }
 
-template <int KR>
+template <int KR, int NWP>
 __global__ void __launch_bounds__(LONG_BLOCK, 3)
 sw_long16_kernel(const SwTask* __restrict__ tasks, int ntasks, int* __restrict__ counter, const int8_t* __restrict__ seq,
                  const Score16 sc, uint32_t* __restrict__ colrec, SwEnds* __restrict__ out, uint32_t* __restrict__ boundary, long long boundary_stride)
@@ -64,35 +69,86 @@ sw_long16_kernel(const SwTask* __restrict__ tasks, int ntasks, int* __restrict__
     uint32_t* const stage = reinterpret_cast<uint32_t*>(lsnap + 2 * KRQ * LONG_BLOCK);   // [2 words][32 steps][warps per block]
     constexpr int NW = LONG_BLOCK / 32;
 
+    static_assert(NWP == 1 || NWP == 2 || NWP == 4, "warps per pair");
+    constexpr int PPB = NW / NWP;                   // pairs per block
+    __shared__ int sh_ti[NW];                       // NWP > 1: task index of each pair of the block
+    __shared__ int sh_progress[NW];                 // NWP > 1: per warp, strip << 16 | 32-column blocks whose boundary words are flushed
+    __shared__ unsigned long long sh_key[NW];
+    __shared__ int sh_row[NW], sh_wide[NW];
     const int tid = threadIdx.x, t = tid & 31, wib = tid >> 5;
-    const long long wslot = (long long)blockIdx.x * NW + wib;
+    const int wip = wib % NWP, pib = wib / NWP;     // warp inside the pair, pair inside the block
+    const long long wslot = NWP == 1 ? (long long)blockIdx.x * NW + wib : (long long)blockIdx.x * PPB + pib;
     uint32_t* const bA = boundary + wslot * 2 * boundary_stride;        // per column: F(bottom) << 16 | running column maximum
     uint32_t* const bB = bA + boundary_stride;                          // per column: H(bottom) << 16 (low half unused)
     const uint32_t mgapO2 = sc.mgapO2, mgapE2 = sc.mgapE2;
     // merge selectors (received word, own word): lo <- received.high, hi <- own.lo; thread 0 receives the boundary words instead
     const uint32_t selFH = 0x5432u;
 
+    int prev_out = -1;                              // NWP > 1: output slot of the pair this warp group just finished (merged after the barrier)
     for (;;) {
         int ti = 0;
-        if (t == 0) ti = atomicAdd(counter, 1);
-        ti = __shfl_sync(0xffffffffu, ti, 0);
-        if (ti >= ntasks) break;
-        const SwTask tk = tasks[ti];
+        if (NWP == 1) {
+            if (t == 0) ti = atomicAdd(counter, 1);
+            ti = __shfl_sync(0xffffffffu, ti, 0);
+            if (ti >= ntasks) break;
+        } else {
+            __syncthreads();                        // every warp of the block has finished its strips of the previous pairs
+            if (prev_out >= 0 && wip == 0 && t == 0) {
+                // merge the warps of the pair: larger (score, -column) wins; on ties the smaller row (rows grow with the strip index)
+                unsigned long long bk = 0; int br = 0, bw_ = 0;
+                for (int q = 0; q < NWP; ++q) {
+                    const unsigned long long k2 = sh_key[pib * NWP + q]; const int r2 = sh_row[pib * NWP + q];
+                    bw_ |= sh_wide[pib * NWP + q];
+                    if ((k2 >> 8) > (bk >> 8) || ((k2 >> 8) == (bk >> 8) && (k2 >> 40) != 0 && r2 < br)) { bk = k2; br = r2; }
+                }
+                SwEnds e;
+                e.score = (int)(bk >> 40);
+                e.col = e.score > 0 ? (int)(0xffffffu - (unsigned)((bk >> 8) & 0xffffffu)) : -1;
+                e.row = e.score > 0 ? br : 0;
+                e.flags = bw_ ? SW_FLAG_NEEDS_WIDE : 0;
+                out[prev_out] = e;
+            }
+            prev_out = -1;
+            __syncthreads();
+            if (tid < PPB) sh_ti[tid] = atomicAdd(counter, 1);
+            if (tid < NW) sh_progress[tid] = -1;
+            __syncthreads();
+            if (sh_ti[0] >= ntasks) break;          // task indices are handed out in order: the first one decides for the block
+            ti = sh_ti[pib];
+        }
+        const bool have = ti < ntasks;
+        SwTask tk;
+        tk.rd_base = tk.rf_base = 0; tk.cm_off = -1; tk.rd_len = tk.rf_len = 0; tk.dir = 1; tk.out = 0; tk.stop = 0; tk.pad_ = 0;
+        if (have) tk = tasks[ti];
         const int rd_len = tk.rd_len, tdir = tk.dir;
         int rf_len = tk.rf_len;
         if (rd_len <= 0 || rf_len <= 0) {
-            if (t == 0) { SwEnds e; e.score = 0; e.col = -1; e.row = 0; e.flags = 0; out[tk.out] = e; }
+            if (have && t == 0 && wip == 0) { SwEnds e; e.score = 0; e.col = -1; e.row = 0; e.flags = 0; out[tk.out] = e; }
+            if (NWP > 1 && t == 0) { sh_key[wib] = 0; sh_row[wib] = 0; sh_wide[wib] = 0; }
             continue;
         }
         const int nstrips = (rd_len + CAP - 1) / CAP;
         const int dead = nstrips * CAP - rd_len;
-        const uint32_t stop2 = tk.stop > 0 ? (((uint32_t)tk.stop + LBIAS) | (((uint32_t)tk.stop + LBIAS) << 16)) : 0u;
+        const uint32_t stop2 = (NWP == 1 && tk.stop > 0) ? (((uint32_t)tk.stop + LBIAS) | (((uint32_t)tk.stop + LBIAS) << 16)) : 0u;
+        const int nblocks_total = (rf_len + 2 * G - 1 + G - 1) / G;        // 32-step blocks of one strip (NWP > 1: no early end)
         unsigned long long runkey = 0;              // (score << 40 | 0xffffff - col << 8): best over the strips done so far
         int runrow = 0;
         int wide = 0;
 
-        for (int strip = 0; strip < nstrips; ++strip) {
+        for (int strip = wip; strip < nstrips; strip += NWP) {
             const bool first = strip == 0, last = strip == nstrips - 1;
+            // NWP > 1: wait until the warp that owns the strip above has flushed `need` blocks of boundary words
+            auto wait_for = [&](int need) {
+                if (NWP == 1 || first) return;
+                const int want = ((strip - 1) << 16) | min(need, nblocks_total);
+                const volatile int* pr = sh_progress + pib * NWP + (strip - 1) % NWP;
+                unsigned spins = 0;
+                while (*pr < want) {
+                    __nanosleep(40);
+                    if (++spins > (1u << 26)) __trap();                     // broken invariant: fail loudly instead of hanging the GPU
+                }
+                __threadfence();
+            };
             uint32_t H[KR], E[KR], sel[KR];
             // selectors: low half = row of stage 2t, high half = row of stage 2t + 1 (sw_strip16.cuh)
 #pragma unroll
@@ -117,9 +173,10 @@ sw_long16_kernel(const SwTask* __restrict__ tasks, int ntasks, int* __restrict__
             int nsteps = rf_len + 2 * G - 1;
             // chunk 0: matrix rows of the target bases and the boundary words of columns t
             uint32_t tnext = 0, anext = LBIAS2, bnext = LBIAS2;
+            wait_for(3);                            // columns 0 .. 31 are flushed at the end of the producer's block 2
             if (t < rf_len) {
                 tnext = sc.matrow[seq[tk.rf_base + (int64_t)tdir * t] & 7];
-                if (!first) { anext = bA[t]; bnext = bB[t]; }
+                if (!first) { anext = NWP == 1 ? bA[t] : __ldcg(bA + t); bnext = NWP == 1 ? bB[t] : __ldcg(bB + t); }
             }
             for (int s0 = 0; s0 < nsteps; s0 += G) {
                 {   // reverse passes: the pass ends in the column whose maximum equals `stop` (ssw.c:483); a stage that has seen it
@@ -132,9 +189,10 @@ sw_long16_kernel(const SwTask* __restrict__ tasks, int ntasks, int* __restrict__
                 {
                     const int idx = s0 + G + t;
                     tnext = 0; anext = LBIAS2; bnext = LBIAS2;
+                    if (s0 + G < rf_len) wait_for(s0 / G + 4);      // columns of the next chunk: flushed at the end of the producer's block s0/G + 3
                     if (idx < rf_len) {
                         tnext = sc.matrow[seq[tk.rf_base + (int64_t)tdir * idx] & 7];
-                        if (!first) { anext = bA[idx]; bnext = bB[idx]; }
+                        if (!first) { anext = NWP == 1 ? bA[idx] : __ldcg(bA + idx); bnext = NWP == 1 ? bB[idx] : __ldcg(bB + idx); }
                     }
                 }
 #pragma unroll 2
@@ -199,6 +257,11 @@ sw_long16_kernel(const SwTask* __restrict__ tasks, int ntasks, int* __restrict__
                         else if (tk.cm_off >= 0) colrec[tk.cm_off + c] = ((wA & 0xffffu) - LBIAS) | (((wB >> 16) - LBIAS) << 16);
                     }
                 }
+                if (NWP > 1 && !last) {             // publish: everything up to this block is visible to the consumer warp
+                    __threadfence();
+                    __syncwarp();
+                    if (t == 0) *(volatile int*)(sh_progress + wib) = (strip << 16) | (s0 / G + 1);
+                }
                 __syncwarp();
             }
             // ---- strip result: reduce (score, first column, stage) over the 64 stages
@@ -234,19 +297,26 @@ sw_long16_kernel(const SwTask* __restrict__ tasks, int ntasks, int* __restrict__
             }
             row = __shfl_sync(0xffffffffu, row, wstage >> 1);
             if ((key >> 8) > (runkey >> 8)) { runkey = key; runrow = row; }     // ties keep the earlier strip (smaller rows)
+            if (NWP > 1 && !last && nblocks_total > 0 && t == 0) *(volatile int*)(sh_progress + wib) = (strip << 16) | 0xffff;   // strip complete
             // a strip that ended early bounds the terminating column for the strips below it
             // (columns up to nsteps - 64 have their boundary words written; the terminating column lies before that)
             if (nsteps < rf_len + 2 * G - 1) rf_len = min(rf_len, nsteps - (2 * G - 1));
             __syncwarp();
         }
         const unsigned anywide = __ballot_sync(0xffffffffu, wide != 0);
-        if (t == 0) {
-            SwEnds e;
-            e.score = (int)(runkey >> 40);
-            e.col = e.score > 0 ? (int)(0xffffffu - (unsigned)((runkey >> 8) & 0xffffffu)) : -1;
-            e.row = e.score > 0 ? runrow : 0;
-            e.flags = anywide ? SW_FLAG_NEEDS_WIDE : 0;
-            out[tk.out] = e;
+        if (NWP == 1) {
+            if (t == 0) {
+                SwEnds e;
+                e.score = (int)(runkey >> 40);
+                e.col = e.score > 0 ? (int)(0xffffffu - (unsigned)((runkey >> 8) & 0xffffffu)) : -1;
+                e.row = e.score > 0 ? runrow : 0;
+                e.flags = anywide ? SW_FLAG_NEEDS_WIDE : 0;
+                out[tk.out] = e;
+            }
+        } else {
+            // merge the warps of the pair: larger (score, -column) wins; on ties the smaller row (rows grow with the strip index)
+            if (t == 0) { sh_key[wib] = runkey; sh_row[wib] = runrow; sh_wide[wib] = anywide ? 1 : 0; }
+            prev_out = tk.out;
         }
     }
 }
