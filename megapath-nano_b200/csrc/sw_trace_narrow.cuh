@@ -37,11 +37,20 @@ sw_band_trace_kernel(const SwTask* __restrict__ order, int ntasks, const FwdResu
     const unsigned long long* dirrow = reinterpret_cast<const unsigned long long*>(scratch.base + br.dir_off);
     int l = 0;
     unsigned long long coff = 0;
+    // The walk yields the CIGAR back to front and its length is only known at the end.  Pass 0 counts and keeps the first SHORT words
+    // in a local buffer: a short-read CIGAR (a handful of runs) is then written from the buffer and the second walk is skipped.
+    constexpr int SHORT = 24;
+    uint32_t buf[SHORT];
     for (int pass = 0; pass < 2; ++pass) {
         int ti = sub_read - 1, tj = sub_ref - 1, state = 2, run = 0, cnt = 0;
         int op = 0, prev = 0;                               // BAM codes: 0 = M, 1 = I, 2 = D
         int cur_row = ti;
         unsigned long long cur = dirrow[ti], nxt = ti > 0 ? dirrow[ti - 1] : 0ull;      // row ti and, prefetched, row ti-1
+        auto emit = [&](uint32_t word) {
+            if (pass) cig[coff + (unsigned)(l - 1 - cnt)] = word;
+            else if (cnt < SHORT) buf[cnt] = word;
+            ++cnt;
+        };
         while (ti > 0) {
             // the reference indexes a flat array; cells left or right of the band alias into the neighbouring rows
             const int cpos = tj - band_x(ti, bw);
@@ -70,22 +79,18 @@ sw_band_trace_kernel(const SwTask* __restrict__ order, int ntasks, const FwdResu
             }
             if (ti != cur_row) { cur = nxt; cur_row = ti; nxt = ti > 0 ? dirrow[ti - 1] : 0ull; }
             if (op == prev) ++run;
-            else {
-                if (pass) cig[coff + (unsigned)(l - 1 - cnt)] = ((uint32_t)run << 4) | (uint32_t)prev;
-                ++cnt; prev = op; run = 1;
-            }
+            else { emit(((uint32_t)run << 4) | (uint32_t)prev); prev = op; run = 1; }
         }
-        if (op == 0) {
-            if (pass) cig[coff + (unsigned)(l - 1 - cnt)] = ((uint32_t)(run + 1) << 4);
-            ++cnt;
-        } else {
-            if (pass) { cig[coff + (unsigned)(l - 1 - cnt)] = ((uint32_t)run << 4) | (uint32_t)op; cig[coff + (unsigned)(l - 2 - cnt)] = 1u << 4; }
-            cnt += 2;
-        }
+        if (op == 0) emit((uint32_t)(run + 1) << 4);
+        else { emit(((uint32_t)run << 4) | (uint32_t)op); emit(1u << 4); }
         if (!pass) {
             l = cnt;
             coff = atomicAdd(cig_used, (unsigned long long)l);
             if (coff + (unsigned long long)l > cig_cap) { r.status = 6; out[i] = r; return; }
+            if (l <= SHORT) {
+                for (int q = 0; q < l; ++q) cig[coff + (unsigned)(l - 1 - q)] = buf[q];
+                break;
+            }
         }
     }
     r.cigar_len = l;
