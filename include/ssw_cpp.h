@@ -55,6 +55,10 @@ struct PairView {
   const char* ref;   int ref_len;
 };
 
+/* AlignIndexed: a pool of distinct sequences plus pairs that name their query and target by index into the pool */
+struct SeqView { const char* text; int len; };
+struct PairIndex { int32_t query; int32_t target; };
+
 class Aligner {
  public:
   Aligner(void);                                                       /* {A,C,G,T,N}, +4/-6, gaps 8/2 (ssw_cpp.cpp:218-230 with realigner.cpp's values) */
@@ -76,6 +80,9 @@ class Aligner {
   bool AlignBatch(const std::vector<std::string>& queries, const Filter& filter, std::vector<Alignment>* out) const;
   /* NEW: arbitrary (query, target) pairs, one GPU submit.  Empty queries give a cleared Alignment (Align would return false). */
   bool AlignPairs(const std::vector<PairView>& pairs, const Filter& filter, std::vector<Alignment>* out) const;
+  /* NEW: the same for callers that already know which pairs share sequences (a haplotype met by hundreds of reads): every
+   * sequence of `pool` is translated and uploaded once; pairs with an empty query or target give a cleared Alignment. */
+  bool AlignIndexed(const std::vector<SeqView>& pool, const std::vector<PairIndex>& pairs, const Filter& filter, std::vector<Alignment>* out) const;
 
   void Clear(void);
   bool ReBuild(void);

@@ -26,7 +26,8 @@
 namespace {
 
 using StripedSmithWaterman::Alignment;
-using StripedSmithWaterman::PairView;
+using StripedSmithWaterman::PairIndex;
+using StripedSmithWaterman::SeqView;
 
 // ---- options fixed by ReAligner::set_options (realigner.cpp:62-72)
 constexpr int kKmer = 32;
@@ -454,25 +455,26 @@ int realign_many(const mpn_region* regions, int nregions, struct_str_arr** out)
     Stats st;
     double t0 = now_s();
     // ---- 1. host: k-mer fast pass, then the list of Smith-Waterman pairs of every region
-    std::vector<PairView> pairs;
     for (int r = 0; r < nregions; ++r) load_region(rgs[r], regions[r]);
     // regions are independent: one host thread each when there are several, else threads over the haplotypes of the one region
     if (nregions > 1) mpn::parallel_for(nregions, 1, [&](int64_t r) { fast_pass(rgs[(size_t)r], false); plan_read_pairs(rgs[(size_t)r]); });
     else if (nregions == 1) { fast_pass(rgs[0], rgs[0].reads.size() * rgs[0].haplotypes.size() >= 2048); plan_read_pairs(rgs[0]); }
+    // sequence pool: per region the reference, its haplotypes and its reads, each once; pairs name them by index
+    std::vector<SeqView> pool;
+    std::vector<PairIndex> pairs;
     for (int r = 0; r < nregions; ++r) {
         Region& rg = rgs[r];
+        const int32_t ref_id = (int32_t)pool.size();
+        pool.push_back(SeqView{rg.reference.c_str(), (int)rg.reference.length()});
+        const int32_t hap0 = (int32_t)pool.size();
+        for (const std::string& h : rg.haplotypes) pool.push_back(SeqView{h.c_str(), (int)strlen(h.c_str())});
+        const int32_t read0 = (int32_t)pool.size();
+        for (const std::string& q : rg.reads) pool.push_back(SeqView{q.c_str(), (int)strlen(q.c_str())});
         rg.first_pair = pairs.size();
-        for (const HapRecord& h : rg.haps) {
-            const std::string& hap = rg.haplotypes[h.index];
-            pairs.push_back(PairView{hap.c_str(), (int)strlen(hap.c_str()), rg.reference.c_str(), (int)rg.reference.length()});
-        }
-        for (const auto& rh : rg.read_hap_pairs) {
-            const std::string& read = rg.reads[rh.first];
-            const std::string& hap = rg.haplotypes[rg.haps[rh.second].index];
-            pairs.push_back(PairView{read.c_str(), (int)strlen(read.c_str()), hap.c_str(), (int)hap.length()});
-        }
+        for (const HapRecord& h : rg.haps) pairs.push_back(PairIndex{hap0 + h.index, ref_id});
+        for (const auto& rh : rg.read_hap_pairs) pairs.push_back(PairIndex{read0 + rh.first, hap0 + rg.haps[rh.second].index});
     }
-    for (const PairView& p : pairs) { st.pairs++; st.cells += (long long)p.query_len * p.ref_len; }
+    for (const PairIndex& p : pairs) { st.pairs++; st.cells += (long long)pool[(size_t)p.query].len * pool[(size_t)p.target].len; }
     double t1 = now_s();
     // ---- 2. GPU: one batch (flag 0x0f, no filters, maskLen = query length: StripedSmithWaterman defaults, ssw_cpp.cpp:343-346)
     std::vector<Alignment> aln;
@@ -480,13 +482,18 @@ int realign_many(const mpn_region* regions, int nregions, struct_str_arr** out)
         StripedSmithWaterman::Aligner aligner(kMatch, kMismatch, kGapOpen, kGapExtend);
         StripedSmithWaterman::Filter filter;
         // a zero-length reference makes Aligner::Align return false in the reference (ssw_cpp.cpp:330); those pairs stay cleared
-        std::vector<PairView> live;
+        std::vector<PairIndex> live;
         std::vector<size_t> where;
-        for (size_t i = 0; i < pairs.size(); ++i) if (pairs[i].ref_len > 0 && pairs[i].query_len > 0) { live.push_back(pairs[i]); where.push_back(i); }
-        std::vector<Alignment> got;
-        aligner.AlignPairs(live, filter, &got);
-        aln.assign(pairs.size(), Alignment());
-        for (size_t k = 0; k < where.size(); ++k) aln[where[k]] = std::move(got[k]);
+        bool all_live = true;
+        for (const PairIndex& p : pairs) if (pool[(size_t)p.target].len <= 0 || pool[(size_t)p.query].len <= 0) { all_live = false; break; }
+        if (all_live) aligner.AlignIndexed(pool, pairs, filter, &aln);
+        else {
+            for (size_t i = 0; i < pairs.size(); ++i) if (pool[(size_t)pairs[i].target].len > 0 && pool[(size_t)pairs[i].query].len > 0) { live.push_back(pairs[i]); where.push_back(i); }
+            std::vector<Alignment> got;
+            aligner.AlignIndexed(pool, live, filter, &got);
+            aln.clear(); aln.resize(pairs.size());
+            for (size_t k = 0; k < where.size(); ++k) aln[where[k]] = std::move(got[k]);
+        }
     }
     double t2 = now_s();
     // ---- 3. host: consume

@@ -11,6 +11,7 @@
 #include <chrono>
 #include <cstring>
 #include <functional>
+#include <memory>
 #include <unordered_map>
 
 namespace StripedSmithWaterman {
@@ -132,65 +133,82 @@ void Aligner::CleanReferenceSequence(void) { reference_.clear(); }
 bool Aligner::AlignPairs(const std::vector<PairView>& pairs, const Filter& filter, std::vector<Alignment>* out) const
 {
     if (translate_.empty() || !out) return false;
+    // every DISTINCT sequence (by address and length) becomes one pool entry -- in the realigner one haplotype meets hundreds of
+    // reads and one read meets every haplotype (realigner.cpp:351-384)
+    struct Key { const void* p; int len; bool operator==(const Key& o) const { return p == o.p && len == o.len; } };
+    struct KeyHash { size_t operator()(const Key& k) const { return std::hash<const void*>()(k.p) * 31u + (size_t)k.len; } };
+    std::unordered_map<Key, int32_t, KeyHash> where;
+    where.reserve(pairs.size());
+    std::vector<SeqView> pool;
+    auto intern = [&](const char* p, int len) -> int32_t {
+        const Key k{p ? (const void*)p : (const void*)reference_.data(), len};
+        auto it = where.find(k);
+        if (it != where.end()) return it->second;
+        const int32_t id = (int32_t)pool.size();
+        where.emplace(k, id);
+        pool.push_back(SeqView{p, len});             // text == nullptr: the stored (already translated) reference
+        return id;
+    };
+    std::vector<PairIndex> idx(pairs.size());
+    for (size_t i = 0; i < pairs.size(); ++i) idx[i] = PairIndex{intern(pairs[i].query, pairs[i].query_len), intern(pairs[i].ref, pairs[i].ref_len)};
+    return AlignIndexed(pool, idx, filter, out);
+}
+
+bool Aligner::AlignIndexed(const std::vector<SeqView>& pool, const std::vector<PairIndex>& pairs, const Filter& filter, std::vector<Alignment>* out) const
+{
+    if (translate_.empty() || !out) return false;
     static const bool timing = getenv("MPN_TIMING") != nullptr;
     auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double t_start = now();
     const size_t np = pairs.size();
-    out->assign(np, Alignment());
-    // ---- pack: every DISTINCT sequence (by address and length) is translated and uploaded once -- in the realigner one haplotype
-    //      meets hundreds of reads and one read meets every haplotype (realigner.cpp:351-384).  Empty queries keep a cleared slot.
-    struct Key { const void* p; int len; bool operator==(const Key& o) const { return p == o.p && len == o.len; } };
-    struct KeyHash { size_t operator()(const Key& k) const { return std::hash<const void*>()(k.p) * 31u + (size_t)k.len; } };
-    std::unordered_map<Key, int64_t, KeyHash> where;
-    std::vector<std::pair<const char*, int>> distinct;     // (text or nullptr = the stored reference, length)
-    std::vector<int64_t> start;                            // arena offset of each distinct sequence
-    int64_t arena_bytes = 0;
-    auto intern = [&](const char* p, int len) -> int64_t {
-        const Key k{p ? (const void*)p : (const void*)reference_.data(), len};
-        auto it = where.find(k);
-        if (it != where.end()) return it->second;
-        const int64_t at = arena_bytes;
-        where.emplace(k, at);
-        distinct.push_back({p, len}); start.push_back(at);
-        arena_bytes += len;
-        return at;
-    };
+    out->clear();
+    out->resize(np);
+    // ---- arena: the pool back to back, translated on host threads
+    std::vector<int64_t> start(pool.size() + 1, 0);
+    for (size_t d = 0; d < pool.size(); ++d) start[d + 1] = start[d] + std::max(pool[d].len, 0);
+    const int64_t arena_bytes = start[pool.size()];
+    std::unique_ptr<int8_t[]> arena_store(new int8_t[(size_t)arena_bytes + 16]);      // no zero fill: every byte is written below
+    int8_t* const arena = arena_store.get();
+    mpn::parallel_for((int64_t)pool.size(), 64, [&](int64_t d) {
+        if (pool[d].len <= 0) return;
+        if (pool[d].text == nullptr) memcpy(arena + start[d], reference_.data(), (size_t)pool[d].len);
+        else translate_into(translate_, pool[d].text, pool[d].len, arena + start[d]);
+    });
+    // ---- spans of the live pairs (an empty query makes Align return false: the slot stays cleared)
     std::vector<int64_t> rd_start, rf_start;
     std::vector<int32_t> rd_len, rf_len, mask;
     std::vector<size_t> slot;
+    rd_start.reserve(np); rf_start.reserve(np); rd_len.reserve(np); rf_len.reserve(np); mask.reserve(np); slot.reserve(np);
     int64_t qbytes = 0, tbytes = 0;
     for (size_t i = 0; i < np; ++i) {
-        const PairView& p = pairs[i];
-        if (p.query_len <= 0) continue;
-        rd_start.push_back(intern(p.query, p.query_len)); rd_len.push_back(p.query_len);
-        rf_start.push_back(intern(p.ref, p.ref_len)); rf_len.push_back(p.ref_len);
-        mask.push_back(p.query_len);                       // maskLen = query_len (ssw_cpp.cpp:346)
+        const SeqView& q = pool[(size_t)pairs[i].query]; const SeqView& t = pool[(size_t)pairs[i].target];
+        if (q.len <= 0) continue;
+        rd_start.push_back(start[(size_t)pairs[i].query]); rd_len.push_back(q.len);
+        rf_start.push_back(start[(size_t)pairs[i].target]); rf_len.push_back(std::max(t.len, 0));
+        mask.push_back(q.len);                             // maskLen = query_len (ssw_cpp.cpp:346)
         slot.push_back(i);
-        qbytes += p.query_len; tbytes += p.ref_len;
+        qbytes += q.len; tbytes += std::max(t.len, 0);
     }
     const int64_t n = (int64_t)slot.size();
     if (n == 0) return true;
-    std::vector<int8_t> arena((size_t)arena_bytes + 1);
-    mpn::parallel_for((int64_t)distinct.size(), 64, [&](int64_t d) {
-        if (distinct[d].first == nullptr) memcpy(arena.data() + start[d], reference_.data(), (size_t)distinct[d].second);
-        else translate_into(translate_, distinct[d].first, distinct[d].second, arena.data() + start[d]);
-    });
     uint8_t flag = 0;                                      // SetFlag, ssw_cpp.cpp:209-212
     if (filter.report_begin_position) flag |= 0x08;
     if (filter.report_cigar) flag |= 0x0f;
     mpn_params pr;
     pr.mat = matrix_.data(); pr.n = n_; pr.gapO = gap_open_; pr.gapE = gap_extend_; pr.score_size = 2;
     pr.flag = flag; pr.filters = filter.score_filter; pr.filterd = filter.distance_filter;
-    std::vector<mpn_result> res((size_t)n);
-    std::vector<uint32_t> cig((size_t)(n * 24 + qbytes / 4 + 4096));
+    std::unique_ptr<mpn_result[]> res(new mpn_result[(size_t)n]);
+    size_t cig_cap = (size_t)(n * 24 + qbytes / 4 + 4096);
+    std::unique_ptr<uint32_t[]> cig(new uint32_t[cig_cap]);
     int rc;
     const double t_packed = now();
     for (int attempt = 0;; ++attempt) {
         mpn::SharedEngineLock lk;
-        rc = mpn_align_batch_spans(lk.engine(), &pr, arena.data(), arena_bytes, rd_start.data(), rd_len.data(), rf_start.data(), rf_len.data(), mask.data(), n,
-                                   res.data(), cig.data(), (int64_t)cig.size());
+        rc = mpn_align_batch_spans(lk.engine(), &pr, arena, arena_bytes, rd_start.data(), rd_len.data(), rf_start.data(), rf_len.data(), mask.data(), n,
+                                   res.get(), cig.get(), (int64_t)cig_cap);
         if (rc != MPN_E_CIGAR_SPACE || attempt == 1) break;
-        cig.resize((size_t)(2 * (qbytes + tbytes) + 16 * n));          // always enough: a CIGAR has at most read + target runs
+        cig_cap = (size_t)(2 * (qbytes + tbytes) + 16 * n);             // always enough: a CIGAR has at most read + target runs
+        cig.reset(new uint32_t[cig_cap]);
     }
     if (rc != 0) {
         fprintf(stderr, "[ssw_cpp] GPU alignment failed (code %d); this library has no CPU fallback\n", rc);
@@ -204,7 +222,7 @@ bool Aligner::AlignPairs(const std::vector<PairView>& pairs, const Filter& filte
     // ---- '=' / 'X' CIGAR + mismatch count per pair (independent: host threads)
     const double t_gpu = now();
     mpn::parallel_for(n, 256, [&](int64_t k) {
-        finish_alignment(res[k], cig.data(), arena.data() + rf_start[k], arena.data() + rd_start[k], rd_len[k], &(*out)[slot[k]]);
+        finish_alignment(res[k], cig.get(), arena + rf_start[k], arena + rd_start[k], rd_len[k], &(*out)[slot[k]]);
     });
     if (timing) fprintf(stderr, "[ssw_cpp] %lld pairs: pack %.3f ms, engine %.3f ms, post-process %.3f ms\n", (long long)n, t_packed - t_start, t_gpu - t_packed, now() - t_gpu);
     return true;
