@@ -70,7 +70,8 @@ def test_struct_str_arr_layout_and_cpp_front_end_symbols(built, tmp_path):
     cpp = tmp_path / "use.cpp"
     cpp.write_text('#include "ssw_cpp.h"\nint probe(){ StripedSmithWaterman::Aligner a(4, 6, 8, 2); StripedSmithWaterman::Filter f; StripedSmithWaterman::Alignment al;'
                    ' std::vector<StripedSmithWaterman::PairView> pv; std::vector<StripedSmithWaterman::Alignment> out; a.SetReferenceSequence("ACGT", 4);'
-                   ' return (int)a.AlignPairs(pv, f, &out) + (int)sizeof(al); }\n')
+                   ' std::vector<StripedSmithWaterman::SeqView> pool; std::vector<StripedSmithWaterman::PairIndex> pi;'
+                   ' return (int)a.AlignPairs(pv, f, &out) + (int)a.AlignIndexed(pool, pi, f, &out) + (int)sizeof(al); }\n')
     so = tmp_path / "use.so"
     subprocess.run(["g++", "-std=c++17", "-shared", "-fPIC", "-I", os.path.join(ROOT, "include"), "-o", str(so), str(cpp), built[0], "-Wl,-z,defs",
                     "-Wl,-rpath," + PKG], check=True)

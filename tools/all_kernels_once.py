@@ -1,5 +1,5 @@
-"""Small mixed workload for compute-sanitizer (memcheck / racecheck): every kernel of the engine runs at least once.
-    compute-sanitizer --tool memcheck python tools/sanitize_small.py"""
+"""Small mixed workload in which every kernel of the engine runs at least once (short / long / clamped reads, all traceback kernels,
+one realigner region): a quick target for a debugger or a profiler capture.  python tools/all_kernels_once.py"""
 import importlib, os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -15,4 +15,4 @@ for b in (w.config2(300, seed=3), w.fuzz_pairs(120, 5, flag=1), w.fuzz_pairs(80,
     assert (rec["status"] == 0).all()
 rg = w.config3(1, seed=3, max_reads=60, max_haps=4)[0]
 R.realign_reads(rg)
-print("sanitize_small: ran", n, "pairs + 1 region")
+print("all_kernels_once: ran", n, "pairs + 1 region")
