@@ -44,6 +44,17 @@ typedef struct {
 } mpn_region;
 int mpn_realign_regions(const mpn_region* regions, int nregions, struct_str_arr** out);
 
+/*
+ * NEW: the same with flat buffers, for bindings where building arrays of C strings is the bottleneck (Python: one join instead of 10^5
+ * c_char_p objects).  `text` holds NUL-terminated strings back to back, per region: reference, haplotypes (white-space separated, one
+ * string), then its read sequences, then its read CIGARs.  region_reads[r] = number of reads; region_geom[3*r ..] = ref_start, ref_prefix,
+ * ref_suffix; positions = current read positions of all regions back to back.  Results: out_positions (same layout as positions) and
+ * *out_cigars = one malloc'ed buffer of NUL-terminated CIGAR strings in read order (release with mpn_realign_free).
+ */
+int mpn_realign_regions_packed(const char* text, long long text_bytes, int nregions, const int* region_reads, const int* region_geom,
+                               const int* positions, int* out_positions, char** out_cigars, long long* out_cigars_bytes);
+void mpn_realign_free(void* p);
+
 /* counters of the last realign_reads / mpn_realign_regions call of this thread's process: Smith-Waterman pairs submitted,
  * forward-matrix cells, and seconds spent in {host k-mer pass, GPU batch (copies included), host CIGAR algebra} */
 int mpn_realign_last_stats(long long* pairs, long long* cells, double* seconds3);

@@ -566,6 +566,57 @@ extern "C" int mpn_realign_regions(const mpn_region* regions, int nregions, stru
     return realign_many(regions, nregions, out);
 }
 
+extern "C" int mpn_realign_regions_packed(const char* text, long long text_bytes, int nregions, const int* region_reads, const int* region_geom,
+                                          const int* positions, int* out_positions, char** out_cigars, long long* out_cigars_bytes)
+{
+    if (nregions < 0 || !out_cigars || !out_cigars_bytes || (nregions > 0 && (!text || !region_reads || !region_geom || !positions || !out_positions))) return -1;
+    // unpack: pointers into the caller's text, one mpn_region per region
+    std::vector<mpn_region> regs((size_t)nregions);
+    std::vector<char*> ptrs;
+    size_t total_reads = 0;
+    for (int r = 0; r < nregions; ++r) { if (region_reads[r] < 0 || region_reads[r] > 1000) return -1; total_reads += (size_t)region_reads[r]; }
+    ptrs.reserve(2 * total_reads);
+    const char* p = text; const char* const end = text + text_bytes;
+    auto next = [&]() -> char* { if (p >= end) return nullptr; char* s0 = const_cast<char*>(p); p += strlen(p) + 1; return s0; };
+    size_t rd = 0;
+    for (int r = 0; r < nregions; ++r) {
+        mpn_region& g = regs[(size_t)r];
+        g.reference = next(); g.haplotypes = next();
+        g.read_size = region_reads[r];
+        const size_t first = ptrs.size();
+        for (int k = 0; k < 2 * g.read_size; ++k) ptrs.push_back(next());
+        if (!g.reference || !g.haplotypes || (g.read_size > 0 && !ptrs.back())) return -1;
+        g.positions = const_cast<int*>(positions) + rd;
+        g.ref_start = region_geom[3 * r]; g.ref_prefix = region_geom[3 * r + 1]; g.ref_suffix = region_geom[3 * r + 2];
+        g.seqs = nullptr; g.cigars = nullptr;
+        rd += (size_t)g.read_size;
+        (void)first;
+    }
+    {   // the pointer array is complete (no more reallocation): hook the regions up
+        size_t at = 0;
+        for (int r = 0; r < nregions; ++r) { regs[(size_t)r].seqs = ptrs.data() + at; regs[(size_t)r].cigars = ptrs.data() + at + regs[(size_t)r].read_size; at += 2 * (size_t)regs[(size_t)r].read_size; }
+    }
+    std::vector<struct_str_arr*> res((size_t)nregions, nullptr);
+    const int rc = realign_many(regs.data(), nregions, res.data());
+    if (rc != 0) return rc;
+    size_t bytes = 0;
+    for (int r = 0; r < nregions; ++r) for (int i = 0; i < regs[(size_t)r].read_size; ++i) bytes += strlen(res[(size_t)r]->cigar_string[i]) + 1;
+    char* blob = (char*)malloc(bytes + 1);
+    char* w = blob; size_t k = 0;
+    for (int r = 0; r < nregions; ++r) {
+        for (int i = 0; i < regs[(size_t)r].read_size; ++i) {
+            const size_t n = strlen(res[(size_t)r]->cigar_string[i]) + 1;
+            memcpy(w, res[(size_t)r]->cigar_string[i], n); w += n;
+            out_positions[k++] = res[(size_t)r]->position[i];
+        }
+        free_memory(res[(size_t)r], regs[(size_t)r].read_size);
+    }
+    *out_cigars = blob; *out_cigars_bytes = (long long)bytes;
+    return 0;
+}
+
+extern "C" void mpn_realign_free(void* p) { free(p); }
+
 extern "C" void free_memory(struct_str_arr* pointer, int size)
 {
     if (!pointer) return;

@@ -37,8 +37,10 @@ def test_batched_regions_equal_per_region_calls(hostlib):
     one = [R.realign_reads(rg, hostlib) for rg in regions]
     many = R.realign_regions(regions, hostlib)
     assert one == many
+    assert R.realign_regions_packed(regions, hostlib) == many        # flat-buffer entry point
     st = R.last_stats(hostlib)
     assert st["pairs"] > 0 and st["cells"] > 0
+    assert R.realign_regions_packed([], hostlib) == []
     assert R.realign_regions([], hostlib) == []
 
 

@@ -20,11 +20,12 @@ t_single = time.perf_counter() - t0
 t0 = time.perf_counter(); many = R.realign_regions(regions); t_cold = time.perf_counter() - t0        # first big batch: device pool + pinned staging grow
 t0 = time.perf_counter(); many = R.realign_regions(regions); t_many = time.perf_counter() - t0
 st = R.last_stats()
-assert many == single
+t0 = time.perf_counter(); packed = R.realign_regions_packed(regions); t_packed = time.perf_counter() - t0
+assert many == single and packed == many
 lat.sort()
 out = {"regions": n, "reads": reads, "ssw_pairs": st["pairs"], "ssw_cells": st["cells"],
        "per_region_ms": {"p50": 1e3 * lat[len(lat) // 2], "p95": 1e3 * lat[int(len(lat) * 0.95)], "sum_s": t_single},
-       "batched_s": t_many, "batched_first_call_s": t_cold, "batched_split_s": {k: st[k] for k in ("fast_pass_s", "gpu_s", "compose_s")},
+       "batched_s": t_many, "batched_first_call_s": t_cold, "batched_packed_s": t_packed, "batched_packed_reads_per_s": reads / t_packed, "batched_split_s": {k: st[k] for k in ("fast_pass_s", "gpu_s", "compose_s")},
        "batched_gcups_ssw_only": st["cells"] / max(st["gpu_s"], 1e-9) / 1e9, "batched_reads_per_s": reads / t_many}
 ref = os.path.join(ROOT, "oracle", "_ref", "realigner_ref")
 if os.path.exists(ref):
