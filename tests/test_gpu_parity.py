@@ -257,3 +257,16 @@ def test_large_alphabet_goes_through_the_int32_kernels(eng):
         r, c = oracle_table(b)
         bad = diff(g, gc, r, c)
         assert len(bad) == 0, (flag, bad[:5], g[bad[:1]], r[bad[:1]])
+
+
+@pytest.mark.parametrize("npairs", [6, 600])
+def test_long_reads_with_n_bases(eng, npairs):
+    """reads beyond the short-read strips that contain N (code 4): the packed multi-strip kernel flags them and the int32 kernel
+    redoes them; with 6 pairs the multi-warp form of the long kernel is in use, with 600 the one-warp-per-pair form"""
+    b = w.make_pairs(npairs, (1400, 3200) if npairs < 100 else (1300, 1700), 1.2, err=0.05, seed=77 + npairs, flag=1, chunk=64, n_frac=0.004)
+    assert int((b.reads == 4).sum()) > 0
+    cap = 2048
+    g, gc, _, _ = gpu_table(eng, b, cap=cap)
+    r, c = oracle_table(b, cap=cap, threads=os.cpu_count() or 8)
+    bad = diff(g, gc, r, c)
+    assert len(bad) == 0, (bad[:5], g[bad[:2]], r[bad[:2]])
