@@ -75,6 +75,9 @@ sw_long16_kernel(const SwTask* __restrict__ tasks, int ntasks, int* __restrict__
     __shared__ int sh_progress[NW];                 // NWP > 1: per warp, strip << 16 | 32-column blocks whose boundary words are flushed
     __shared__ unsigned long long sh_key[NW];
     __shared__ int sh_row[NW], sh_wide[NW];
+    __shared__ uint32_t smatrow[8];                 // matrix rows by target code (run-time index: shared memory, not the parameter struct)
+    if (threadIdx.x < 8) smatrow[threadIdx.x] = sc.matrow[threadIdx.x];
+    __syncthreads();
     const int tid = threadIdx.x, t = tid & 31, wib = tid >> 5;
     const int wip = wib % NWP, pib = wib / NWP;     // warp inside the pair, pair inside the block
     const long long wslot = NWP == 1 ? (long long)blockIdx.x * NW + wib : (long long)blockIdx.x * PPB + pib;
@@ -175,7 +178,7 @@ sw_long16_kernel(const SwTask* __restrict__ tasks, int ntasks, int* __restrict__
             uint32_t tnext = 0, anext = LBIAS2, bnext = LBIAS2;
             wait_for(3);                            // columns 0 .. 31 are flushed at the end of the producer's block 2
             if (t < rf_len) {
-                tnext = sc.matrow[seq[tk.rf_base + (int64_t)tdir * t] & 7];
+                tnext = smatrow[seq[tk.rf_base + (int64_t)tdir * t] & 7];
                 if (!first) { anext = NWP == 1 ? bA[t] : __ldcg(bA + t); bnext = NWP == 1 ? bB[t] : __ldcg(bB + t); }
             }
             for (int s0 = 0; s0 < nsteps; s0 += G) {
@@ -191,7 +194,7 @@ sw_long16_kernel(const SwTask* __restrict__ tasks, int ntasks, int* __restrict__
                     tnext = 0; anext = LBIAS2; bnext = LBIAS2;
                     if (s0 + G < rf_len) wait_for(s0 / G + 4);      // columns of the next chunk: flushed at the end of the producer's block s0/G + 3
                     if (idx < rf_len) {
-                        tnext = sc.matrow[seq[tk.rf_base + (int64_t)tdir * idx] & 7];
+                        tnext = smatrow[seq[tk.rf_base + (int64_t)tdir * idx] & 7];
                         if (!first) { anext = NWP == 1 ? bA[idx] : __ldcg(bA + idx); bnext = NWP == 1 ? bB[idx] : __ldcg(bB + idx); }
                     }
                 }

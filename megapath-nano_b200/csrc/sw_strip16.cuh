@@ -56,6 +56,11 @@ sw_strip16_kernel(const SwTask* __restrict__ tasks, int ntasks, int* __restrict_
     extern __shared__ uint4 snap[];               // [2 halves][KRQ][STRIP_BLOCK]: H column of a stage at its last improvement
     uint32_t* const crow = reinterpret_cast<uint32_t*>(snap + 2 * KRQ * STRIP_BLOCK);   // [G][STRIP_BLOCK]: column records of the last G steps
 
+    // the 8 matrix rows are looked up by a run-time target code: shared memory (one LDS) instead of the by-value parameter struct
+    // (which ptxas can only index with a chain of predicated constant loads)
+    __shared__ uint32_t smatrow[8];
+    if (threadIdx.x < 8) smatrow[threadIdx.x] = sc.matrow[threadIdx.x];
+    __syncthreads();
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int t = lane % G;                       // thread index inside the group
@@ -176,7 +181,7 @@ sw_strip16_kernel(const SwTask* __restrict__ tasks, int ntasks, int* __restrict_
                 {   // matrix rows of target chunk 0
                     const int idx = t;
                     uint32_t mr = 0;
-                    if (idx < rf_len) mr = sc.matrow[seq[rf_base + (int64_t)tdir * idx] & 7];
+                    if (idx < rf_len) mr = smatrow[seq[rf_base + (int64_t)tdir * idx] & 7];
                     tnext = mr;
                 }
             }
@@ -188,7 +193,7 @@ sw_strip16_kernel(const SwTask* __restrict__ tasks, int ntasks, int* __restrict_
         {
             const int idx = s + G + t;
             uint32_t mr = 0;
-            if (idx < rf_len) mr = sc.matrow[seq[rf_base + (int64_t)tdir * idx] & 7];
+            if (idx < rf_len) mr = smatrow[seq[rf_base + (int64_t)tdir * idx] & 7];
             tnext = mr;
         }
 
