@@ -81,4 +81,18 @@ __device__ __forceinline__ uint32_t max2_track(uint32_t a, uint32_t b, bool& a_g
 __device__ __forceinline__ uint32_t max3(uint32_t a, uint32_t b, uint32_t c) { return __vimax3_s16x2(a, b, c); }             // VIMNMX3.S16x2
 __device__ __forceinline__ uint32_t addmax_relu(uint32_t a, uint32_t b, uint32_t c) { return __viaddmax_s16x2_relu(a, b, c); } // VIADDMNMX.S16x2.RELU
 
+// up to eight consecutive arena bytes starting at p (bytes beyond `left` are zero): two aligned 64-bit loads + a funnel shift.
+// The sequence arena starts 256-byte aligned and is padded by 16 bytes (engine.cu), so the aligned words around any base are readable.
+__device__ __forceinline__ unsigned long long load8_aligned(const int8_t* __restrict__ p, int left)
+{
+    if (left <= 0) return 0ull;
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const unsigned long long* w = reinterpret_cast<const unsigned long long*>(a & ~(uintptr_t)7);
+    const unsigned sh = (unsigned)(a & 7u) * 8u;
+    const unsigned long long lo = w[0], hi = w[1];
+    unsigned long long v = sh ? ((lo >> sh) | (hi << (64u - sh))) : lo;
+    if (left < 8) v &= (1ull << (8 * left)) - 1ull;
+    return v;
+}
+
 }  // namespace mpn

@@ -159,20 +159,43 @@ sw_strip16_kernel(const SwTask* __restrict__ tasks, int ntasks, int* __restrict_
                 dead = CAP - rd_len;
                 wide = 0;
                 // selectors: low half = row (2t)*KR + j, high half = row (2t+1)*KR + j, both minus the dead rows on top
+                const int r0 = 2 * t * KR - dead;                                // this thread's first row; it owns 2*KR consecutive rows
+                if (r0 >= 0 && rd_len <= CAP) {
+                    // common case, no dead row in this thread: the 2*KR read bases are one contiguous span -> a few aligned 64-bit loads
+                    // instead of 2*KR byte loads.  Forward passes walk the read upwards (span starts at row r0), reverse passes downwards
+                    // (span starts at the LAST row of the thread; row k sits at byte 2*KR-1-k).
+                    constexpr int NB = 2 * KR, NWORD = (NB + 7) / 8;
+                    const int8_t* span = REV ? seq + tk.rd_base - (int64_t)(r0 + NB - 1) : seq + tk.rd_base + r0;
+                    unsigned long long wq[NWORD];
 #pragma unroll
-                for (int j = 0; j < KR; ++j) {
-                    const int r_lo = 2 * t * KR + j - dead, r_hi = r_lo + KR;
-                    uint32_t n_lo = 0x88u, n_hi = 0xccu;                      // dead row: sign bytes only -> score 0 or -1
-                    if (r_lo >= 0) {
-                        const int q = seq[tk.rd_base + (int64_t)tdir * r_lo];
-                        if ((unsigned)q < 4u) n_lo = (uint32_t)q | ((uint32_t)(q | 8) << 4); else wide = 1;
+                    for (int q = 0; q < NWORD; ++q) wq[q] = load8_aligned(span + 8 * q, NB - 8 * q);
+                    unsigned long long bad = 0;
+#pragma unroll
+                    for (int q = 0; q < NWORD; ++q) bad |= wq[q] & 0xfcfcfcfcfcfcfcfcull;          // any code >= 4 (N): 32-bit kernel
+                    if (bad != 0ull) wide = 1;
+#pragma unroll
+                    for (int j = 0; j < KR; ++j) {
+                        const int b_lo = REV ? NB - 1 - j : j, b_hi = REV ? NB - 1 - (j + KR) : j + KR;
+                        const uint32_t q_lo = (uint32_t)(wq[b_lo >> 3] >> (8 * (b_lo & 7))) & 3u, q_hi = (uint32_t)(wq[b_hi >> 3] >> (8 * (b_hi & 7))) & 3u;
+                        sel[j] = (q_lo * 0x11u + 0x80u) | ((q_hi * 0x11u + 0xc4u) << 8);
+                        H[j] = 0; E[j] = 0;
                     }
-                    if (r_hi >= 0) {
-                        const int q = seq[tk.rd_base + (int64_t)tdir * r_hi];
-                        if ((unsigned)q < 4u) n_hi = (uint32_t)(q | 4) | ((uint32_t)(q | 12) << 4); else wide = 1;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < KR; ++j) {
+                        const int r_lo = 2 * t * KR + j - dead, r_hi = r_lo + KR;
+                        uint32_t n_lo = 0x88u, n_hi = 0xccu;                      // dead row: sign bytes only -> score 0 or -1
+                        if (r_lo >= 0) {
+                            const int q = seq[tk.rd_base + (int64_t)tdir * r_lo];
+                            if ((unsigned)q < 4u) n_lo = (uint32_t)q | ((uint32_t)(q | 8) << 4); else wide = 1;
+                        }
+                        if (r_hi >= 0) {
+                            const int q = seq[tk.rd_base + (int64_t)tdir * r_hi];
+                            if ((unsigned)q < 4u) n_hi = (uint32_t)(q | 4) | ((uint32_t)(q | 12) << 4); else wide = 1;
+                        }
+                        sel[j] = n_lo | (n_hi << 8);
+                        H[j] = 0; E[j] = 0;
                     }
-                    sel[j] = n_lo | (n_hi << 8);
-                    H[j] = 0; E[j] = 0;
                 }
                 Ftop = Hdtop = cmin = a = b = best = 0; cvlo = cvhi = 0;
                 s = 0;
