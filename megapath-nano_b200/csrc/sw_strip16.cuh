@@ -89,9 +89,17 @@ sw_strip16_kernel(const SwTask* __restrict__ tasks, int ntasks, int* __restrict_
         if (REV) {   // early end of a reverse pass (ssw.c:281 / :483): once some stage has seen the terminating score in column c, every
             // stage has passed column c after at most 2G-1 further steps; the usual first-column / first-row selection then applies.
             const uint32_t x = best ^ stop2;
-            const bool hit = stop2 != 0u && ((x & 0xffffu) == 0u || (x >> 16) == 0u);
-            const unsigned hits = __ballot_sync(0xffffffffu, hit) & gmask;
-            if (hits != 0u) nsteps = min(nsteps, s + 2 * G);
+            const bool hit_lo = stop2 != 0u && (x & 0xffffu) == 0u, hit_hi = stop2 != 0u && (x >> 16) == 0u;
+            const unsigned hits = __ballot_sync(0xffffffffu, hit_lo || hit_hi) & gmask;
+            if (hits != 0u) {
+                // the terminating column is the smallest column in which a stage reached the score; every stage is past it at step col + 2G - 1
+                int col = 0x3fffffff;
+                if (hit_lo) col = (int)cvlo - 2 * t;
+                if (hit_hi) col = min(col, (int)cvhi - 2 * t - 1);
+#pragma unroll
+                for (int off = G / 2; off >= 1; off >>= 1) col = min(col, __shfl_xor_sync(gmask, col, off));
+                nsteps = min(nsteps, col + 2 * G);
+            }
         }
         if (active && s >= nsteps) {
             if (nsteps > 0) {
