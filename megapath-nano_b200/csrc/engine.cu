@@ -524,7 +524,7 @@ static void launch_strips(mpn_batch* b, const SwTask* tasks, bool forward, SwEnd
             e->wide_pairs += forward ? bl.count : 0;
         } else if (bl.cfg == WIDE_BIN) {
             launch_wide32_impl(tasks + bl.first, (int)bl.count, counter, b->seq.as<int8_t>(), b->dmat.as<int8_t>(), b->p.n, b->fin.gapO, b->fin.gapE,
-                               forward ? b->colrec.as<uint32_t>() : nullptr, ends, b->wide_boundary.as<int>(), b->wide_stride, b->wide_blocks, 0, st);
+                               forward ? b->colrec.as<uint32_t>() : nullptr, ends, b->wide_boundary.as<int>(), b->wide_stride, b->wide_blocks, 0, b->max_rd <= 512, st);
             e->wide_pairs += forward ? bl.count : 0;
         } else {
             const StripCfg& c = g_strips[bl.cfg];
@@ -562,7 +562,7 @@ extern "C" int mpn_batch_run(mpn_batch* b)
     // pairs the packed kernel refused (read code >= 4) are re-run in the 32-bit kernel before anything reads their ends
     launch_wide32_impl(b->tasks_fwd.as<SwTask>(), (int)n, reinterpret_cast<int*>(b->counters.as<unsigned long long>() + 100),
                        b->seq.as<int8_t>(), b->dmat.as<int8_t>(), b->p.n, b->fin.gapO, b->fin.gapE, b->colrec.as<uint32_t>(), b->ends_fwd.as<SwEnds>(),
-                       b->wide_boundary.as<int>(), b->wide_stride, b->wide_blocks, 1, st);
+                       b->wide_boundary.as<int>(), b->wide_stride, b->wide_blocks, 1, b->max_rd <= 512, st);
     CK(cudaGetLastError());
     e->launches++;
     if (e->profile) { CK(cudaEventRecord(e->ev[1], st)); e->ev_valid = 2; }
@@ -581,7 +581,7 @@ extern "C" int mpn_batch_run(mpn_batch* b)
         launch_strips(b, b->tasks_rev.as<SwTask>(), false, b->ends_rev.as<SwEnds>(), 256);
         launch_wide32_impl(b->tasks_rev.as<SwTask>(), (int)n, reinterpret_cast<int*>(b->counters.as<unsigned long long>() + 101),
                            b->seq.as<int8_t>(), b->dmat.as<int8_t>(), b->p.n, b->fin.gapO, b->fin.gapE, nullptr, b->ends_rev.as<SwEnds>(),
-                           b->wide_boundary.as<int>(), b->wide_stride, b->wide_blocks, 1, st);
+                           b->wide_boundary.as<int>(), b->wide_stride, b->wide_blocks, 1, b->max_rd <= 512, st);
         CK(cudaGetLastError());
         e->launches++;
         if (e->profile) { CK(cudaEventRecord(e->ev[3], st)); e->ev_valid = 4; }

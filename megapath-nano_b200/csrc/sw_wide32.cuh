@@ -2,7 +2,7 @@
 // ONT-scale pairs whose scores reach the int16 clamp of sw_sse2_word (ssw.c:425 `_mm_adds_epi16`, result fields are
 // uint16_t), reads longer than the largest packed strip, reads containing codes >= 4 (N), and alphabets with n > 8.
 //
-// The read is cut into strips of 32 lanes x WIDE_KR rows; inside a strip lane L runs WIDE_KR rows of column s-L at step s
+// The read is cut into strips of 32 lanes x WIDE_KR rows (16, or 8 when all reads of the batch are short); inside a strip lane L runs WIDE_KR rows of column s-L at step s
 // (anti-diagonal wavefront over the lanes).  Between strips the bottom row (H, F) and the running column maximum live in a
 // per-warp global boundary buffer, streamed through registers 32 columns at a time.  Scores are int32 with the reference's
 // clamp applied per cell: h = min(Hdiag + s, 32767) is one VIADDMNMX.  Substitution scores come from a copy of the matrix
@@ -15,15 +15,17 @@
 
 namespace mpn {
 
-constexpr int WIDE_KR = 16;
+constexpr int WIDE_KR_LONG = 16;                 // rows per lane: 512-row strips for long reads ...
+constexpr int WIDE_KR_SHORT = 8;                 // ... 256-row strips when every read of the batch is short (fewer dead lanes)
 constexpr int WIDE_BLOCK = 128;
-constexpr int WIDE_CAP = 32 * WIDE_KR;
 
+template <int WIDE_KR>
 __global__ void __launch_bounds__(WIDE_BLOCK, 3)
 sw_wide32_kernel(const SwTask* __restrict__ tasks, int ntasks, int* __restrict__ counter, const int8_t* __restrict__ seq,
                  const int8_t* __restrict__ mat, int n, int gapO, int gapE, uint32_t* __restrict__ colrec, SwEnds* __restrict__ out,
                  int* __restrict__ boundary, long long boundary_stride, int only_flagged)
 {
+    constexpr int WIDE_CAP = 32 * WIDE_KR;
     extern __shared__ int wsm[];
     const int n1 = n + 1;
     int* smat = wsm;                                              // (n+1) x (n+1), last row / column zero
@@ -156,14 +158,15 @@ sw_wide32_kernel(const SwTask* __restrict__ tasks, int ntasks, int* __restrict__
     }
 }
 
-inline size_t wide32_smem_bytes(int n) { return sizeof(int) * (size_t)((((n + 1) * (n + 1) + 31) & ~31) + WIDE_KR * WIDE_BLOCK); }
+inline size_t wide32_smem_bytes(int n, int kr) { return sizeof(int) * (size_t)((((n + 1) * (n + 1) + 31) & ~31) + kr * WIDE_BLOCK); }
 
 // host launchers.  `boundary` must hold 2 * stride ints per warp of the grid.
 inline void launch_wide32_impl(const SwTask* tasks, int ntasks, int* counter, const int8_t* seq, const int8_t* mat, int n, int gapO, int gapE,
-                               uint32_t* colrec, SwEnds* ends, int* boundary, long long stride, int blocks, int only_flagged, cudaStream_t st)
+                               uint32_t* colrec, SwEnds* ends, int* boundary, long long stride, int blocks, int only_flagged, bool short_reads, cudaStream_t st)
 {
     if (ntasks <= 0) return;
-    sw_wide32_kernel<<<blocks, WIDE_BLOCK, wide32_smem_bytes(n), st>>>(tasks, ntasks, counter, seq, mat, n, gapO, gapE, colrec, ends, boundary, stride, only_flagged);
+    if (short_reads) sw_wide32_kernel<WIDE_KR_SHORT><<<blocks, WIDE_BLOCK, wide32_smem_bytes(n, WIDE_KR_SHORT), st>>>(tasks, ntasks, counter, seq, mat, n, gapO, gapE, colrec, ends, boundary, stride, only_flagged);
+    else sw_wide32_kernel<WIDE_KR_LONG><<<blocks, WIDE_BLOCK, wide32_smem_bytes(n, WIDE_KR_LONG), st>>>(tasks, ntasks, counter, seq, mat, n, gapO, gapE, colrec, ends, boundary, stride, only_flagged);
 }
 
 }  // namespace mpn
