@@ -315,6 +315,13 @@ static mpn_batch* upload_impl(mpn_engine* e, int slot_id, const mpn_params* p, c
         for (int q = 0; q < 4 && q < n; ++q) w |= (uint32_t)(uint8_t)p->mat[t * n + q] << (8 * q);
         b->sc16.matrow[t] = w;
     }
+    if (n == 5) {       // N column constant over the target codes (both matrix builders of the reference: ssw_cpp.cpp:23-48, pyssw.py:61-79)
+        bool same = true;
+        for (int t = 1; t < 5; ++t) same = same && p->mat[t * 5 + 4] == p->mat[4];
+        const uint32_t c = (uint32_t)(uint16_t)(int16_t)p->mat[4];
+        b->sc16.ncol2 = c | (c << 16);
+        b->sc16.ncol_ok = same ? 1u : 0u;
+    }
     const uint32_t go = (uint32_t)(uint16_t)(int16_t)(-(p->gapO & 0xff)), ge = (uint32_t)(uint16_t)(int16_t)(-(p->gapE & 0xff));
     b->sc16.mgapO2 = go | (go << 16);
     b->sc16.mgapE2 = ge | (ge << 16);

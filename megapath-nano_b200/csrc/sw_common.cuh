@@ -33,6 +33,8 @@ struct Score16 {
     uint32_t matrow[8];
     uint32_t mgapO2;   // (-gapO) in both 16-bit halves
     uint32_t mgapE2;   // (-gapE) in both 16-bit halves
+    uint32_t ncol2;    // score of read code 4 (N) against every target code, in both halves -- valid if ncol_ok
+    uint32_t ncol_ok;  // n == 5 and mat[t][4] is the same for all t: reads containing N can stay in the short-read packed kernel
 };
 
 // ---- packed s16x2 helpers.  All single SASS instructions on sm_100a (profiles/r01_ubench_cell_pipes.md):

@@ -24,6 +24,7 @@
 #pragma once
 #include "sw_common.cuh"
 #include <cstdio>
+#include <type_traits>
 
 namespace mpn {
 
@@ -37,9 +38,10 @@ constexpr int STRIP_UNROLL = MPN_STRIP_UNROLL;
 #define MPN_STRIP_MINB 4
 #endif
 
-// shared memory: H-column snapshots [2 halves][ceil(KR/4)][STRIP_BLOCK] uint4, then the column-record staging [G][STRIP_BLOCK] words
+// shared memory: H-column snapshots [2 halves][ceil(KR/4)][STRIP_BLOCK] uint4, the column-record staging [G][STRIP_BLOCK] words, and the
+// per-row score fix-up selectors [KR][STRIP_BLOCK] used while a warp holds a read with N (see the N mode below)
 template <int KR, int G>
-__host__ __device__ constexpr size_t strip16_smem_bytes() { return (size_t)2 * ((KR + 3) / 4) * STRIP_BLOCK * sizeof(uint4) + (size_t)G * STRIP_BLOCK * sizeof(uint32_t); }
+__host__ __device__ constexpr size_t strip16_smem_bytes() { return (size_t)2 * ((KR + 3) / 4) * STRIP_BLOCK * sizeof(uint4) + (size_t)(G + KR) * STRIP_BLOCK * sizeof(uint32_t); }
 
 // REV = false: forward passes (column records written, no early end).  REV = true: reverse passes (ssw.c:820-832): no column records, the
 // pass ends once the terminating score has been seen, and only a stage that REACHES that score can be the winner, so the H-column
@@ -55,6 +57,11 @@ sw_strip16_kernel(const SwTask* __restrict__ tasks, int ntasks, int* __restrict_
     constexpr int CAP = 2 * G * KR;               // rows covered by one strip
     extern __shared__ uint4 snap[];               // [2 halves][KRQ][STRIP_BLOCK]: H column of a stage at its last improvement
     uint32_t* const crow = reinterpret_cast<uint32_t*>(snap + 2 * KRQ * STRIP_BLOCK);   // [G][STRIP_BLOCK]: column records of the last G steps
+    // N mode.  The score PRMT picks mat[t][q] out of the 4-byte matrix rows of the two target bases: there is no slot for a fifth read
+    // code.  When the N column of the matrix is one constant c (sc.ncol_ok), rows holding an N get a second PRMT that replaces their
+    // half of the looked-up score by c; its selector sits in shared memory (identity for ordinary rows).  Only warps that currently hold
+    // such a read run this variant of the step (warp-uniform switch), everybody else runs the plain one.
+    uint32_t* const nfix = crow + G * STRIP_BLOCK;                                        // [KR][STRIP_BLOCK]
 
     // the 8 matrix rows are looked up by a run-time target code: shared memory (one LDS) instead of the by-value parameter struct
     // (which ptxas can only index with a chain of predicated constant loads)
@@ -80,6 +87,7 @@ sw_strip16_kernel(const SwTask* __restrict__ tasks, int ntasks, int* __restrict_
     uint32_t stop2 = 0;                           // reverse passes: score at which the pass may end, in both halves (0: never)
     int64_t rf_base = 0, cm_off = -1;
     bool active = true;                           // group still has (or may fetch) a task
+    bool has_n = false, nfix_stale = true;        // this thread's rows hold an N / its nfix entries are not the identity (or never written)
 
 #pragma unroll
     for (int j = 0; j < KR; ++j) { H[j] = 0; E[j] = 0; sel[j] = 0x8888u | 0x4400u; }
@@ -154,7 +162,7 @@ sw_strip16_kernel(const SwTask* __restrict__ tasks, int ntasks, int* __restrict_
             if (t == 0) ti = atomicAdd(counter, 1);
             ti = __shfl_sync(gmask, ti, lane - t);
             if (ti >= ntasks) {
-                active = false;
+                active = false; has_n = false;
                 rf_len = 0; nsteps = 0; cm_off = -1; stop2 = 0;
 #pragma unroll
                 for (int j = 0; j < KR; ++j) { H[j] = 0; E[j] = 0; sel[j] = 0x8888u | 0x4400u; }
@@ -180,30 +188,45 @@ sw_strip16_kernel(const SwTask* __restrict__ tasks, int ntasks, int* __restrict_
                     unsigned long long bad = 0;
 #pragma unroll
                     for (int q = 0; q < NWORD; ++q) bad |= wq[q] & 0xfcfcfcfcfcfcfcfcull;          // any code >= 4 (N): 32-bit kernel
-                    if (bad != 0ull) wide = 1;
+                    has_n = bad != 0ull && sc.ncol_ok != 0u;
+                    if (bad != 0ull && !has_n) wide = 1;
 #pragma unroll
                     for (int j = 0; j < KR; ++j) {
                         const int b_lo = REV ? NB - 1 - j : j, b_hi = REV ? NB - 1 - (j + KR) : j + KR;
-                        const uint32_t q_lo = (uint32_t)(wq[b_lo >> 3] >> (8 * (b_lo & 7))) & 3u, q_hi = (uint32_t)(wq[b_hi >> 3] >> (8 * (b_hi & 7))) & 3u;
+                        const uint32_t c_lo = (uint32_t)(wq[b_lo >> 3] >> (8 * (b_lo & 7))) & 0xffu, c_hi = (uint32_t)(wq[b_hi >> 3] >> (8 * (b_hi & 7))) & 0xffu;
+                        const uint32_t q_lo = c_lo & 3u, q_hi = c_hi & 3u;
                         sel[j] = (q_lo * 0x11u + 0x80u) | ((q_hi * 0x11u + 0xc4u) << 8);
                         H[j] = 0; E[j] = 0;
+                        if (has_n || nfix_stale) {
+                            if (c_lo > 4u || c_hi > 4u) wide = 1;                       // codes beyond N: not a DNA read
+                            nfix[j * STRIP_BLOCK + tid] = ((has_n && c_lo == 4u) ? 0x54u : 0x10u) | (((has_n && c_hi == 4u) ? 0x76u : 0x32u) << 8);
+                        }
                     }
+                    nfix_stale = has_n;
                 } else {
+                    has_n = false;
 #pragma unroll
                     for (int j = 0; j < KR; ++j) {
                         const int r_lo = 2 * t * KR + j - dead, r_hi = r_lo + KR;
                         uint32_t n_lo = 0x88u, n_hi = 0xccu;                      // dead row: sign bytes only -> score 0 or -1
+                        uint32_t fix = 0x3210u;
                         if (r_lo >= 0) {
                             const int q = seq[tk.rd_base + (int64_t)tdir * r_lo];
-                            if ((unsigned)q < 4u) n_lo = (uint32_t)q | ((uint32_t)(q | 8) << 4); else wide = 1;
+                            if ((unsigned)q < 4u) n_lo = (uint32_t)q | ((uint32_t)(q | 8) << 4);
+                            else if (q == 4 && sc.ncol_ok != 0u) { fix = (fix & 0xff00u) | 0x54u; has_n = true; }
+                            else wide = 1;
                         }
                         if (r_hi >= 0) {
                             const int q = seq[tk.rd_base + (int64_t)tdir * r_hi];
-                            if ((unsigned)q < 4u) n_hi = (uint32_t)(q | 4) | ((uint32_t)(q | 12) << 4); else wide = 1;
+                            if ((unsigned)q < 4u) n_hi = (uint32_t)(q | 4) | ((uint32_t)(q | 12) << 4);
+                            else if (q == 4 && sc.ncol_ok != 0u) { fix = (fix & 0x00ffu) | 0x7600u; has_n = true; }
+                            else wide = 1;
                         }
                         sel[j] = n_lo | (n_hi << 8);
                         H[j] = 0; E[j] = 0;
+                        nfix[j * STRIP_BLOCK + tid] = fix;
                     }
+                    nfix_stale = has_n;
                 }
                 Ftop = Hdtop = cmin = a = b = best = 0; cvlo = cvhi = 0;
                 s = 0;
@@ -229,18 +252,23 @@ sw_strip16_kernel(const SwTask* __restrict__ tasks, int ntasks, int* __restrict_
         }
 
         // ------------------------------------------------------------------ G wavefront steps ---------------------------
-#pragma unroll STRIP_UNROLL
-        for (int u = 0; u < G; ++u, ++s) {
+        // one step, in two variants: NM = false looks the score up with one PRMT, NM = true adds the N fix-up (see nfix above)
+        auto step = [&](auto nm_tag, const int u) {
+            constexpr bool NM = decltype(nm_tag)::value;
+            auto score = [&](const int j) -> uint32_t {
+                const uint32_t v = prmt(a, b, sel[j]);
+                return NM ? prmt(v, sc.ncol2, nfix[j * STRIP_BLOCK + tid]) : v;
+            };
             {   // the first stage takes the next target base from the chunk, the others got theirs by shuffle last step
                 const uint32_t a0 = __shfl_sync(0xffffffffu, tchunk, u, G);
                 a = (t == 0) ? a0 : a;
             }
             uint32_t F = Ftop, m = 0;
-            uint32_t h = add2(Hdtop, prmt(a, b, sel[0]));
+            uint32_t h = add2(Hdtop, score(0));
 #pragma unroll
             for (int j = 0; j < KR; ++j) {
                 uint32_t hnext = 0;
-                if (j + 1 < KR) hnext = add2(H[j], prmt(a, b, sel[j + 1]));   // uses H(j) of the previous column: diagonal of row j+1
+                if (j + 1 < KR) hnext = add2(H[j], score(j + 1));   // uses H(j) of the previous column: diagonal of row j+1
                 else Hdtop = H[j];                                            // bottom H of the previous column: diagonal for the next stage
                 const uint32_t Hn = max3_relu(h, E[j], F);
                 const uint32_t Hg = add2(Hn, sc.mgapO2);
@@ -300,6 +328,13 @@ sw_strip16_kernel(const SwTask* __restrict__ tasks, int ntasks, int* __restrict_
             }
             b = a;
             a = rA;
+        };
+        if (__any_sync(0xffffffffu, has_n)) {
+#pragma unroll STRIP_UNROLL
+            for (int u = 0; u < G; ++u, ++s) step(std::true_type{}, u);
+        } else {
+#pragma unroll STRIP_UNROLL
+            for (int u = 0; u < G; ++u, ++s) step(std::false_type{}, u);
         }
         // ---- column records of the G steps just done: thread t of the group stores the one of step s - G + t (one 4*G-byte run per group)
         if (!REV) {

@@ -270,3 +270,29 @@ def test_long_reads_with_n_bases(eng, npairs):
     r, c = oracle_table(b, cap=cap, threads=os.cpu_count() or 8)
     bad = diff(g, gc, r, c)
     assert len(bad) == 0, (bad[:5], g[bad[:2]], r[bad[:2]])
+
+
+@pytest.mark.parametrize("ncol", ["minus_mismatch", "zero", "plus_one", "varying"])
+def test_short_reads_with_n_bases(eng, ncol):
+    """reads of every short-read strip size that contain N (code 4): with a constant N column (both matrix builders of the reference,
+    ssw_cpp.cpp:23-48 and pyssw.py:61-79) they stay in the packed kernel (second PRMT per row); with a varying N column they are flagged
+    and redone by the int32 kernel.  Targets contain N too."""
+    parts = [w.make_pairs(300, (lo, hi), 1.6, err=0.04, seed=900 + lo, flag=1, chunk=128, n_frac=0.006)
+             for lo, hi in ((20, 64), (65, 330), (331, 700), (701, 1280))]
+    reads = np.concatenate([p.reads for p in parts]); refs = np.concatenate([p.refs for p in parts])
+    rl = np.concatenate([p.read_len for p in parts]); fl = np.concatenate([p.ref_len for p in parts])
+    ro = np.zeros(len(rl) + 1, dtype=np.int64); np.cumsum(rl, out=ro[1:])
+    fo = np.zeros(len(fl) + 1, dtype=np.int64); np.cumsum(fl, out=fo[1:])
+    assert int((reads == 4).sum()) > 500 and int((refs == 4).sum()) > 500
+    mat = w.dna_matrix(2, 3, n_zero=(ncol == "zero")).reshape(5, 5).copy()
+    if ncol == "plus_one":
+        mat[:, 4] = 1; mat[4, :] = 1
+    elif ncol == "varying":
+        mat[:, 4] = [0, -1, -2, -3, 1]; mat[4, :] = mat[:, 4]
+    for flag in (1, 0):
+        b = w.PairBatch(reads, ro, refs, fo, np.maximum(rl // 2, 15).astype(np.int32), mat=mat.reshape(-1), flag=flag)
+        cap = 2048
+        g, gc, _, _ = gpu_table(eng, b, cap=cap)
+        r, c = oracle_table(b, cap=cap, threads=os.cpu_count() or 8)
+        bad = diff(g, gc, r, c)
+        assert len(bad) == 0, (ncol, flag, bad[:5], g[bad[:2]], r[bad[:2]])
