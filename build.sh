@@ -6,6 +6,9 @@
 set -e
 cd "$(dirname "$0")"
 mkdir -p megapath-nano_b200/realign
+#   megapath-nano_b200/realign/debruijn_graph   the name realign_illumina_reads.py:30 loads (get_consensus / free_memory), host only
+g++ -O2 -std=c++17 -fPIC -Wall -shared -pthread -o megapath-nano_b200/realign/debruijn_graph megapath-nano_b200/csrc/debruijn_assemble.cpp
+[ "$1" = "dbg" ] && exit 0
 NVCC_FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC $MPN_EXTRA_NVCC_FLAGS"
 OBJ=build/obj${MPN_BUILD_TAG:+_$MPN_BUILD_TAG}
 OUT=${MPN_SSW_OUT:-megapath-nano_b200/libmpn_ssw.so}

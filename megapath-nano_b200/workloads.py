@@ -319,3 +319,70 @@ def config3(nregions=64, seed=13, max_reads=1000, max_haps=32, err=0.005, n_frac
             reads.append(r); positions.append(ref_start + st); cigars.append(f"{len(r)}M")
         regions.append(RegionWorkload(reference, haps, reads, positions, cigars, ref_start, pre, suf))
     return regions
+
+
+def dbg_windows(nwindows=32, seed=21, max_reads=400, err=0.005, repeat_frac=0.2, n_frac=0.0005, lowq_frac=0.01):
+    """Assembler inputs shaped like realign_illumina_reads.py:532-553: a 160-1000 bp reference window, reads
+    of 100-250 bp sampled from 1-3 truth haplotypes (reference + planted SNVs / indels) that overlap the window (so they may start before
+    it or run past it), 0.5 % sequencing error, a few N and a few low-quality positions per read.  A fraction of the windows carries a
+    tandem repeat, which pushes the smallest acyclic k up.  Returns a list of (ref, reads, low_quality_fields)."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for _ in range(nwindows):
+        wlen = int(rng.integers(160, 1001))
+        ref = _rand_dna(rng, wlen)
+        if rng.random() < repeat_frac:
+            unit = _rand_dna(rng, int(rng.integers(2, 30)))
+            at = int(rng.integers(20, wlen - 60))
+            rep = (unit * 40)[:int(rng.integers(20, 60))]
+            ref = ref[:at] + rep + ref[at + len(rep):]
+        flank_l, flank_r = _rand_dna(rng, 120), _rand_dna(rng, 120)
+        truth = [ref] + [_plant_variants(rng, ref, int(rng.integers(1, 4))) for _ in range(int(rng.integers(0, 3)))]
+        reads, lowq = [], []
+        for _ in range(int(rng.integers(0 if rng.random() < 0.05 else 20, max_reads + 1))):
+            h = flank_l + truth[int(rng.integers(0, len(truth)))] + flank_r
+            rl = int(rng.integers(100, 251))
+            st = int(rng.integers(0, max(1, len(h) - rl)))
+            r = _noisy_copy(rng, h[st:st + rl], err)
+            if n_frac > 0:
+                r = "".join("N" if rng.random() < n_frac else c for c in r)
+            reads.append(r)
+            lowq.append(" ".join(str(i) for i in np.nonzero(rng.random(len(r)) < lowq_frac)[0]))
+        out.append((ref, reads, lowq))
+    return out
+
+
+@dataclass
+class WindowWorkload:
+    """one candidate window before assembly (realign_illumina_reads.py:532-580): `chrom` is a piece of reference sequence whose first
+    base sits at chromosome position chrom_start; the window is chrom[win_start:win_end]; reads carry chromosome positions."""
+    chrom: str
+    chrom_start: int
+    win_start: int
+    win_end: int
+    reads: list
+    positions: list
+    cigars: list
+    low_quality: list
+
+
+def config3_windows(nwindows=32, seed=51, max_reads=400, err=0.005, lowq_frac=0.005):
+    """BASELINE configs[2] one step earlier: windows whose haplotypes are NOT given but have to be assembled from the reads."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for _ in range(nwindows):
+        wlen = int(rng.integers(160, 1001)); pad = 300
+        chrom = _rand_dna(rng, pad + wlen + pad)
+        center = chrom[pad:pad + wlen]
+        truth = [center] + [_plant_variants(rng, center, int(rng.integers(1, 4))) for _ in range(int(rng.integers(1, 3)))]
+        chrom_start = int(rng.integers(1000, 5_000_000))
+        reads, positions, cigars, lowq = [], [], [], []
+        for _ in range(int(rng.integers(50, max_reads + 1))):
+            h = chrom[:pad] + truth[int(rng.integers(0, len(truth)))] + chrom[pad + wlen:]
+            rl = int(rng.integers(100, 251))
+            st = int(rng.integers(pad - 80, max(pad - 79, pad + wlen - 20)))          # overlaps the window, overhang up to ~250 bp
+            r = _noisy_copy(rng, h[st:st + rl], err) or "A"
+            reads.append(r); positions.append(chrom_start + st); cigars.append(f"{len(r)}M")
+            lowq.append(" ".join(str(i) for i in np.nonzero(rng.random(len(r)) < lowq_frac)[0]))
+        out.append(WindowWorkload(chrom, chrom_start, pad, pad + wlen, reads, positions, cigars, lowq))
+    return out

@@ -40,6 +40,14 @@ def test_libraries_export_every_declared_symbol(built):
         lib = ct.CDLL(path)
         for name in want:
             assert hasattr(lib, name), (path, name)
+    # the assembler is its own shared object (its free_memory has a different argument type than the realigner's)
+    dbg = os.path.join(PKG, "realign", "debruijn_graph")
+    if not os.path.exists(dbg):
+        subprocess.run(["bash", os.path.join(ROOT, "build.sh"), "dbg"], check=True)
+    lib = ct.CDLL(dbg)
+    assert set(declared_functions("debruijn_graph.h")) >= {"get_consensus", "free_memory", "mpn_dbg_consensus_packed"}
+    for name in declared_functions("debruijn_graph.h"):
+        assert hasattr(lib, name), (dbg, name)
 
 
 def test_s_align_layout_is_the_reference_layout(tmp_path):

@@ -42,3 +42,18 @@ def test_config3_live_against_compiled_reference(seed, n_frac):
     assert not bad, bad[:5]
     single = [R.realign_reads(rg) for rg in regions[:4]]
     assert single == got[:4]
+
+
+def test_assembled_haplotypes_through_the_gpu_realigner():
+    """SURVEY.md section 8f N4 -> N3 -> hot path: haplotypes assembled by realign/debruijn_graph from the reads of each window, then
+    realign_regions on the GPU == the compiled reference realigner on the same inputs"""
+    from oracle import oracle
+    if not oracle.have_ref():
+        pytest.skip("compiled reference realigner not present")
+    D = importlib.import_module("megapath-nano_b200.debruijn")
+    regions, kept = D.regions_from_windows(w.config3_windows(12, seed=71, max_reads=150))
+    assert len(regions) >= 8
+    want = run_reference(regions, oracle.realigner_ref_path())
+    got = R.realign_regions(regions)
+    bad = mismatches(got, want)
+    assert not bad, bad[:5]
