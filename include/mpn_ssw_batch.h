@@ -102,6 +102,42 @@ int mpn_batch_fetch(mpn_batch* b, mpn_result* out, uint32_t* cigar, int64_t ciga
 int mpn_batch_io_bytes(const mpn_batch* b, int64_t* h2d, int64_t* d2h);
 void mpn_batch_free(mpn_batch* b);
 
+/*
+ * ---- k-mer fast pass of the region realigner on the GPU ----------------------------------------
+ * Replaces, for many regions at once, the reference's BuildIndex + FastAlignReadsToHaplotype + FastAlignStrings
+ * (realigner.cpp:429-451, :170-230, :232-253): every read of a region against every haplotype of that region, ungapped, at most
+ * 2 mismatches (N on either side matches), only at placements that share an exact 32-mer with the haplotype; best placement per
+ * (haplotype, read) with the reference's evaluation order as tie-break; haplotype score = sum of its reads' best scores, 0 when a
+ * non-reference haplotype has a base inside the window that no read covered by the time the scan reached it (:248-252).
+ *
+ *   text                     ASCII bases of all haplotypes and reads (any layout; spans below index it)
+ *   hap_start/hap_len        nhaps spans; haplotypes of one region are consecutive
+ *   hap_is_ref               1 if the haplotype equals the region's reference string (never dropped, :172)
+ *   read_start/read_len      nreads spans; reads of one region are consecutive
+ *   regions                  per region: its haplotypes, its reads, ref_prefix / ref_suffix, and where its placements start
+ *   places                   out: for region g, haplotype h (local), read r (local): places[g.place_first + h * g.nread + r]
+ *                            = {score, pos}; score 0 / pos -1 when the read has no placement on that haplotype
+ *   hap_score                out, nhaps entries
+ *   region_flag              out, nregions entries: 1 = the region holds a base other than A,C,G,T,N; its outputs are undefined and
+ *                            the caller must use its own string-exact path for that region
+ * Limits (MPN_E_UNSUPPORTED otherwise, nothing is computed): reads of at most 256 bases, haplotypes of at most 2816 bases.
+ */
+typedef struct { int32_t score; int32_t pos; } mpn_placement;
+typedef struct {
+    int64_t place_first;
+    int32_t hap_first, nhap;
+    int32_t read_first, nread;
+    int32_t prefix, suffix;
+} mpn_fp_region;
+enum { MPN_FP_MAX_READ = 256, MPN_FP_MAX_HAP = 2816 };
+int mpn_fastpass(mpn_engine* e, const char* text, int64_t text_bytes,
+                 const int64_t* hap_start, const int32_t* hap_len, const uint8_t* hap_is_ref, int32_t nhaps,
+                 const int64_t* read_start, const int32_t* read_len, int32_t nreads,
+                 const mpn_fp_region* regions, int32_t nregions,
+                 mpn_placement* places, int32_t* hap_score, uint8_t* region_flag);
+/* milliseconds the kernel of the last mpn_fastpass call took on the device (CUDA events) */
+float mpn_fastpass_last_kernel_ms(const mpn_engine* e);
+
 #ifdef __cplusplus
 }
 #endif

@@ -59,6 +59,13 @@ void mpn_realign_free(void* p);
  * forward-matrix cells, and seconds spent in {host k-mer pass, GPU batch (copies included), host CIGAR algebra} */
 int mpn_realign_last_stats(long long* pairs, long long* cells, double* seconds3);
 
+
+/* the fast pass alone (test and A/B hook): which = 0 the GPU kernel mpn_fastpass (include/mpn_ssw_batch.h), 1 the host k-mer index.
+ * hap_scores: one int per haplotype of every region; places: per region nhap * nread pairs (score, pos), pos -1 = not placed. */
+int mpn_realign_fastpass_only(const mpn_region* regions, int nregions, int which, int* hap_scores, int* places, double* kernel_ms);
+/* device milliseconds of the fast-pass kernel inside the last realign_reads / mpn_realign_regions call */
+double mpn_realign_last_fastpass_kernel_ms(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -11,6 +11,7 @@
 #include "sw_trace_narrow.cuh"
 #include "sw_trace_warp.cuh"
 #include "sw_trace_rows.cuh"
+#include "fastpass.cuh"
 
 #include <algorithm>
 #include <chrono>
@@ -126,6 +127,11 @@ struct mpn_engine {
     Slot slot[NSLOT];
     std::vector<int32_t> h_bin;
     std::vector<int64_t> h_order, h_idx, h_cnt;
+    // k-mer fast pass (mpn_fastpass)
+    DevBuf fp_text, fp_haps, fp_regions, fp_rstart, fp_rlen, fp_places, fp_score, fp_flag;
+    cudaEvent_t fp_ev[2] = {nullptr, nullptr};
+    float fp_kernel_ms = 0.f;
+    bool fp_attr_done = false;
 };
 
 struct BinLaunch { int cfg; int64_t first; int64_t count; };
@@ -199,6 +205,8 @@ extern "C" void mpn_engine_destroy(mpn_engine* e)
     cudaStreamDestroy(e->own_stream);
     for (int k = 0; k < mpn_engine::NAUX; ++k) { cudaStreamDestroy(e->aux[k]); cudaEventDestroy(e->ev_join[k]); }
     cudaEventDestroy(e->ev_fork);
+    for (DevBuf* d : {&e->fp_text, &e->fp_haps, &e->fp_regions, &e->fp_rstart, &e->fp_rlen, &e->fp_places, &e->fp_score, &e->fp_flag}) e->pool.give(*d);
+    if (e->fp_attr_done) { cudaEventDestroy(e->fp_ev[0]); cudaEventDestroy(e->fp_ev[1]); }
     e->pool.clear();
     for (int k = 0; k < mpn_engine::NSLOT; ++k) {
         mpn_engine::Slot& sl = e->slot[k];
@@ -787,3 +795,75 @@ extern "C" int mpn_align_batch(mpn_engine* e, const mpn_params* p, const int8_t*
     for (int64_t c = std::max<int64_t>(0, issued - DEPTH); c < issued + DEPTH; ++c) drain((int)(c % DEPTH));
     return rc;
 }
+
+
+// ------------------------------------------------------------------------------------------------ k-mer fast pass of the realigner
+extern "C" int mpn_fastpass(mpn_engine* e, const char* text, int64_t text_bytes,
+                            const int64_t* hap_start, const int32_t* hap_len, const uint8_t* hap_is_ref, int32_t nhaps,
+                            const int64_t* read_start, const int32_t* read_len, int32_t nreads,
+                            const mpn_fp_region* regions, int32_t nregions,
+                            mpn_placement* places, int32_t* hap_score, uint8_t* region_flag)
+{
+    if (!e || nhaps < 0 || nreads < 0 || nregions < 0 || text_bytes < 0) return MPN_E_ARG;
+    if (nregions == 0 || nhaps == 0) return 0;
+    if (!text || !hap_start || !hap_len || !hap_is_ref || !regions || !places || !hap_score || !region_flag || (nreads > 0 && (!read_start || !read_len))) return MPN_E_ARG;
+    static_assert(sizeof(FpRegion) == sizeof(mpn_fp_region) && sizeof(mpn_placement) == sizeof(int2), "ABI structs mirror the kernel's");
+    int max_hap = 0;
+    for (int h = 0; h < nhaps; ++h) {
+        if (hap_len[h] < 0 || hap_start[h] < 0 || hap_start[h] + hap_len[h] > text_bytes) return MPN_E_ARG;
+        if (hap_len[h] > MPN_FP_MAX_HAP) return MPN_E_UNSUPPORTED;
+        max_hap = std::max(max_hap, hap_len[h]);
+    }
+    for (int r = 0; r < nreads; ++r) {
+        if (read_len[r] < 0 || read_start[r] < 0 || read_start[r] + read_len[r] > text_bytes) return MPN_E_ARG;
+        if (read_len[r] > MPN_FP_MAX_READ) return MPN_E_UNSUPPORTED;
+    }
+    std::vector<FpHap> haps((size_t)nhaps, FpHap{0, 0, -1, 0, 0});
+    int64_t nplaces = 0;
+    for (int g = 0; g < nregions; ++g) {
+        const mpn_fp_region& rg = regions[g];
+        if (rg.nhap < 0 || rg.nread < 0 || rg.hap_first < 0 || rg.read_first < 0 || rg.hap_first + rg.nhap > nhaps || rg.read_first + rg.nread > nreads || rg.place_first < 0) return MPN_E_ARG;
+        for (int h = 0; h < rg.nhap; ++h) haps[(size_t)(rg.hap_first + h)] = FpHap{hap_start[rg.hap_first + h], hap_len[rg.hap_first + h], g, h, hap_is_ref[rg.hap_first + h] ? 1 : 0};
+        nplaces = std::max<int64_t>(nplaces, rg.place_first + (int64_t)rg.nhap * rg.nread);
+    }
+    for (const FpHap& h : haps) if (h.region < 0) return MPN_E_ARG;          // every haplotype belongs to a region
+    CK(cudaSetDevice(e->device));
+    cudaStream_t st = e->stream;
+    if (!e->fp_attr_done) {
+        CK(cudaFuncSetAttribute(fastpass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fp_smem_bytes(MPN_FP_MAX_HAP)));
+        CK(cudaEventCreate(&e->fp_ev[0])); CK(cudaEventCreate(&e->fp_ev[1]));
+        e->fp_attr_done = true;
+    }
+    e->pool.take(e->fp_text, (size_t)text_bytes + 16);
+    e->pool.take(e->fp_haps, sizeof(FpHap) * (size_t)nhaps);
+    e->pool.take(e->fp_regions, sizeof(FpRegion) * (size_t)nregions);
+    e->pool.take(e->fp_rstart, sizeof(int64_t) * (size_t)std::max(nreads, 1));
+    e->pool.take(e->fp_rlen, sizeof(int32_t) * (size_t)std::max(nreads, 1));
+    e->pool.take(e->fp_places, sizeof(int2) * (size_t)std::max<int64_t>(nplaces, 1));
+    e->pool.take(e->fp_score, sizeof(int) * (size_t)nhaps);
+    e->pool.take(e->fp_flag, sizeof(int) * (size_t)nregions);
+    CK(cudaMemcpyAsync(e->fp_text.p, text, (size_t)text_bytes, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(e->fp_haps.p, haps.data(), sizeof(FpHap) * (size_t)nhaps, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(e->fp_regions.p, regions, sizeof(FpRegion) * (size_t)nregions, cudaMemcpyHostToDevice, st));
+    if (nreads > 0) {
+        CK(cudaMemcpyAsync(e->fp_rstart.p, read_start, sizeof(int64_t) * (size_t)nreads, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(e->fp_rlen.p, read_len, sizeof(int32_t) * (size_t)nreads, cudaMemcpyHostToDevice, st));
+    }
+    CK(cudaMemsetAsync(e->fp_flag.p, 0, sizeof(int) * (size_t)nregions, st));
+    CK(cudaEventRecord(e->fp_ev[0], st));
+    fastpass_kernel<<<(unsigned)nhaps, FP_BLOCK, fp_smem_bytes(max_hap), st>>>(e->fp_text.as<char>(), e->fp_haps.as<FpHap>(), e->fp_regions.as<FpRegion>(),
+        e->fp_rstart.as<long long>(), e->fp_rlen.as<int>(), e->fp_places.as<int2>(), e->fp_score.as<int>(), e->fp_flag.as<int>());
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(e->fp_ev[1], st));
+    e->launches++;
+    std::vector<int> flags((size_t)nregions);
+    if (nplaces > 0) CK(cudaMemcpyAsync(places, e->fp_places.p, sizeof(int2) * (size_t)nplaces, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(hap_score, e->fp_score.p, sizeof(int) * (size_t)nhaps, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(flags.data(), e->fp_flag.p, sizeof(int) * (size_t)nregions, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    CK(cudaEventElapsedTime(&e->fp_kernel_ms, e->fp_ev[0], e->fp_ev[1]));
+    for (int g = 0; g < nregions; ++g) region_flag[g] = flags[(size_t)g] ? 1 : 0;
+    return 0;
+}
+
+extern "C" float mpn_fastpass_last_kernel_ms(const mpn_engine* e) { return e ? e->fp_kernel_ms : 0.f; }

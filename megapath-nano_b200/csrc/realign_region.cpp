@@ -3,7 +3,8 @@
 //
 // Per region, in the reference's order (ReAligner::AlignReads, realigner.cpp:88-117):
 //   1. k-mer index over the reads (k = 32, BuildIndex :429-451) and the <= 2-mismatch ungapped "fast pass" of every read
-//      against every haplotype (FastAlignReadsToHaplotype :170-230, FastAlignStrings :232-253)                    [host]
+//      against every haplotype (FastAlignReadsToHaplotype :170-230, FastAlignStrings :232-253)
+//      [GPU: mpn_fastpass, all regions in one launch, no index; host k-mer index only for regions outside the kernel's limits]
 //   2. haplotype -> reference alignments (AlignHaplotypesToReference :325-349) and, for reads the fast pass could not
 //      place, read -> haplotype alignments (SswAlignReadsToHaplotypes :351-384)                      [GPU, one batch]
 //   3. haplotype position maps (SetPositionsMap :453-509), best haplotype per read (GetBestReadAlignment :517-540) and
@@ -19,6 +20,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <deque>
+#include <memory>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -293,6 +295,77 @@ void fast_pass(Region& rg, bool threads)
     if (threads) mpn::parallel_for(nh, 1, one); else for (int h = 0; h < nh; ++h) one(h);
 }
 
+// The fast pass of many regions in one GPU call (mpn_fastpass, include/mpn_ssw_batch.h).  Regions the kernel does not take -- reads
+// longer than 256 bases, haplotypes longer than 2816, bases other than A,C,G,T,N (the kernel's 3-bit alphabet; the reference compares
+// raw characters) -- keep the string-exact host pass above, which is the placement the reference itself has for this step.
+void fast_pass_regions(std::vector<Region>& rgs, double* kernel_ms)
+{
+    const int nr = (int)rgs.size();
+    static const bool force_host = getenv("MPN_FASTPASS_HOST") != nullptr;      // A/B timing of the two placements of this step
+    std::vector<char> on_gpu((size_t)nr, force_host ? 0 : 1);
+    mpn::parallel_for(nr, 4, [&](int64_t g) {
+        const Region& rg = rgs[(size_t)g];
+        if (rg.haplotypes.empty() || rg.reads.empty()) { on_gpu[(size_t)g] = 0; return; }
+        for (const std::string& h : rg.haplotypes) if (h.size() > (size_t)MPN_FP_MAX_HAP) { on_gpu[(size_t)g] = 0; return; }
+        for (const std::string& q : rg.reads) if (q.size() > (size_t)MPN_FP_MAX_READ) { on_gpu[(size_t)g] = 0; return; }
+    });
+    // spans of every haplotype and read inside one text buffer
+    std::vector<mpn_fp_region> fr;
+    std::vector<int> region_of;
+    std::vector<int64_t> hap_start, read_start;
+    std::vector<int32_t> hap_len, read_len;
+    std::vector<uint8_t> is_ref;
+    std::vector<const std::string*> src;
+    int64_t bytes = 0, nplaces = 0;
+    for (int g = 0; g < nr; ++g) {
+        if (!on_gpu[(size_t)g]) continue;
+        const Region& rg = rgs[(size_t)g];
+        mpn_fp_region f;
+        f.place_first = nplaces; f.hap_first = (int32_t)hap_start.size(); f.nhap = (int32_t)rg.haplotypes.size();
+        f.read_first = (int32_t)read_start.size(); f.nread = (int32_t)rg.reads.size(); f.prefix = rg.prefix; f.suffix = rg.suffix;
+        for (const std::string& h : rg.haplotypes) { hap_start.push_back(bytes); hap_len.push_back((int32_t)h.size()); is_ref.push_back(h == rg.reference); src.push_back(&h); bytes += (int64_t)h.size(); }
+        for (const std::string& q : rg.reads) { read_start.push_back(bytes); read_len.push_back((int32_t)q.size()); src.push_back(&q); bytes += (int64_t)q.size(); }
+        nplaces += (int64_t)f.nhap * f.nread;
+        fr.push_back(f); region_of.push_back(g);
+    }
+    std::vector<mpn_placement> places((size_t)nplaces);
+    std::vector<int32_t> hap_score(hap_start.size());
+    std::vector<uint8_t> flag(fr.size(), 0);
+    if (!fr.empty()) {
+        std::unique_ptr<char[]> text(new char[(size_t)bytes + 1]);
+        {
+            std::vector<int64_t> at(src.size());
+            int64_t b = 0;
+            for (size_t k = 0; k < src.size(); ++k) { at[k] = b; b += (int64_t)src[k]->size(); }
+            mpn::parallel_for((int64_t)src.size(), 256, [&](int64_t k) { memcpy(text.get() + at[(size_t)k], src[(size_t)k]->data(), src[(size_t)k]->size()); });
+        }
+        mpn::SharedEngineLock lk;
+        const int rc = mpn_fastpass(lk.engine(), text.get(), bytes, hap_start.data(), hap_len.data(), is_ref.data(), (int32_t)hap_start.size(),
+                                    read_start.data(), read_len.data(), (int32_t)read_start.size(), fr.data(), (int32_t)fr.size(),
+                                    places.data(), hap_score.data(), flag.data());
+        if (rc != 0) { fprintf(stderr, "[realigner] mpn_fastpass failed (code %d)\n", rc); abort(); }
+        if (kernel_ms) *kernel_ms = mpn_fastpass_last_kernel_ms(lk.engine());
+    }
+    std::vector<int> slot_of((size_t)nr, -1);
+    for (size_t k = 0; k < region_of.size(); ++k) slot_of[(size_t)region_of[k]] = flag[k] ? -1 : (int)k;
+    mpn::parallel_for(nr, 1, [&](int64_t g) {
+        Region& rg = rgs[(size_t)g];
+        const int k = slot_of[(size_t)g];
+        if (k < 0) { fast_pass(rg, nr == 1 && rg.reads.size() * rg.haplotypes.size() >= 2048); return; }
+        const mpn_fp_region& f = fr[(size_t)k];
+        rg.haps.assign((size_t)f.nhap, HapRecord());
+        for (int h = 0; h < f.nhap; ++h) {
+            HapRecord& rec = rg.haps[(size_t)h];
+            rec.index = h; rec.score = hap_score[(size_t)(f.hap_first + h)];
+            rec.reads.assign((size_t)f.nread, Placement());
+            if (rec.score == 0) continue;                    // dropped or nothing placed: every read stays unplaced (realigner.cpp:160-165)
+            const mpn_placement* pl = places.data() + f.place_first + (int64_t)h * f.nread;
+            for (int r = 0; r < f.nread; ++r)
+                if (pl[r].score > 0) { rec.reads[(size_t)r].score = pl[r].score; rec.reads[(size_t)r].pos = pl[r].pos; rec.reads[(size_t)r].cigar = std::to_string(rg.reads[(size_t)r].size()) + "="; }
+        }
+    });
+}
+
 // which (read, haplotype) pairs need Smith-Waterman (realigner.cpp:351-366)
 void plan_read_pairs(Region& rg)
 {
@@ -425,7 +498,7 @@ bool best_haplotype(const Region& rg, int read, int* best)
     return found;
 }
 
-struct Stats { long long pairs = 0, cells = 0; double t_fast = 0, t_gpu = 0, t_compose = 0; };
+struct Stats { long long pairs = 0, cells = 0; double t_fast = 0, t_gpu = 0, t_compose = 0, fp_kernel_ms = 0; };
 Stats g_last;
 
 double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
@@ -454,11 +527,11 @@ int realign_many(const mpn_region* regions, int nregions, struct_str_arr** out)
     std::vector<Region> rgs((size_t)nregions);
     Stats st;
     double t0 = now_s();
-    // ---- 1. host: k-mer fast pass, then the list of Smith-Waterman pairs of every region
+    // ---- 1. k-mer fast pass (GPU), then the list of Smith-Waterman pairs of every region
     for (int r = 0; r < nregions; ++r) load_region(rgs[r], regions[r]);
-    // regions are independent: one host thread each when there are several, else threads over the haplotypes of the one region
-    if (nregions > 1) mpn::parallel_for(nregions, 1, [&](int64_t r) { fast_pass(rgs[(size_t)r], false); plan_read_pairs(rgs[(size_t)r]); });
-    else if (nregions == 1) { fast_pass(rgs[0], rgs[0].reads.size() * rgs[0].haplotypes.size() >= 2048); plan_read_pairs(rgs[0]); }
+    // every (haplotype, read) of every region in one kernel launch; then the Smith-Waterman work list per region
+    fast_pass_regions(rgs, &st.fp_kernel_ms);
+    mpn::parallel_for(nregions, 1, [&](int64_t r) { plan_read_pairs(rgs[(size_t)r]); });
     // sequence pool: per region the reference, its haplotypes and its reads, each once; pairs name them by index
     std::vector<SeqView> pool;
     std::vector<PairIndex> pairs;
@@ -624,6 +697,24 @@ extern "C" void free_memory(struct_str_arr* pointer, int size)
     delete pointer;
 }
 
+/* test / A-B hook: the fast pass alone.  which = 0: GPU kernel (with the per-region host path for what it does not take), 1: host
+ * k-mer index path for every region.  hap_scores: sum of nhap entries; places: per region nhap * nread pairs (score, pos). */
+extern "C" int mpn_realign_fastpass_only(const mpn_region* regions, int nregions, int which, int* hap_scores, int* places, double* kernel_ms)
+{
+    std::vector<Region> rgs((size_t)std::max(nregions, 0));
+    for (int r = 0; r < nregions; ++r) load_region(rgs[(size_t)r], regions[r]);
+    if (kernel_ms) *kernel_ms = 0;
+    if (which == 0) fast_pass_regions(rgs, kernel_ms);
+    else mpn::parallel_for(nregions, 1, [&](int64_t r) { fast_pass(rgs[(size_t)r], false); });
+    size_t hs = 0, pl = 0;
+    for (const Region& rg : rgs)
+        for (const HapRecord& h : rg.haps) {
+            hap_scores[hs++] = h.score;
+            for (const Placement& p : h.reads) { places[pl++] = p.score; places[pl++] = p.pos; }
+        }
+    return 0;
+}
+
 extern "C" int mpn_realign_last_stats(long long* pairs, long long* cells, double* seconds3)
 {
     if (pairs) *pairs = g_last.pairs;
@@ -631,3 +722,5 @@ extern "C" int mpn_realign_last_stats(long long* pairs, long long* cells, double
     if (seconds3) { seconds3[0] = g_last.t_fast; seconds3[1] = g_last.t_gpu; seconds3[2] = g_last.t_compose; }
     return 0;
 }
+
+extern "C" double mpn_realign_last_fastpass_kernel_ms() { return g_last.fp_kernel_ms; }

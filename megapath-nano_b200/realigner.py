@@ -133,3 +133,31 @@ def last_stats(lib_path=None):
     secs = (ctypes.c_double * 3)()
     L.mpn_realign_last_stats(ctypes.byref(pairs), ctypes.byref(cells), secs)
     return dict(pairs=pairs.value, cells=cells.value, fast_pass_s=secs[0], gpu_s=secs[1], compose_s=secs[2])
+
+
+def fastpass_only(regions, which=0, lib_path=None):
+    """Test / A-B hook (mpn_realign_fastpass_only): the k-mer fast pass alone.  which = 0: GPU kernel, 1: host k-mer index.
+    Returns (hap_scores, places[(score, pos)], kernel_ms), both flat in region / haplotype / read order."""
+    import array
+    L = load(lib_path)
+    nr = len(regions)
+    arr = (MpnRegion * max(nr, 1))()
+    keep = []
+    nh = npl = 0
+    for k, region in enumerate(regions):
+        n, seq_list, position_list, cigars_list = _marshal(region)
+        ref_b, hap_b = byte(region.reference), byte(" ".join(region.haplotypes))
+        keep.append((seq_list, position_list, cigars_list, ref_b, hap_b))
+        arr[k] = MpnRegion(ctypes.cast(seq_list, ctypes.POINTER(ctypes.c_char_p)), ctypes.cast(position_list, ctypes.POINTER(ctypes.c_int)),
+                           ctypes.cast(cigars_list, ctypes.POINTER(ctypes.c_char_p)), n, ref_b, hap_b,
+                           int(region.ref_start), int(region.ref_prefix), int(region.ref_suffix))
+        nhap = len(" ".join(region.haplotypes).split())
+        nh += nhap; npl += nhap * n
+    scores = (ctypes.c_int * max(nh, 1))()
+    places = (ctypes.c_int * max(2 * npl, 1))()
+    ms = ctypes.c_double(0)
+    L.mpn_realign_fastpass_only.argtypes = [ctypes.POINTER(MpnRegion), ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(ctypes.c_double)]
+    rc = L.mpn_realign_fastpass_only(arr, nr, int(which), scores, places, ctypes.byref(ms))
+    if rc:
+        raise RuntimeError(f"mpn_realign_fastpass_only -> {rc}")
+    return list(scores[:nh]), list(places[:2 * npl]), ms.value

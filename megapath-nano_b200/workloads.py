@@ -386,3 +386,53 @@ def config3_windows(nwindows=32, seed=51, max_reads=400, err=0.005, lowq_frac=0.
             lowq.append(" ".join(str(i) for i in np.nonzero(rng.random(len(r)) < lowq_frac)[0]))
         out.append(WindowWorkload(chrom, chrom_start, pad, pad + wlen, reads, positions, cigars, lowq))
     return out
+
+
+def fastpass_adversarial(nregions=12, seed=81):
+    """Regions that stress the fast pass's order-dependent rules (realigner.cpp:170-253): tandem repeats and duplicated blocks (equal-score
+    placements at several starts: the first evaluated wins), reads hanging over either end of the haplotype (start clamp at 0, skipped
+    overhang), reads of 1..40 bases (not indexed up to 32), haplotypes shorter than k, N in reads and haplotypes, haplotypes that lose
+    coverage inside the window (dropped), window flanks from 0 to longer than the haplotype."""
+    rng = np.random.default_rng(seed)
+    regions = []
+    for g in range(nregions):
+        wlen = int(rng.integers(40, 500))
+        unit = _rand_dna(rng, int(rng.integers(1, 45)))
+        core = _rand_dna(rng, wlen)
+        if g % 3 != 2:
+            at = int(rng.integers(0, max(1, wlen - 20)))
+            rep = (unit * 200)[:int(rng.integers(40, 200))]
+            core = core[:at] + rep + core[at:]
+            if g % 3 == 1:
+                core = core + _rand_dna(rng, 30) + rep[:90] + _rand_dna(rng, 40)
+        pre, suf = int(rng.integers(0, 60)), int(rng.integers(0, 60))
+        reference = _rand_dna(rng, pre) + core + _rand_dna(rng, suf)
+        haps = [reference]
+        for _ in range(int(rng.integers(1, 7))):
+            h = reference[:pre] + _plant_variants(rng, core, int(rng.integers(1, 4))) + reference[len(reference) - suf:]
+            if rng.random() < 0.2:
+                h = "".join("N" if rng.random() < 0.01 else c for c in h)
+            haps.append(h)
+        if rng.random() < 0.3:
+            haps.append(_rand_dna(rng, int(rng.integers(1, 40))))
+        order = rng.permutation(len(haps)); haps = [haps[i] for i in order]
+        reads, positions, cigars = [], [], []
+        for _ in range(int(rng.integers(5, 120))):
+            h = haps[int(rng.integers(0, len(haps)))]
+            u = rng.random()
+            rl = int(rng.integers(1, 41)) if u < 0.1 else int(rng.integers(33, 257))
+            ext = _rand_dna(rng, 60) + h + _rand_dna(rng, 60)                           # lets reads hang over both ends
+            st = int(rng.integers(0, max(1, len(ext) - rl)))
+            r = ext[st:st + rl]
+            nm = int(rng.integers(0, 5)) if rng.random() < 0.5 else 0
+            r = list(r)
+            for _ in range(nm):
+                p = int(rng.integers(0, len(r))); r[p] = "ACGTN"[int(rng.integers(0, 5))]
+            r = "".join(r) or "A"
+            reads.append(r); positions.append(1000 + st); cigars.append(f"{len(r)}M")
+        if g % 4 == 0:
+            pre, suf = 0, 0
+        elif g % 4 == 1:
+            suf = len(reference) + 5
+        regions.append(RegionWorkload(reference, haps, reads, positions, cigars, 1000, pre, suf))
+    return regions

@@ -80,3 +80,65 @@ extern "C" int mpn_align_batch(mpn_engine*, const mpn_params* p, const int8_t* r
     }
     return 0;
 }
+
+// ---- stand-in for mpn_fastpass (the GPU k-mer fast pass): the same "diagonal run" formulation, scalar and character-exact.
+// It lets the CPU tier check that formulation end to end against the compiled reference realigner (which uses a k-mer hash index).
+extern "C" int mpn_fastpass(mpn_engine*, const char* text, int64_t, const int64_t* hap_start, const int32_t* hap_len, const uint8_t* hap_is_ref, int32_t nhaps,
+                            const int64_t* read_start, const int32_t* read_len, int32_t nreads, const mpn_fp_region* regions, int32_t nregions,
+                            mpn_placement* places, int32_t* hap_score, uint8_t* region_flag)
+{
+    (void)nhaps; (void)nreads;
+    const int K = 32;
+    for (int g = 0; g < nregions; ++g) {
+        const mpn_fp_region& rg = regions[g];
+        region_flag[g] = 0;
+        mpn::parallel_for(rg.nhap, 1, [&](int64_t h) {
+            const char* hap = text + hap_start[rg.hap_first + h];
+            const int L = hap_len[rg.hap_first + h];
+            mpn_placement* out = places + rg.place_first + h * rg.nread;
+            std::vector<int> cov((size_t)std::max(L, 1), 1 << 30);
+            std::vector<char> occ((size_t)std::max(L, 1), 0);
+            long long total = 0;
+            for (int r = 0; r < rg.nread; ++r) {
+                out[r].score = 0; out[r].pos = -1;
+                const char* read = text + read_start[rg.read_first + r];
+                const int n = read_len[rg.read_first + r];
+                if (n <= K || L < K) continue;
+                // per start: earliest trigger (t, o); starts are 0 .. L - n
+                struct Ev { int t, o; };
+                std::vector<Ev> ev((size_t)std::max(L - n + 1, 0), Ev{-1, -1});
+                for (int d = -(n - K); d <= L - K; ++d) {
+                    int run = 0;
+                    for (int x = std::max(0, -d); x < n && d + x < L; ++x) {
+                        run = (read[x] == hap[d + x]) ? run + 1 : 0;
+                        if (run >= K) {
+                            const int o = x - K + 1, i = d + o;
+                            occ[(size_t)i] = 1;
+                            const int s = std::max(0, d);
+                            if (s + n <= L) { Ev& e = ev[(size_t)s]; if (e.t < 0 || i < e.t || (i == e.t && o < e.o)) e = Ev{i, o}; }
+                        }
+                    }
+                }
+                int best = 0, bt = 0, bo = 0, bpos = -1;
+                for (int s = 0; s + n <= L; ++s) {
+                    if (ev[(size_t)s].t < 0) continue;
+                    int mism = 0;
+                    for (int x = 0; x < n; ++x) if (read[x] != hap[s + x] && read[x] != 'N' && hap[s + x] != 'N') ++mism;
+                    if (mism > 2) continue;
+                    const int sc = (n - mism) * 4 - mism * 6, t = ev[(size_t)s].t, o = ev[(size_t)s].o;
+                    for (int p = s; p < s + n; ++p) cov[(size_t)p] = std::min(cov[(size_t)p], t);
+                    if (sc > best || (sc == best && (t < bt || (t == bt && o < bo)))) { best = sc; bt = t; bo = o; bpos = s; }
+                }
+                if (best > 0) { out[r].score = best; out[r].pos = bpos; total += best; }
+            }
+            bool drop = false;
+            if (!hap_is_ref[rg.hap_first + h])
+                for (int i = 0; i + K <= L; ++i)
+                    if (i >= rg.prefix && (size_t)i < (size_t)L - (size_t)rg.suffix && occ[(size_t)i] && cov[(size_t)i] > i) drop = true;
+            hap_score[rg.hap_first + h] = drop ? 0 : (int32_t)total;
+        });
+    }
+    return 0;
+}
+
+extern "C" float mpn_fastpass_last_kernel_ms(const mpn_engine*) { return 0.f; }

@@ -57,3 +57,21 @@ def test_assembled_haplotypes_through_the_gpu_realigner():
     got = R.realign_regions(regions)
     bad = mismatches(got, want)
     assert not bad, bad[:5]
+
+
+@pytest.mark.parametrize("seed", [81, 82, 83, 84, 85, 86])
+def test_fast_pass_kernel_equals_the_kmer_index(seed):
+    """the fast pass alone, GPU kernel (mpn_fastpass: bit-parallel diagonals, no index) against the host k-mer
+    index path (the reference's algorithm), exact on every haplotype score and every (score, position): adversarial regions (equal-score
+    placements, clamped starts, dropped haplotypes, N, tiny reads / haplotypes) plus config-3 regions; a region with a lower-case base
+    is flagged by the kernel and redone on the host"""
+    regions = w.fastpass_adversarial(16, seed=seed) + w.config3(4, seed=seed, max_reads=300, max_haps=12, n_frac=0.002 if seed % 2 else 0.0)
+    odd = w.config3(1, seed=seed + 100, max_reads=60, max_haps=4)[0]
+    odd.reads[3] = odd.reads[3][:50] + "a" + odd.reads[3][51:]
+    regions.append(odd)
+    s0, p0, ms = R.fastpass_only(regions, 0)
+    s1, p1, _ = R.fastpass_only(regions, 1)
+    assert ms > 0
+    assert s0 == s1
+    assert p0 == p1
+    assert sum(1 for x in s1 if x > 0) > 20 and sum(1 for x in p1[1::2] if x >= 0) > 500

@@ -52,3 +52,16 @@ def test_host_logic_live_against_compiled_reference(hostlib, seed, n_frac):
     got = R.realign_regions(regions, hostlib)
     bad = mismatches(got, want)
     assert not bad, bad[:5]
+
+
+@pytest.mark.parametrize("seed", [81, 82, 83, 84])
+def test_fast_pass_diagonal_run_formulation_equals_the_kmer_index(hostlib, seed):
+    """the fast pass alone: the index-free "diagonal run" formulation that the GPU kernel implements (here its scalar stand-in in
+    oracle/host_shim.cpp) against the product's host k-mer index path (the reference's algorithm, pinned end to end above), on regions built to
+    hit the order-dependent rules: equal-score placements, clamped starts, dropped haplotypes, N, tiny reads and haplotypes"""
+    regions = w.fastpass_adversarial(10, seed=seed) + w.config3(2, seed=seed, max_reads=80, max_haps=6, n_frac=0.002)
+    s0, p0, _ = R.fastpass_only(regions, 0, hostlib)
+    s1, p1, _ = R.fastpass_only(regions, 1, hostlib)
+    assert s0 == s1
+    assert p0 == p1
+    assert sum(1 for x in s1 if x > 0) > 10 and sum(1 for x in p1[1::2] if x >= 0) > 100

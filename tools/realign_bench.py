@@ -27,8 +27,16 @@ out = {"regions": n, "reads": reads, "ssw_pairs": st["pairs"], "ssw_cells": st["
        "per_region_ms": {"p50": 1e3 * lat[len(lat) // 2], "p95": 1e3 * lat[int(len(lat) * 0.95)], "sum_s": t_single},
        "batched_s": t_many, "batched_first_call_s": t_cold, "batched_packed_s": t_packed, "batched_packed_reads_per_s": reads / t_packed, "batched_split_s": {k: st[k] for k in ("fast_pass_s", "gpu_s", "compose_s")},
        "batched_gcups_ssw_only": st["cells"] / max(st["gpu_s"], 1e-9) / 1e9, "batched_reads_per_s": reads / t_many}
+import ctypes
+L = R.load(); L.mpn_realign_last_fastpass_kernel_ms.restype = ctypes.c_double
+out["fastpass_kernel_ms"] = L.mpn_realign_last_fastpass_kernel_ms()
+# the fast pass alone, both placements of the step: GPU kernel (copies and result marshalling included) vs host k-mer index on all cores
+t0 = time.perf_counter(); s0, p0, kms = R.fastpass_only(regions, 0); out["fastpass_only_gpu_s"] = time.perf_counter() - t0
+t0 = time.perf_counter(); s1, p1, _ = R.fastpass_only(regions, 1); out["fastpass_only_host_s"] = time.perf_counter() - t0
+out["fastpass_identical"] = (s0 == s1 and p0 == p1)
+out["fastpass_hap_read_pairs"] = len(p0) // 2
 ref = os.path.join(ROOT, "oracle", "_ref", "realigner_ref")
-if os.path.exists(ref):
+if os.path.exists(ref) and "noref" not in sys.argv:
     t0 = time.perf_counter()
     p = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "ref_realigner_runner.py"), ref], input=json.dumps([dataclasses.asdict(r) for r in regions]).encode(), capture_output=True, check=True)
     t_ref = time.perf_counter() - t0
