@@ -827,6 +827,12 @@ extern "C" int mpn_fastpass(mpn_engine* e, const char* text, int64_t text_bytes,
         nplaces = std::max<int64_t>(nplaces, rg.place_first + (int64_t)rg.nhap * rg.nread);
     }
     for (const FpHap& h : haps) if (h.region < 0) return MPN_E_ARG;          // every haplotype belongs to a region
+    // one block per haplotype, heaviest (reads x length) first so that the last wave of blocks is the light one
+    std::stable_sort(haps.begin(), haps.end(), [&](const FpHap& a, const FpHap& b) {
+        return (int64_t)regions[a.region].nread * (a.len + 256) > (int64_t)regions[b.region].nread * (b.len + 256); });
+    static const bool timing = getenv("MPN_TIMING") != nullptr;
+    auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t0 = now();
     CK(cudaSetDevice(e->device));
     cudaStream_t st = e->stream;
     if (!e->fp_attr_done) {
@@ -863,6 +869,8 @@ extern "C" int mpn_fastpass(mpn_engine* e, const char* text, int64_t text_bytes,
     CK(cudaStreamSynchronize(st));
     CK(cudaEventElapsedTime(&e->fp_kernel_ms, e->fp_ev[0], e->fp_ev[1]));
     for (int g = 0; g < nregions; ++g) region_flag[g] = flags[(size_t)g] ? 1 : 0;
+    if (timing) fprintf(stderr, "[mpn_ssw] fast pass: %d haplotypes x reads of %d regions, %lld placements, text %.1f MB: call %.3f ms, kernel %.3f ms\n",
+                        nhaps, nregions, (long long)nplaces, text_bytes / 1e6, now() - t0, e->fp_kernel_ms);
     return 0;
 }
 

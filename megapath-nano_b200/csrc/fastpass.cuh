@@ -59,7 +59,7 @@ fastpass_kernel(const char* __restrict__ text, const FpHap* __restrict__ haps, c
 
     if (L < FP_K) {                          // realigner.cpp:176 loops over an unsigned bound that wraps; nothing can be placed
         for (int r = tid; r < rg.nread; r += FP_BLOCK) my_places[r] = make_int2(0, -1);
-        if (tid == 0) hap_score[blockIdx.x] = 0;
+        if (tid == 0) hap_score[rg.hap_first + hp.local] = 0;
         return;
     }
     const int nhw = fp_hap_words(L);
@@ -117,33 +117,49 @@ fastpass_kernel(const char* __restrict__ text, const FpHap* __restrict__ haps, c
         for (int q = d_lo >> 5; q <= (d_hi >> 5); ++q) {
             const int D = 32 * q + lane, d = D - FP_PAD;
             int mism = 0, first_o = -1;
-            uint32_t eprev = 0u;
+            // Filter: a 32-base run contains a whole aligned 16-base block, so on a diagonal with a run some half word of
+            // (plane 0 differs | plane 1 differs) is zero.  Two loads and five integer instructions per word decide that for almost every
+            // diagonal; one VIMNMX3 per two words tracks the smallest half word; only the few diagonals that pass (and diagonal 0, whose mismatch count the start-0 rule needs) take the exact path below.
+            uint32_t lowest = 0xffffffffu;                       // per half word: minimum over the words of the diagonal (VIMNMX3.U16x2)
 #pragma unroll
-            for (int w = 0; w <= FP_READ_WORDS; ++w) {
-                if (w <= nw) {                                   // warp-uniform
-                    uint32_t e = 0u;
-                    if (w < nw) {
-                        const uint32_t h0 = hs0[(q + w) * 32], h1 = hs1[(q + w) * 32], h2 = hs2[(q + w) * 32];
-                        const uint32_t x0 = r0[w < FP_READ_WORDS ? w : 0] ^ h0, x1 = r1[w < FP_READ_WORDS ? w : 0] ^ h1, x2 = r2[w < FP_READ_WORDS ? w : 0] ^ h2;
-                        e = ~(x0 | x1 | x2);
-                        uint32_t m = (x0 | x1) & ~(r2[w < FP_READ_WORDS ? w : 0] | h2);
-                        if (w == nw - 1) { e &= tail; m &= tail; }
-                        mism += __popc(m);
-                    }
-                    if (w > 0 && eprev != 0u) {
-                        // 32-base windows that start at bit b of word w-1: its top 32-b bits and the low b bits of word w are all equal
-                        const int hi = __clz((int)~eprev), lo = (e == 0xffffffffu) ? 32 : (__ffs((int)~e) - 1);
-                        const int b_min = 32 - hi, b_max = min(31, lo);
-                        if (hi > 0 && b_min <= b_max) {
-                            const int o_a = 32 * (w - 1) + b_min, o_b = 32 * (w - 1) + b_max;
-                            if (first_o < 0) first_o = o_a;
-                            const int i_a = d + o_a, cnt = o_b - o_a + 1;                    // hap positions i_a .. i_a + cnt - 1 share a 32-mer with this read
-                            const unsigned long long bits = ((cnt >= 64 ? 0ull : (1ull << cnt)) - 1ull) << (i_a & 31);
-                            atomicOr(&occ[i_a >> 5], (uint32_t)bits);
-                            if ((uint32_t)(bits >> 32)) atomicOr(&occ[(i_a >> 5) + 1], (uint32_t)(bits >> 32));
+            for (int w = 0; w < FP_READ_WORDS; w += 2) {
+                if (w < nw) {                                    // warp-uniform
+                    const uint32_t xa = (r0[w] ^ hs0[(q + w) * 32]) | (r1[w] ^ hs1[(q + w) * 32]);
+                    uint32_t xb = 0xffffffffu;
+                    if (w + 1 < nw) xb = (r0[w + 1] ^ hs0[(q + w + 1) * 32]) | (r1[w + 1] ^ hs1[(q + w + 1) * 32]);
+                    lowest = __vimin3_u16x2(lowest, xa, xb);
+                }
+            }
+            const bool maybe = (lowest & 0xffffu) == 0u || (lowest >> 16) == 0u;
+            if (maybe || d == 0) {
+                uint32_t eprev = 0u;
+#pragma unroll
+                for (int w = 0; w <= FP_READ_WORDS; ++w) {
+                    if (w <= nw) {                               // warp-uniform
+                        uint32_t e = 0u;
+                        if (w < nw) {
+                            const uint32_t h0 = hs0[(q + w) * 32], h1 = hs1[(q + w) * 32], h2 = hs2[(q + w) * 32];
+                            const uint32_t x0 = r0[w < FP_READ_WORDS ? w : 0] ^ h0, x1 = r1[w < FP_READ_WORDS ? w : 0] ^ h1, x2 = r2[w < FP_READ_WORDS ? w : 0] ^ h2;
+                            e = ~(x0 | x1 | x2);
+                            uint32_t m = (x0 | x1) & ~(r2[w < FP_READ_WORDS ? w : 0] | h2);
+                            if (w == nw - 1) { e &= tail; m &= tail; }
+                            mism += __popc(m);
                         }
+                        if (w > 0 && eprev != 0u) {
+                            // 32-base windows that start at bit b of word w-1: its top 32-b bits and the low b bits of word w are all equal
+                            const int hi = __clz((int)~eprev), lo = (e == 0xffffffffu) ? 32 : (__ffs((int)~e) - 1);
+                            const int b_min = 32 - hi, b_max = min(31, lo);
+                            if (hi > 0 && b_min <= b_max) {
+                                const int o_a = 32 * (w - 1) + b_min, o_b = 32 * (w - 1) + b_max;
+                                if (first_o < 0) first_o = o_a;
+                                const int i_a = d + o_a, cnt = o_b - o_a + 1;                // hap positions i_a .. i_a + cnt - 1 share a 32-mer with this read
+                                const unsigned long long bits = ((1ull << cnt) - 1ull) << (i_a & 31);
+                                atomicOr(&occ[i_a >> 5], (uint32_t)bits);
+                                if ((uint32_t)(bits >> 32)) atomicOr(&occ[(i_a >> 5) + 1], (uint32_t)(bits >> 32));
+                            }
+                        }
+                        eprev = e;
                     }
-                    eprev = e;
                 }
             }
             if (d == 0) zero_mism = mism;
@@ -202,7 +218,7 @@ fastpass_kernel(const char* __restrict__ text, const FpHap* __restrict__ haps, c
             if (i >= rg.prefix && (unsigned long long)i < limit && ((occ[i >> 5] >> (i & 31)) & 1u) && cov[i] > i) s_drop = 1;
     }
     __syncthreads();
-    if (tid == 0) hap_score[blockIdx.x] = s_drop ? 0 : s_acc;
+    if (tid == 0) hap_score[rg.hap_first + hp.local] = s_drop ? 0 : s_acc;
     if (other) atomicOr(&region_flag[hp.region], 1);
 }
 

@@ -295,12 +295,16 @@ void fast_pass(Region& rg, bool threads)
     if (threads) mpn::parallel_for(nh, 1, one); else for (int h = 0; h < nh; ++h) one(h);
 }
 
+double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
 // The fast pass of many regions in one GPU call (mpn_fastpass, include/mpn_ssw_batch.h).  Regions the kernel does not take -- reads
 // longer than 256 bases, haplotypes longer than 2816, bases other than A,C,G,T,N (the kernel's 3-bit alphabet; the reference compares
 // raw characters) -- keep the string-exact host pass above, which is the placement the reference itself has for this step.
 void fast_pass_regions(std::vector<Region>& rgs, double* kernel_ms)
 {
     const int nr = (int)rgs.size();
+    static const bool timing = getenv("MPN_TIMING") != nullptr;
+    const double t_in = now_s();
     static const bool force_host = getenv("MPN_FASTPASS_HOST") != nullptr;      // A/B timing of the two placements of this step
     std::vector<char> on_gpu((size_t)nr, force_host ? 0 : 1);
     mpn::parallel_for(nr, 4, [&](int64_t g) {
@@ -328,11 +332,15 @@ void fast_pass_regions(std::vector<Region>& rgs, double* kernel_ms)
         nplaces += (int64_t)f.nhap * f.nread;
         fr.push_back(f); region_of.push_back(g);
     }
-    std::vector<mpn_placement> places((size_t)nplaces);
+    // grow-only buffers kept across calls: fresh allocations of this size cost more in page faults than the copies themselves
+    static thread_local std::vector<mpn_placement> places;
+    static thread_local std::vector<char> text_buf;
+    if (places.size() < (size_t)nplaces) places.resize((size_t)nplaces);
     std::vector<int32_t> hap_score(hap_start.size());
     std::vector<uint8_t> flag(fr.size(), 0);
     if (!fr.empty()) {
-        std::unique_ptr<char[]> text(new char[(size_t)bytes + 1]);
+        if (text_buf.size() < (size_t)bytes + 1) text_buf.resize((size_t)bytes + 1);
+        struct { std::vector<char>* v; char* get() const { return v->data(); } } text{&text_buf};
         {
             std::vector<int64_t> at(src.size());
             int64_t b = 0;
@@ -346,6 +354,7 @@ void fast_pass_regions(std::vector<Region>& rgs, double* kernel_ms)
         if (rc != 0) { fprintf(stderr, "[realigner] mpn_fastpass failed (code %d)\n", rc); abort(); }
         if (kernel_ms) *kernel_ms = mpn_fastpass_last_kernel_ms(lk.engine());
     }
+    const double t_gpu = now_s();
     std::vector<int> slot_of((size_t)nr, -1);
     for (size_t k = 0; k < region_of.size(); ++k) slot_of[(size_t)region_of[k]] = flag[k] ? -1 : (int)k;
     mpn::parallel_for(nr, 1, [&](int64_t g) {
@@ -364,6 +373,7 @@ void fast_pass_regions(std::vector<Region>& rgs, double* kernel_ms)
                 if (pl[r].score > 0) { rec.reads[(size_t)r].score = pl[r].score; rec.reads[(size_t)r].pos = pl[r].pos; rec.reads[(size_t)r].cigar = std::to_string(rg.reads[(size_t)r].size()) + "="; }
         }
     });
+    if (timing) fprintf(stderr, "[realigner] fast pass of %d regions: through the GPU call %.3f ms, records %.3f ms\n", nr, 1e3 * (t_gpu - t_in), 1e3 * (now_s() - t_gpu));
 }
 
 // which (read, haplotype) pairs need Smith-Waterman (realigner.cpp:351-366)
@@ -501,7 +511,6 @@ bool best_haplotype(const Region& rg, int read, int* best)
 struct Stats { long long pairs = 0, cells = 0; double t_fast = 0, t_gpu = 0, t_compose = 0, fp_kernel_ms = 0; };
 Stats g_last;
 
-double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 void load_region(Region& rg, const mpn_region& in)
 {
@@ -528,10 +537,13 @@ int realign_many(const mpn_region* regions, int nregions, struct_str_arr** out)
     Stats st;
     double t0 = now_s();
     // ---- 1. k-mer fast pass (GPU), then the list of Smith-Waterman pairs of every region
-    for (int r = 0; r < nregions; ++r) load_region(rgs[r], regions[r]);
+    mpn::parallel_for(nregions, 1, [&](int64_t r) { load_region(rgs[(size_t)r], regions[r]); });
+    const double t_loaded = now_s();
     // every (haplotype, read) of every region in one kernel launch; then the Smith-Waterman work list per region
     fast_pass_regions(rgs, &st.fp_kernel_ms);
+    const double t_fp = now_s();
     mpn::parallel_for(nregions, 1, [&](int64_t r) { plan_read_pairs(rgs[(size_t)r]); });
+    if (getenv("MPN_TIMING")) fprintf(stderr, "[realigner] load %.3f ms, fast pass %.3f ms, plan %.3f ms\n", 1e3 * (t_loaded - t0), 1e3 * (t_fp - t_loaded), 1e3 * (now_s() - t_fp));
     // sequence pool: per region the reference, its haplotypes and its reads, each once; pairs name them by index
     std::vector<SeqView> pool;
     std::vector<PairIndex> pairs;
