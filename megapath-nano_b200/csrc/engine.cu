@@ -148,7 +148,7 @@ struct mpn_batch {
     Score16 sc16{};
     FinishParams fin{};
     // device
-    DevBuf seq, mask, tasks_fwd, tasks_rev, ends_fwd, ends_rev, colrec, fwdres, finalres, counters, dmat, scratch, cig, wide_boundary, long_boundary, warp_dir, bandrec, flaglist, bandq_items, bandq_meta;
+    DevBuf seq, mask, tasks_fwd, tasks_rev, ends_fwd, ends_rev, colrec, fwdres, finalres, counters, dmat, scratch, cig, wide_boundary, long_boundary, warp_dir, bandrec, flaglist, bandq_items, bandq_meta, relist;
     size_t seq_reads_bytes = 0, seq_bytes = 0;
     int64_t colrec_words = 0;
     unsigned long long scratch_bytes = 0, cig_cap = 0;
@@ -258,7 +258,7 @@ extern "C" void mpn_batch_free(mpn_batch* b)
     if (!b) return;
     cudaSetDevice(b->e->device);
     DevBuf* bufs[] = {&b->seq, &b->mask, &b->tasks_fwd, &b->tasks_rev, &b->ends_fwd, &b->ends_rev,
-                      &b->colrec, &b->fwdres, &b->finalres, &b->counters, &b->dmat, &b->scratch, &b->cig, &b->wide_boundary, &b->long_boundary, &b->warp_dir, &b->bandrec, &b->flaglist, &b->bandq_items, &b->bandq_meta};
+                      &b->colrec, &b->fwdres, &b->finalres, &b->counters, &b->dmat, &b->scratch, &b->cig, &b->wide_boundary, &b->long_boundary, &b->warp_dir, &b->bandrec, &b->flaglist, &b->bandq_items, &b->bandq_meta, &b->relist};
     for (DevBuf* d : bufs) b->e->pool.give(*d);
     delete b;
 }
@@ -429,6 +429,7 @@ static mpn_batch* upload_impl(mpn_engine* e, int slot_id, const mpn_params* p, c
     pool.take(b->fwdres, sizeof(FwdResult) * (size_t)(npairs + 1)); pool.take(b->finalres, sizeof(FinalResult) * (size_t)(npairs + 1));
     pool.take(b->counters, 512 * sizeof(unsigned long long));   // [0,128) misc (arena cursors at 64/65, task cursors at 100..104), [128,256) forward bins, [256,384) reverse bins
     pool.take(b->dmat, (size_t)n * n + 16);
+    pool.take(b->relist, 2 * sizeof(int) * (size_t)(npairs + 2));       // pairs refused by the packed kernel (reads with N): [count, task indices...] per pass
     if (npairs) {
         src.copy_arena(b->seq.as<int8_t>(), st);
         CK(cudaGetLastError());
@@ -511,6 +512,13 @@ extern "C" int mpn_align_batch_spans(mpn_engine* e, const mpn_params* p, const i
     return rc;
 }
 
+// list of the pairs the packed kernel refuses (reads with N) for the N variants to walk; nullptr when those variants do not apply
+static int* relist_of(mpn_batch* b, bool forward)
+{
+    if (!b->sc16.ncol_ok) return nullptr;
+    return b->relist.as<int>() + (forward ? 0 : b->npairs + 2);
+}
+
 static void launch_strips(mpn_batch* b, const SwTask* tasks, bool forward, SwEnds* ends, int counter_base)
 {
     mpn_engine* e = b->e;
@@ -547,7 +555,7 @@ static void launch_strips(mpn_batch* b, const SwTask* tasks, bool forward, SwEnd
             int64_t blocks = (bl.count + groups_per_block - 1) / groups_per_block;
             blocks = std::min<int64_t>(blocks, (int64_t)e->sm_count * c.blocks_per_sm);
             (forward ? c.fn : c.fn_rev)<<<(unsigned)blocks, STRIP_BLOCK_THREADS, c.smem, st>>>(tasks + bl.first, (int)bl.count, counter, b->seq.as<int8_t>(), b->sc16,
-                                                                  forward ? b->colrec.as<uint32_t>() : nullptr, ends);
+                                                                  forward ? b->colrec.as<uint32_t>() : nullptr, ends, relist_of(b, forward), (int)bl.first);
         }
         CK(cudaGetLastError());
         e->launches++;
@@ -560,6 +568,28 @@ static void launch_strips(mpn_batch* b, const SwTask* tasks, bool forward, SwEnd
     }
 }
 
+// re-run of the listed pairs in the N variants of the packed kernel (one per group width, each takes its length class)
+static void launch_n_variants(mpn_batch* b, const SwTask* tasks, bool forward, SwEnds* ends, int counter_base)
+{
+    int* relist = relist_of(b, forward);
+    if (!relist) return;
+    mpn_engine* e = b->e;
+    const StripEntry* nv[4] = {&g_strip_n_a, &g_strip_n_b, &g_strip_n_c, &g_strip_n_d};
+    int min_len = 0;
+    for (int k = 0; k < 4; ++k) {
+        const StripEntry& c = *nv[k];
+        const int cap = 2 * c.G * c.KR;
+        if (b->max_rd > min_len) {
+            int* counter = reinterpret_cast<int*>(b->counters.as<unsigned long long>() + counter_base + k);
+            (forward ? c.fn : c.fn_rev)<<<(unsigned)(e->sm_count * 2), STRIP_BLOCK_THREADS, c.smem, b->st>>>(tasks, 0, counter, b->seq.as<int8_t>(), b->sc16,
+                                                                  forward ? b->colrec.as<uint32_t>() : nullptr, ends, relist, min_len);
+            CK(cudaGetLastError());
+            e->launches++;
+        }
+        min_len = cap;
+    }
+}
+
 extern "C" int mpn_batch_run(mpn_batch* b)
 {
     if (!b) return MPN_E_ARG;
@@ -569,12 +599,18 @@ extern "C" int mpn_batch_run(mpn_batch* b)
     const int64_t n = b->npairs;
     if (n == 0) { b->ran = true; return 0; }
     CK(cudaMemsetAsync(b->counters.p, 0, 512 * sizeof(unsigned long long), st));
+    if (b->sc16.ncol_ok) {
+        CK(cudaMemsetAsync(relist_of(b, true), 0, sizeof(int), st));
+        CK(cudaMemsetAsync(relist_of(b, false), 0, sizeof(int), st));
+    }
     PairArrays pa{b->mask.as<int32_t>()};
 
     if (e->profile) { CK(cudaEventRecord(e->ev[0], st)); e->ev_valid = 1; }
     // forward score pass -> ends + column records
     launch_strips(b, b->tasks_fwd.as<SwTask>(), true, b->ends_fwd.as<SwEnds>(), 128);
-    // pairs the packed kernel refused (read code >= 4) are re-run in the 32-bit kernel before anything reads their ends
+    // pairs the packed kernel refused (read code >= 4): its N variants take reads with N when the matrix's N column is constant,
+    // whatever is still flagged after that is re-run in the 32-bit kernel before anything reads the ends
+    launch_n_variants(b, b->tasks_fwd.as<SwTask>(), true, b->ends_fwd.as<SwEnds>(), 110);
     launch_wide32_impl(b->tasks_fwd.as<SwTask>(), (int)n, reinterpret_cast<int*>(b->counters.as<unsigned long long>() + 100),
                        b->seq.as<int8_t>(), b->dmat.as<int8_t>(), b->p.n, b->fin.gapO, b->fin.gapE, b->colrec.as<uint32_t>(), b->ends_fwd.as<SwEnds>(),
                        b->wide_boundary.as<int>(), b->wide_stride, b->wide_blocks, 1, b->max_rd <= 512, st);
@@ -594,6 +630,7 @@ extern "C" int mpn_batch_run(mpn_batch* b)
     const bool any_rev = !(b->fin.flag == 0);
     if (any_rev) {
         launch_strips(b, b->tasks_rev.as<SwTask>(), false, b->ends_rev.as<SwEnds>(), 256);
+        launch_n_variants(b, b->tasks_rev.as<SwTask>(), false, b->ends_rev.as<SwEnds>(), 114);
         launch_wide32_impl(b->tasks_rev.as<SwTask>(), (int)n, reinterpret_cast<int*>(b->counters.as<unsigned long long>() + 101),
                            b->seq.as<int8_t>(), b->dmat.as<int8_t>(), b->p.n, b->fin.gapO, b->fin.gapE, nullptr, b->ends_rev.as<SwEnds>(),
                            b->wide_boundary.as<int>(), b->wide_stride, b->wide_blocks, 1, b->max_rd <= 512, st);

@@ -336,21 +336,22 @@ void fast_pass_regions(std::vector<Region>& rgs, double* kernel_ms)
     static thread_local std::vector<mpn_placement> places;
     static thread_local std::vector<char> text_buf;
     if (places.size() < (size_t)nplaces) places.resize((size_t)nplaces);
+    mpn_placement* const places_p = places.data();       // thread_local: worker threads must not name `places` themselves
     std::vector<int32_t> hap_score(hap_start.size());
     std::vector<uint8_t> flag(fr.size(), 0);
     if (!fr.empty()) {
         if (text_buf.size() < (size_t)bytes + 1) text_buf.resize((size_t)bytes + 1);
-        struct { std::vector<char>* v; char* get() const { return v->data(); } } text{&text_buf};
+        char* const text_p = text_buf.data();
         {
             std::vector<int64_t> at(src.size());
             int64_t b = 0;
             for (size_t k = 0; k < src.size(); ++k) { at[k] = b; b += (int64_t)src[k]->size(); }
-            mpn::parallel_for((int64_t)src.size(), 256, [&](int64_t k) { memcpy(text.get() + at[(size_t)k], src[(size_t)k]->data(), src[(size_t)k]->size()); });
+            mpn::parallel_for((int64_t)src.size(), 256, [&](int64_t k) { memcpy(text_p + at[(size_t)k], src[(size_t)k]->data(), src[(size_t)k]->size()); });
         }
         mpn::SharedEngineLock lk;
-        const int rc = mpn_fastpass(lk.engine(), text.get(), bytes, hap_start.data(), hap_len.data(), is_ref.data(), (int32_t)hap_start.size(),
+        const int rc = mpn_fastpass(lk.engine(), text_p, bytes, hap_start.data(), hap_len.data(), is_ref.data(), (int32_t)hap_start.size(),
                                     read_start.data(), read_len.data(), (int32_t)read_start.size(), fr.data(), (int32_t)fr.size(),
-                                    places.data(), hap_score.data(), flag.data());
+                                    places_p, hap_score.data(), flag.data());
         if (rc != 0) { fprintf(stderr, "[realigner] mpn_fastpass failed (code %d)\n", rc); abort(); }
         if (kernel_ms) *kernel_ms = mpn_fastpass_last_kernel_ms(lk.engine());
     }
@@ -368,7 +369,7 @@ void fast_pass_regions(std::vector<Region>& rgs, double* kernel_ms)
             rec.index = h; rec.score = hap_score[(size_t)(f.hap_first + h)];
             rec.reads.assign((size_t)f.nread, Placement());
             if (rec.score == 0) continue;                    // dropped or nothing placed: every read stays unplaced (realigner.cpp:160-165)
-            const mpn_placement* pl = places.data() + f.place_first + (int64_t)h * f.nread;
+            const mpn_placement* pl = places_p + f.place_first + (int64_t)h * f.nread;
             for (int r = 0; r < f.nread; ++r)
                 if (pl[r].score > 0) { rec.reads[(size_t)r].score = pl[r].score; rec.reads[(size_t)r].pos = pl[r].pos; rec.reads[(size_t)r].cigar = std::to_string(rg.reads[(size_t)r].size()) + "="; }
         }

@@ -24,7 +24,6 @@
 #pragma once
 #include "sw_common.cuh"
 #include <cstdio>
-#include <type_traits>
 
 namespace mpn {
 
@@ -38,18 +37,27 @@ constexpr int STRIP_UNROLL = MPN_STRIP_UNROLL;
 #define MPN_STRIP_MINB 4
 #endif
 
-// shared memory: H-column snapshots [2 halves][ceil(KR/4)][STRIP_BLOCK] uint4, the column-record staging [G][STRIP_BLOCK] words, and the
-// per-row score fix-up selectors [KR][STRIP_BLOCK] used while a warp holds a read with N (see the N mode below)
-template <int KR, int G>
-__host__ __device__ constexpr size_t strip16_smem_bytes() { return (size_t)2 * ((KR + 3) / 4) * STRIP_BLOCK * sizeof(uint4) + (size_t)(G + KR) * STRIP_BLOCK * sizeof(uint32_t); }
+// shared memory: H-column snapshots [2 halves][ceil(KR/4)][STRIP_BLOCK] uint4, the column-record staging [G][STRIP_BLOCK] words and, in
+// the N variant only, the per-row score fix-up selectors [KR][STRIP_BLOCK]
+template <int KR, int G, bool NM = false>
+__host__ __device__ constexpr size_t strip16_smem_bytes() { return (size_t)2 * ((KR + 3) / 4) * STRIP_BLOCK * sizeof(uint4) + (size_t)(G + (NM ? KR : 0)) * STRIP_BLOCK * sizeof(uint32_t); }
 
 // REV = false: forward passes (column records written, no early end).  REV = true: reverse passes (ssw.c:820-832): no column records, the
 // pass ends once the terminating score has been seen, and only a stage that REACHES that score can be the winner, so the H-column
 // snapshots sit behind a warp-uniform branch that is taken a handful of times per pair instead of being issued (predicated off) every step.
-template <int KR, int G, bool REV>
+//
+// NM = false: the kernel every pair goes through.  A read that contains N (code 4) cannot be scored by the one-PRMT lookup (the 4-byte
+// matrix rows have no slot for a fifth read code): the pair is flagged and its task index appended to `relist` (relist[0] = count).
+// NM = true: the re-run of those pairs.  When the matrix's N column is one constant c (both matrix builders of the reference:
+// ssw_cpp.cpp:23-48, pyssw.py:61-79) every row gets a second PRMT that swaps its half of the looked-up score for c where the read has
+// an N (selector in shared memory, identity elsewhere).  This variant walks `relist` instead of a task range (`tasks` is then the whole
+// task array and `aux` the largest read length a smaller N variant already took); pairs it cannot take either (codes above 4) stay
+// flagged for the int32 kernel.  Keeping the N code out of the main instantiation keeps its inner loop at the 146 instructions per step
+// it had before (the switchable version cost 3 % on reads without N).
+template <int KR, int G, bool REV, bool NM = false>
 __global__ void __launch_bounds__(STRIP_BLOCK, MPN_STRIP_MINB)
 sw_strip16_kernel(const SwTask* __restrict__ tasks, int ntasks, int* __restrict__ counter, const int8_t* __restrict__ seq,
-                  const Score16 sc, uint32_t* __restrict__ colrec, SwEnds* __restrict__ out)
+                  const Score16 sc, uint32_t* __restrict__ colrec, SwEnds* __restrict__ out, int* __restrict__ relist, int aux)
 {
     static_assert(KR >= 2, "KR too small");
     constexpr int KRQ = (KR + 3) / 4;             // snapshot quads per half
@@ -57,11 +65,7 @@ sw_strip16_kernel(const SwTask* __restrict__ tasks, int ntasks, int* __restrict_
     constexpr int CAP = 2 * G * KR;               // rows covered by one strip
     extern __shared__ uint4 snap[];               // [2 halves][KRQ][STRIP_BLOCK]: H column of a stage at its last improvement
     uint32_t* const crow = reinterpret_cast<uint32_t*>(snap + 2 * KRQ * STRIP_BLOCK);   // [G][STRIP_BLOCK]: column records of the last G steps
-    // N mode.  The score PRMT picks mat[t][q] out of the 4-byte matrix rows of the two target bases: there is no slot for a fifth read
-    // code.  When the N column of the matrix is one constant c (sc.ncol_ok), rows holding an N get a second PRMT that replaces their
-    // half of the looked-up score by c; its selector sits in shared memory (identity for ordinary rows).  Only warps that currently hold
-    // such a read run this variant of the step (warp-uniform switch), everybody else runs the plain one.
-    uint32_t* const nfix = crow + G * STRIP_BLOCK;                                        // [KR][STRIP_BLOCK]
+    uint32_t* const nfix = crow + G * STRIP_BLOCK;                                        // NM only: [KR][STRIP_BLOCK] fix-up selectors
 
     // the 8 matrix rows are looked up by a run-time target code: shared memory (one LDS) instead of the by-value parameter struct
     // (which ptxas can only index with a chain of predicated constant loads)
@@ -87,7 +91,7 @@ sw_strip16_kernel(const SwTask* __restrict__ tasks, int ntasks, int* __restrict_
     uint32_t stop2 = 0;                           // reverse passes: score at which the pass may end, in both halves (0: never)
     int64_t rf_base = 0, cm_off = -1;
     bool active = true;                           // group still has (or may fetch) a task
-    bool has_n = false, nfix_stale = true;        // this thread's rows hold an N / its nfix entries are not the identity (or never written)
+    const int relist_n = NM ? relist[0] : 0;      // NM: number of flagged pairs to walk
 
 #pragma unroll
     for (int j = 0; j < KR; ++j) { H[j] = 0; E[j] = 0; sel[j] = 0x8888u | 0x4400u; }
@@ -159,10 +163,25 @@ sw_strip16_kernel(const SwTask* __restrict__ tasks, int ntasks, int* __restrict_
             }
             // ---- fetch the next task of this group
             int ti = 0;
-            if (t == 0) ti = atomicAdd(counter, 1);
-            ti = __shfl_sync(gmask, ti, lane - t);
-            if (ti >= ntasks) {
-                active = false; has_n = false;
+            bool have = false;
+            if (NM) {
+                // walk the list of flagged pairs: take those of this variant's length class that are still flagged
+                for (;;) {
+                    int k = 0;
+                    if (t == 0) k = atomicAdd(counter, 1);
+                    k = __shfl_sync(gmask, k, lane - t);
+                    if (k >= relist_n) break;
+                    ti = relist[1 + k];
+                    const int len = tasks[ti].rd_len;
+                    if (len > aux && len <= CAP && (out[tasks[ti].out].flags & SW_FLAG_NEEDS_WIDE)) { have = true; break; }
+                }
+            } else {
+                if (t == 0) ti = atomicAdd(counter, 1);
+                ti = __shfl_sync(gmask, ti, lane - t);
+                have = ti < ntasks;
+            }
+            if (!have) {
+                active = false;
                 rf_len = 0; nsteps = 0; cm_off = -1; stop2 = 0;
 #pragma unroll
                 for (int j = 0; j < KR; ++j) { H[j] = 0; E[j] = 0; sel[j] = 0x8888u | 0x4400u; }
@@ -176,7 +195,7 @@ sw_strip16_kernel(const SwTask* __restrict__ tasks, int ntasks, int* __restrict_
                 wide = 0;
                 // selectors: low half = row (2t)*KR + j, high half = row (2t+1)*KR + j, both minus the dead rows on top
                 const int r0 = 2 * t * KR - dead;                                // this thread's first row; it owns 2*KR consecutive rows
-                if (r0 >= 0 && rd_len <= CAP) {
+                if (!NM && r0 >= 0 && rd_len <= CAP) {
                     // common case, no dead row in this thread: the 2*KR read bases are one contiguous span -> a few aligned 64-bit loads
                     // instead of 2*KR byte loads.  Forward passes walk the read upwards (span starts at row r0), reverse passes downwards
                     // (span starts at the LAST row of the thread; row k sits at byte 2*KR-1-k).
@@ -187,51 +206,50 @@ sw_strip16_kernel(const SwTask* __restrict__ tasks, int ntasks, int* __restrict_
                     for (int q = 0; q < NWORD; ++q) wq[q] = load8_aligned(span + 8 * q, NB - 8 * q);
                     unsigned long long bad = 0;
 #pragma unroll
-                    for (int q = 0; q < NWORD; ++q) bad |= wq[q] & 0xfcfcfcfcfcfcfcfcull;          // any code >= 4 (N): 32-bit kernel
-                    has_n = bad != 0ull && sc.ncol_ok != 0u;
-                    if (bad != 0ull && !has_n) wide = 1;
+                    for (int q = 0; q < NWORD; ++q) bad |= wq[q] & 0xfcfcfcfcfcfcfcfcull;          // any code >= 4 (N): flagged, redone by the N variant or the 32-bit kernel
+                    if (bad != 0ull) wide = 1;
 #pragma unroll
                     for (int j = 0; j < KR; ++j) {
                         const int b_lo = REV ? NB - 1 - j : j, b_hi = REV ? NB - 1 - (j + KR) : j + KR;
-                        const uint32_t c_lo = (uint32_t)(wq[b_lo >> 3] >> (8 * (b_lo & 7))) & 0xffu, c_hi = (uint32_t)(wq[b_hi >> 3] >> (8 * (b_hi & 7))) & 0xffu;
-                        const uint32_t q_lo = c_lo & 3u, q_hi = c_hi & 3u;
+                        const uint32_t q_lo = (uint32_t)(wq[b_lo >> 3] >> (8 * (b_lo & 7))) & 3u, q_hi = (uint32_t)(wq[b_hi >> 3] >> (8 * (b_hi & 7))) & 3u;
                         sel[j] = (q_lo * 0x11u + 0x80u) | ((q_hi * 0x11u + 0xc4u) << 8);
                         H[j] = 0; E[j] = 0;
-                        if (has_n || nfix_stale) {
-                            if (c_lo > 4u || c_hi > 4u) wide = 1;                       // codes beyond N: not a DNA read
-                            nfix[j * STRIP_BLOCK + tid] = ((has_n && c_lo == 4u) ? 0x54u : 0x10u) | (((has_n && c_hi == 4u) ? 0x76u : 0x32u) << 8);
-                        }
                     }
-                    nfix_stale = has_n;
                 } else {
-                    has_n = false;
 #pragma unroll
                     for (int j = 0; j < KR; ++j) {
                         const int r_lo = 2 * t * KR + j - dead, r_hi = r_lo + KR;
                         uint32_t n_lo = 0x88u, n_hi = 0xccu;                      // dead row: sign bytes only -> score 0 or -1
-                        uint32_t fix = 0x3210u;
+                        uint32_t fix = 0x3210u;                                   // NM: identity = keep the looked-up score
                         if (r_lo >= 0) {
                             const int q = seq[tk.rd_base + (int64_t)tdir * r_lo];
                             if ((unsigned)q < 4u) n_lo = (uint32_t)q | ((uint32_t)(q | 8) << 4);
-                            else if (q == 4 && sc.ncol_ok != 0u) { fix = (fix & 0xff00u) | 0x54u; has_n = true; }
+                            else if (NM && q == 4) fix = (fix & 0xff00u) | 0x54u;      // low half <- the N column's constant
                             else wide = 1;
                         }
                         if (r_hi >= 0) {
                             const int q = seq[tk.rd_base + (int64_t)tdir * r_hi];
                             if ((unsigned)q < 4u) n_hi = (uint32_t)(q | 4) | ((uint32_t)(q | 12) << 4);
-                            else if (q == 4 && sc.ncol_ok != 0u) { fix = (fix & 0x00ffu) | 0x7600u; has_n = true; }
+                            else if (NM && q == 4) fix = (fix & 0x00ffu) | 0x7600u;    // high half <- the N column's constant
                             else wide = 1;
                         }
                         sel[j] = n_lo | (n_hi << 8);
                         H[j] = 0; E[j] = 0;
-                        nfix[j * STRIP_BLOCK + tid] = fix;
+                        if (NM) nfix[j * STRIP_BLOCK + tid] = fix;
                     }
-                    nfix_stale = has_n;
                 }
                 Ftop = Hdtop = cmin = a = b = best = 0; cvlo = cvhi = 0;
                 s = 0;
                 nsteps = (rf_len > 0 && rd_len > 0) ? rf_len + 2 * G - 1 : 1;
                 if (rd_len > CAP) { wide = 1; nsteps = 1; rf_len = 0; }      // host scheduling error: never index out of the strip
+                {   // a pair this variant cannot score is redone completely elsewhere: stop after one block of steps, and (main variant,
+                    // constant N column) put it on the list the N variants walk
+                    const unsigned refused = __ballot_sync(gmask, wide != 0);
+                    if (refused != 0u) {
+                        nsteps = 1; rf_len = 0;
+                        if (!NM && relist != nullptr && lane == __ffs((int)refused) - 1) relist[1 + atomicAdd(&relist[0], 1)] = aux + ti;
+                    }
+                }
                 {   // matrix rows of target chunk 0
                     const int idx = t;
                     uint32_t mr = 0;
@@ -252,12 +270,10 @@ sw_strip16_kernel(const SwTask* __restrict__ tasks, int ntasks, int* __restrict_
         }
 
         // ------------------------------------------------------------------ G wavefront steps ---------------------------
-        // one step, in two variants: NM = false looks the score up with one PRMT, NM = true adds the N fix-up (see nfix above)
-        auto step = [&](auto nm_tag, const int u) {
-            constexpr bool NM = decltype(nm_tag)::value;
+        auto step = [&](const int u) {
             auto score = [&](const int j) -> uint32_t {
                 const uint32_t v = prmt(a, b, sel[j]);
-                return NM ? prmt(v, sc.ncol2, nfix[j * STRIP_BLOCK + tid]) : v;
+                return NM ? prmt(v, sc.ncol2, nfix[j * STRIP_BLOCK + tid]) : v;      // N variant: rows holding an N take the N column's constant
             };
             {   // the first stage takes the next target base from the chunk, the others got theirs by shuffle last step
                 const uint32_t a0 = __shfl_sync(0xffffffffu, tchunk, u, G);
@@ -329,13 +345,8 @@ sw_strip16_kernel(const SwTask* __restrict__ tasks, int ntasks, int* __restrict_
             b = a;
             a = rA;
         };
-        if (__any_sync(0xffffffffu, has_n)) {
 #pragma unroll STRIP_UNROLL
-            for (int u = 0; u < G; ++u, ++s) step(std::true_type{}, u);
-        } else {
-#pragma unroll STRIP_UNROLL
-            for (int u = 0; u < G; ++u, ++s) step(std::false_type{}, u);
-        }
+        for (int u = 0; u < G; ++u, ++s) step(u);
         // ---- column records of the G steps just done: thread t of the group stores the one of step s - G + t (one 4*G-byte run per group)
         if (!REV) {
             __syncwarp();
