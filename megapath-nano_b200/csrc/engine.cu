@@ -778,10 +778,10 @@ extern "C" int mpn_align_batch(mpn_engine* e, const mpn_params* p, const int8_t*
                                const int64_t* ref_off, const int32_t* masklen, int64_t npairs, mpn_result* out, uint32_t* cigar, int64_t cigar_cap)
 {
     if (!e || npairs < 0) return MPN_E_ARG;
-    // Small batches: one chunk on the engine stream.  Large batches: chunks of ~128 k pairs alternate between two pipeline slots
+    // Small batches: one chunk on the engine stream.  Large batches: chunks of ~192 k pairs alternate between two pipeline slots
     // (own stream + own pinned staging each), so the H2D copies and host-side scheduling of chunk k+1 overlap the kernels of chunk k
     // and the D2H of chunk k-1.
-    static const int64_t CHUNK = []() { const char* v = getenv("MPN_CHUNK_PAIRS"); const long long c = v ? atoll(v) : 0; return c >= 1024 ? (int64_t)c : (int64_t)131072; }();
+    static const int64_t CHUNK = []() { const char* v = getenv("MPN_CHUNK_PAIRS"); const long long c = v ? atoll(v) : 0; return c >= 1024 ? (int64_t)c : (int64_t)196608; }();
     if (npairs <= CHUNK + CHUNK / 2) {
         mpn_batch* b = mpn_batch_upload(e, p, reads, read_off, refs, ref_off, masklen, npairs);
         if (!b) return MPN_E_ARG;
@@ -794,10 +794,13 @@ extern "C" int mpn_align_batch(mpn_engine* e, const mpn_params* p, const int8_t*
     // after a short upload instead of waiting for a full chunk to be scheduled and copied
     std::vector<int64_t> bounds(1, 0);
     {
-        int64_t at = 0;
-        for (int64_t want : {CHUNK / 4, CHUNK / 2}) if (npairs - at > 2 * CHUNK) { at += want; bounds.push_back(at); }
-        const int64_t rest = npairs - at, nrest = (rest + CHUNK - 1) / CHUNK, per = (rest + nrest - 1) / nrest;
-        while (at < npairs) { at = std::min(npairs, at + per); bounds.push_back(at); }
+        // ... and the last two are a half and a quarter, so little is left to copy back and convert after the last kernel ends
+        int64_t at = 0, tail = 0;
+        std::vector<int64_t> tail_sizes;
+        for (int64_t want : {CHUNK / 4, CHUNK / 2}) if (npairs - at - tail > 3 * CHUNK) { at += want; bounds.push_back(at); tail_sizes.push_back(want); tail += want; }
+        const int64_t rest = npairs - at - tail, nrest = (rest + CHUNK - 1) / CHUNK, per = (rest + nrest - 1) / nrest;
+        while (at < npairs - tail) { at = std::min(npairs - tail, at + per); bounds.push_back(at); }
+        for (size_t k = tail_sizes.size(); k-- > 0;) { at += tail_sizes[k]; bounds.push_back(at); }
     }
     const int64_t nchunks = (int64_t)bounds.size() - 1;
     // ring of in-flight chunks, one pipeline slot each (own stream + own pinned staging).  Several chunks are queued on the GPU at any

@@ -42,13 +42,29 @@ sw_wide32_kernel(const SwTask* __restrict__ tasks, int ntasks, int* __restrict__
     int* bF = boundary + wslot * 2 * boundary_stride + boundary_stride;                      // bottom-row F per column
     const int mgapO = -gapO, mgapE = -gapE;
 
+    // Task fetch.  Direct mode: one task per atomic.  Flagged-only mode (the re-run pass over ALL tasks of a batch, of which usually none is
+    // flagged): a warp takes 32 tasks per atomic, every lane checks one flag, and only the flagged ones are processed -- 1/32 of the atomics.
+    int chunk_base = 0;
+    unsigned chunk_todo = 0u;
     for (;;) {
         int ti = 0;
-        if (lane == 0) ti = atomicAdd(counter, 1);
-        ti = __shfl_sync(0xffffffffu, ti, 0);
-        if (ti >= ntasks) break;
+        if (only_flagged) {
+            while (chunk_todo == 0u) {
+                if (lane == 0) chunk_base = atomicAdd(counter, 32);
+                chunk_base = __shfl_sync(0xffffffffu, chunk_base, 0);
+                if (chunk_base >= ntasks) break;
+                const int mine = chunk_base + lane;
+                chunk_todo = __ballot_sync(0xffffffffu, mine < ntasks && (out[tasks[mine].out].flags & SW_FLAG_NEEDS_WIDE) != 0);
+            }
+            if (chunk_todo == 0u) break;
+            ti = chunk_base + __ffs((int)chunk_todo) - 1;
+            chunk_todo &= chunk_todo - 1u;
+        } else {
+            if (lane == 0) ti = atomicAdd(counter, 1);
+            ti = __shfl_sync(0xffffffffu, ti, 0);
+            if (ti >= ntasks) break;
+        }
         const SwTask tk = tasks[ti];
-        if (only_flagged && !(out[tk.out].flags & SW_FLAG_NEEDS_WIDE)) continue;
         const int rd_len = tk.rd_len, rf_len = tk.rf_len, dir = tk.dir;
         if (rd_len <= 0 || rf_len <= 0) {
             if (lane == 0) { SwEnds e; e.score = 0; e.col = -1; e.row = 0; e.flags = 0; out[tk.out] = e; }
