@@ -794,10 +794,14 @@ extern "C" int mpn_align_batch(mpn_engine* e, const mpn_params* p, const int8_t*
     // after a short upload instead of waiting for a full chunk to be scheduled and copied
     std::vector<int64_t> bounds(1, 0);
     {
-        // ... and the last two are a half and a quarter, so little is left to copy back and convert after the last kernel ends
+        // ... and the last ones shrink again, so little is left to copy back and convert after the last kernel ends
+        static const int LADDER = []() { const char* v = getenv("MPN_CHUNK_LADDER"); return v ? atoi(v) : 3; }();     // steps of the ramp at either end (A/B on config 2: 2 -> 75.6 ms, 3 -> 74.2 ms, 4 -> 79.9 ms per step)
         int64_t at = 0, tail = 0;
         std::vector<int64_t> tail_sizes;
-        for (int64_t want : {CHUNK / 4, CHUNK / 2}) if (npairs - at - tail > 3 * CHUNK) { at += want; bounds.push_back(at); tail_sizes.push_back(want); tail += want; }
+        for (int k = LADDER; k >= 1; --k) {
+            const int64_t want = CHUNK >> k;
+            if (want >= 4096 && npairs - at - tail > 3 * CHUNK) { at += want; bounds.push_back(at); tail_sizes.push_back(want); tail += want; }
+        }
         const int64_t rest = npairs - at - tail, nrest = (rest + CHUNK - 1) / CHUNK, per = (rest + nrest - 1) / nrest;
         while (at < npairs - tail) { at = std::min(npairs - tail, at + per); bounds.push_back(at); }
         for (size_t k = tail_sizes.size(); k-- > 0;) { at += tail_sizes[k]; bounds.push_back(at); }
