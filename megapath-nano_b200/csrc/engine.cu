@@ -12,8 +12,10 @@
 #include "sw_trace_warp.cuh"
 #include "sw_trace_rows.cuh"
 #include "fastpass.cuh"
+#include "host_shared.h"
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -711,7 +713,11 @@ static int fetch_impl(mpn_batch* b, mpn_result* out, uint32_t* cigar, int64_t ci
         CK(cudaMemcpyAsync(used, b->counters.as<unsigned long long>() + 64, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
         b->d2h_bytes += sizeof(FinalResult) * (size_t)n + 16;
     }
+    static const bool timing = getenv("MPN_TIMING_FETCH") != nullptr;
+    auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double tf0 = now();
     CK(cudaStreamSynchronize(st));
+    const double tf1 = now();
     int rc = 0;
     if (any_rev && (b->p.flag & 7)) {
         const unsigned long long words = std::min<unsigned long long>(used[1], b->cig_cap);
@@ -722,7 +728,10 @@ static int fetch_impl(mpn_batch* b, mpn_result* out, uint32_t* cigar, int64_t ci
     }
     const FwdResult* h_fwd = sl.pin_fwd.as<FwdResult>();
     const FinalResult* h_fin = sl.pin_fin.as<FinalResult>();
-    for (int64_t i = 0; i < n; ++i) {
+    // record conversion: independent per pair; on a few host threads for large chunks (it is the serial tail of mpn_align_batch's pipeline)
+    std::atomic<long long> first_bad(-1);
+    const bool report = b->arena_retries > 0;
+    auto convert = [&](int64_t i) {
         const FwdResult& f = h_fwd[i];
         mpn_result& r = out[i];
         r.score1 = (uint16_t)f.score1; r.score2 = (uint16_t)f.score2;
@@ -735,12 +744,22 @@ static int fetch_impl(mpn_batch* b, mpn_result* out, uint32_t* cigar, int64_t ci
             r.cigar_len = g.cigar_len; r.cigar_off = g.cigar_len > 0 ? g.cigar_off + cigar_base : 0;
             if (g.status == 3) r.status = MPN_ST_NULL;
             else if (g.status != 0) {
-                if (rc == 0 && (b->arena_retries > 0 || (g.status != 5 && g.status != 6))) fprintf(stderr, "[mpn_ssw] traceback could not complete (first at pair %lld, status %d: 5/6 = arena exhausted, 7/8 = band beyond kernel limits)\n", (long long)i, g.status);
-                rc = MPN_E_UNSUPPORTED;
+                long long none = -1;
+                if (report || (g.status != 5 && g.status != 6)) first_bad.compare_exchange_strong(none, (long long)i);
+                else { long long none2 = -1; first_bad.compare_exchange_strong(none2, -2 - (long long)i); }       // arena exhausted: silent on the first attempt
             }
         }
+    };
+    if (n >= 65536) mpn::parallel_for(n, 16384, convert, 4);
+    else for (int64_t i = 0; i < n; ++i) convert(i);
+    if (first_bad.load() != -1) {
+        rc = MPN_E_UNSUPPORTED;
+        const long long fb = first_bad.load();
+        if (fb >= 0) fprintf(stderr, "[mpn_ssw] traceback could not complete (at pair %lld, status %d: 5/6 = arena exhausted, 7/8 = band beyond kernel limits)\n", fb, h_fin[fb].status);
     }
+    const double tf2 = now();
     CK(cudaStreamSynchronize(st));      // CIGAR arena copy
+    if (timing) fprintf(stderr, "[mpn_ssw] fetch %lld pairs: wait %.3f ms, convert %.3f ms, cigar wait %.3f ms\n", (long long)n, tf1 - tf0, tf2 - tf1, now() - tf2);
     if (rc == MPN_E_UNSUPPORTED && b->arena_retries == 0) {
         // An arena of the traceback ran out (statuses 5 / 6: direction words or CIGAR words beyond the typical-case budget, e.g.
         // reads made of alternating indels).  Size both for the worst case and run the batch once more; results are deterministic.
@@ -811,18 +830,24 @@ extern "C" int mpn_align_batch(mpn_engine* e, const mpn_params* p, const int8_t*
     // time, so the persistent grids of chunk k+1 fill the SMs that the tail of chunk k leaves idle, and the host work of a chunk
     // (scheduling, H2D enqueue, D2H + record conversion) hides behind the kernels of the others.  Fetch order = chunk order (CIGAR offsets).
     constexpr int DEPTH = mpn_engine::NSLOT - 1;
+    static const bool timing = getenv("MPN_TIMING") != nullptr;
+    auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t_begin = now();
+    double t_upload = 0, t_run = 0, t_drain = 0, t_first = 0;
     mpn_batch* inflight[DEPTH] = {};
     int64_t start_of[DEPTH] = {};
     int64_t cig_base = 0;
     int rc = 0;
     auto drain = [&](int s) {
         if (!inflight[s]) return;
+        const double td = now();
         int64_t words = 0;
         const int r2 = fetch_impl(inflight[s], out + start_of[s], cigar ? cigar + cig_base : nullptr, cigar_cap - cig_base, cig_base, &words);
         if (r2 != 0 && rc == 0) rc = r2;
         cig_base += words;
         mpn_batch_free(inflight[s]);
         inflight[s] = nullptr;
+        t_drain += now() - td;
     };
     int64_t issued = 0;
     for (int64_t c = 0; c < nchunks; ++c, ++issued) {
@@ -830,13 +855,20 @@ extern "C" int mpn_align_batch(mpn_engine* e, const mpn_params* p, const int8_t*
         drain(s);                                   // the oldest chunk (c - DEPTH) used this slot
         const int64_t c0 = bounds[c], n_c = bounds[c + 1] - c0;
         if (n_c <= 0) break;
+        const double tu = now();
         mpn_batch* b = upload_impl(e, 1 + s, p, CsrPairs{reads, read_off + c0, refs, ref_off + c0, n_c}, masklen + c0, n_c);
         if (!b) { rc = MPN_E_ARG; break; }
+        const double tr = now();
         mpn_batch_run(b);
         inflight[s] = b; start_of[s] = c0;
+        t_upload += tr - tu; t_run += now() - tr;
+        if (c == 0) t_first = now() - t_begin;
     }
+    const double t_issued = now();
     // the remaining chunks, oldest first
     for (int64_t c = std::max<int64_t>(0, issued - DEPTH); c < issued + DEPTH; ++c) drain((int)(c % DEPTH));
+    if (timing) fprintf(stderr, "[mpn_ssw] align_batch %lld pairs in %lld chunks: total %.2f ms (first chunk enqueued at %.2f, all issued at %.2f); host: upload %.2f, enqueue %.2f, drain (wait + copy + convert) %.2f\n",
+                        (long long)npairs, (long long)nchunks, now() - t_begin, t_first, t_issued - t_begin, t_upload, t_run, t_drain);
     return rc;
 }
 
