@@ -45,7 +45,6 @@ __global__ void __launch_bounds__(128)
 sw_finish_kernel(const SwTask* __restrict__ fwd_tasks, int ntasks, const SwEnds* __restrict__ ends, const uint32_t* __restrict__ colrec,
                  PairArrays pa, FinishParams fp, FwdResult* __restrict__ res, SwTask* __restrict__ rev_tasks)
 {
-    __shared__ int fsm[4 * 512];                  // per warp: ring of B (256) + ring of prefix maxima (256)
     const int lane = threadIdx.x & 31;
     const int k = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
     if (k >= ntasks) return;
@@ -74,83 +73,73 @@ sw_finish_kernel(const SwTask* __restrict__ fwd_tasks, int ntasks, const SwEnds*
         const int e1 = max(end_ref - masklen, 0);
         const int e2 = min(end_ref + masklen, rf_len) + (byte_mode ? 1 : 0);
         const uint32_t* rec = colrec + tk.cm_off;
-        // 128 columns per iteration, 4 consecutive columns per lane.  Two 256-entry rings in shared memory (this warp's slice) hold B and
-        // the prefix maximum of the last two iterations, so "the value d columns back" is one LDS.  Entries of columns < 0 are the
-        // zero / -inf the formulas expect.
-        int* ringB = fsm + (threadIdx.x >> 5) * 512;
-        int* ringX = ringB + 256;
-        const int NEGV = INT_MIN / 2;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) { ringB[q * 32 + lane] = 0; ringX[q * 32 + lane] = NEGV; }
-        __syncwarp();
-        int carryPM = NEGV;            // prefix max of (B[j] + j*gapE) over all earlier iterations
-        int bestL = 0, idxL = 0, bestR = 0, idxR = 0;     // strict-greater-first maxima of the two ranges (per lane, merged at the end)
-        bool anyL = false, anyR = false;
-        for (int c0 = 0; c0 < rf_len; c0 += 128) {
-            const int cb = c0 + 4 * lane;
-            int cm[4], B[4], v[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const uint32_t w = cb + q < rf_len ? rec[cb + q] : 0u;
-                cm[q] = (int)(w & 0xffffu); B[q] = (int)(w >> 16); v[q] = cm[q];
-            }
-            if (P > 0) {
-                // inclusive prefix max of x = B[j] + j*gapE: serial inside the lane, one warp scan of the lane aggregates
-                int x[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    x[q] = cb + q < rf_len ? B[q] + (cb + q) * fp.gapE : NEGV;
-                    if (q) x[q] = max(x[q], x[q - 1]);
-                    ringB[(cb + q) & 255] = B[q];
+        // Both scans are "largest value, smallest column" reductions, and every term of the pad formula is tied to ONE source column j:
+        //   cm[j] lands on column j;  B[j] carried diagonally lands on columns j+1 .. j+P (first one counts);  B[j] eroded by a horizontal
+        //   gap lands on columns >= j+P+1 with B[j] - gapO - (c-P-1-j)*gapE, largest at the first such column.
+        // So each lane walks its columns once and offers at most three (value, column) candidates per range -- no prefix scans, no rings.
+        int bestL = 0, idxL = 0, bestR = 0, idxR = 0;
+        if (rf_len <= 0xffff) {
+            // usual case: value (<= 65535) and column both fit 16 bits -> one 32-bit key, one IMNMX per candidate; values <= 0 clamp to 0,
+            // which never beats the "strictly greater than 0" start of the scans
+            uint32_t kL = 0u, kR = 0u;                    // (value << 16) | (0xffff - column)
+            auto offer = [](uint32_t& k, int value, int col) { k = max(k, ((uint32_t)max(value, 0) << 16) | (uint32_t)(0xffff - col)); };
+            auto column = [&](const int j, const uint32_t w) {
+                const int cmj = (int)(w & 0xffffu), Bj = (int)(w >> 16);
+                if (j < e1) offer(kL, cmj, j);
+                else if (j >= e2) offer(kR, cmj, j);
+                if (P > 0 && Bj > 0) {
+                    if (j + 1 < e1) offer(kL, Bj, j + 1);
+                    if (j + P + 1 < e1) offer(kL, Bj - fp.gapO, j + P + 1);
+                    const int c2 = max(j + 1, e2);
+                    if (c2 <= j + P && c2 < rf_len) offer(kR, Bj, c2);
+                    const int c3 = max(j + P + 1, e2);
+                    if (c3 < rf_len) offer(kR, Bj - fp.gapO - (c3 - P - 1 - j) * fp.gapE, c3);
                 }
-                int inc = x[3];
+            };
+            // 256 columns per iteration: eight coalesced loads in flight per lane before any of them is used (the walk is latency bound otherwise)
+            for (int c0 = 0; c0 < rf_len; c0 += 256) {
+                uint32_t w8[8];
 #pragma unroll
-                for (int off = 1; off < 32; off <<= 1) {
-                    const int o = __shfl_up_sync(0xffffffffu, inc, off);
-                    if (lane >= off) inc = max(inc, o);
-                }
-                int pre = __shfl_up_sync(0xffffffffu, inc, 1);
-                if (lane == 0) pre = NEGV;
-                pre = max(pre, carryPM);
+                for (int q = 0; q < 8; ++q) { const int j = c0 + 32 * q + lane; w8[q] = j < rf_len ? rec[j] : 0u; }
 #pragma unroll
-                for (int q = 0; q < 4; ++q) ringX[(cb + q) & 255] = max(x[q], pre);
-                carryPM = max(carryPM, __shfl_sync(0xffffffffu, inc, 31));
-                __syncwarp();
-                // window maximum of B over the previous P (<= 15) columns: s0..s3 = running max over the d = 1.. columns before this
-                // lane's block, captured at depths P, P-1, P-2, P-3 (what columns 0..3 of the block still see of it) ...
-                int s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-                for (int d = 1; d <= P; ++d) { s3 = s2; s2 = s1; s1 = s0; s0 = max(s0, ringB[(cb - d) & 255]); }
-                // ... plus the columns of the block itself that lie inside the window
-                v[0] = max(v[0], s0);
-                v[1] = max(v[1], max(s1, B[0]));
-                v[2] = max(v[2], max(s2, P >= 2 ? max(B[1], B[0]) : B[1]));
-                v[3] = max(v[3], max(s3, P >= 3 ? max(B[2], max(B[1], B[0])) : (P >= 2 ? max(B[2], B[1]) : B[2])));
-                // eroded contribution: PM[c-P-1] - gapO - (c-P-1)*gapE with PM the inclusive prefix max of B[j] + j*gapE (-inf for columns < 0)
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int cc = cb + q - P - 1;
-                    v[q] = max(v[q], ringX[cc & 255] - fp.gapO - cc * fp.gapE);
-                }
-                __syncwarp();
+                for (int q = 0; q < 8; ++q) { const int j = c0 + 32 * q + lane; if (j < rf_len) column(j, w8[q]); }
             }
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int c = cb + q;
-                if (c < rf_len) {
-                    if (c < e1) { if (!anyL || v[q] > bestL) { bestL = v[q]; idxL = c; anyL = true; } }
-                    else if (c >= e2) { if (!anyR || v[q] > bestR) { bestR = v[q]; idxR = c; anyR = true; } }
+            for (int off = 16; off >= 1; off >>= 1) {
+                kL = max(kL, __shfl_xor_sync(0xffffffffu, kL, off));
+                kR = max(kR, __shfl_xor_sync(0xffffffffu, kR, off));
+            }
+            bestL = (int)(kL >> 16); idxL = 0xffff - (int)(kL & 0xffffu);
+            bestR = (int)(kR >> 16); idxR = 0xffff - (int)(kR & 0xffffu);
+        } else {
+            unsigned long long kL = 0ull, kR = 0ull;      // (value << 32) | ~column
+            auto offer = [](unsigned long long& k, int value, int col) {
+                if (value > 0) {
+                    const unsigned long long c = ((unsigned long long)(unsigned)value << 32) | (unsigned long long)(0xffffffffu - (unsigned)col);
+                    k = c > k ? c : k;
+                }
+            };
+            for (int j = lane; j < rf_len; j += 32) {
+                const uint32_t w = rec[j];
+                const int cmj = (int)(w & 0xffffu), Bj = (int)(w >> 16);
+                if (j < e1) offer(kL, cmj, j);
+                else if (j >= e2) offer(kR, cmj, j);
+                if (P > 0 && Bj > 0) {
+                    if (j + 1 < e1) offer(kL, Bj, j + 1);
+                    if (j + P + 1 < e1) offer(kL, Bj - fp.gapO, j + P + 1);
+                    const int c2 = max(j + 1, e2);
+                    if (c2 <= j + P && c2 < rf_len) offer(kR, Bj, c2);
+                    const int c3 = max(j + P + 1, e2);
+                    if (c3 < rf_len) offer(kR, Bj - fp.gapO - (c3 - P - 1 - j) * fp.gapE, c3);
                 }
             }
-        }
-        // merge lanes: larger value wins, ties -> smaller column
-        if (!anyL) { bestL = -1; idxL = 0x7fffffff; }
-        if (!anyR) { bestR = -1; idxR = 0x7fffffff; }
 #pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) {
-            int ob = __shfl_xor_sync(0xffffffffu, bestL, off), oi = __shfl_xor_sync(0xffffffffu, idxL, off);
-            if (ob > bestL || (ob == bestL && oi < idxL)) { bestL = ob; idxL = oi; }
-            ob = __shfl_xor_sync(0xffffffffu, bestR, off); oi = __shfl_xor_sync(0xffffffffu, idxR, off);
-            if (ob > bestR || (ob == bestR && oi < idxR)) { bestR = ob; idxR = oi; }
+            for (int off = 16; off >= 1; off >>= 1) {
+                const unsigned long long oL = __shfl_xor_sync(0xffffffffu, kL, off), oR = __shfl_xor_sync(0xffffffffu, kR, off);
+                kL = oL > kL ? oL : kL; kR = oR > kR ? oR : kR;
+            }
+            bestL = (int)(kL >> 32); idxL = (int)(0xffffffffu - (unsigned)(kL & 0xffffffffull));
+            bestR = (int)(kR >> 32); idxR = (int)(0xffffffffu - (unsigned)(kR & 0xffffffffull));
         }
         int s2 = 0, r2 = 0;
         if (bestL > s2) { s2 = bestL; r2 = idxL; }
