@@ -10,7 +10,9 @@
 //     moves, the bottom-row H of an earlier column, or that value eroded by one horizontal gap.  With B[i] = H of the
 //     read's last row in column i the pad contribution to column i is
 //         max( max_{1<=d<=P} B[i-d] ,  max_{d>P} B[i-d] - gapO - (d-P-1)*gapE )
-//     (pinned by tests/test_pad_rows.py).
+//     (pinned by tests/test_pad_rows.py).  Every term belongs to one source column j, so the scans below are reductions over
+//     (value, column) candidates: cm[j] at column j, B[j] at the first column of j+1 .. j+P inside the range, and the eroded
+//     B[j] at the first column >= j+P+1 inside the range.
 //   * second best = first strictly greater maxColumn over [0, max(end_ref-maskLen,0)) and then over
 //     [min(end_ref+maskLen, refLen) + (byte ? 1 : 0), refLen)  (ssw.c:310-323 vs :512-525); nothing if maskLen < 15
 //     (ssw.c:809-815).
