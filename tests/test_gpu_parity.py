@@ -296,3 +296,31 @@ def test_short_reads_with_n_bases(eng, ncol):
         r, c = oracle_table(b, cap=cap, threads=os.cpu_count() or 8)
         bad = diff(g, gc, r, c)
         assert len(bad) == 0, (ncol, flag, bad[:5], g[bad[:2]], r[bad[:2]])
+
+
+def test_targets_longer_than_65535_columns(eng):
+    """short reads against targets of 66 k - 90 k bases: column indices no longer fit the 16-bit keys of the second-best reduction
+    (sw_finish.cuh takes its 64-bit path), the score kernel runs 70 k+ wavefront steps per pair; a second copy of the read far from the
+    first gives a real score2 / ref_end2"""
+    rng = np.random.default_rng(4242)
+    reads, refs, masks = [], [], []
+    for k in range(12):
+        fl = int(rng.integers(66_000, 90_000))
+        t = rng.integers(0, 4, size=fl).astype(np.int8)
+        rl = int(rng.integers(60, 400))
+        s1 = int(rng.integers(0, fl // 2 - rl)); s2 = int(rng.integers(fl // 2, fl - rl))
+        r = t[s1:s1 + rl].copy()
+        t[s2:s2 + rl] = r                                   # exact second copy
+        r[rng.random(rl) < 0.03] = rng.integers(0, 4)
+        if k % 3 == 0:
+            r = np.delete(r, slice(rl // 2, rl // 2 + 3))
+        reads.append(r); refs.append(t); masks.append(max(15, len(r) // 2))
+    ro = np.concatenate([[0], np.cumsum([len(x) for x in reads])]).astype(np.int64)
+    fo = np.concatenate([[0], np.cumsum([len(x) for x in refs])]).astype(np.int64)
+    for flag in (1, 0):
+        b = w.PairBatch(np.concatenate(reads), ro, np.concatenate(refs), fo, np.array(masks, dtype=np.int32), flag=flag)
+        g, gc, _, _ = gpu_table(eng, b)
+        r, c = oracle_table(b, threads=os.cpu_count() or 8)
+        bad = diff(g, gc, r, c)
+        assert len(bad) == 0, (flag, bad[:5], g[bad[:2]], r[bad[:2]])
+        assert int((g[:, 1] > 100).sum()) >= 8              # score2 comes from the second copy
