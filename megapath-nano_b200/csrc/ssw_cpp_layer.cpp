@@ -36,9 +36,12 @@ void fill_dna_matrix(std::vector<int8_t>& m, uint8_t match, uint8_t mismatch)
 
 inline void append_run(std::string& s, std::vector<uint32_t>& words, uint32_t len, char op, uint32_t code)
 {
-    char buf[16];
-    const int k = snprintf(buf, sizeof buf, "%u%c", len, op);
-    s.append(buf, (size_t)k);
+    char buf[16];                                   // decimal digits back to front, then the operation letter (no snprintf on this path:
+    int at = 15;                                    // it runs once per CIGAR run of every pair)
+    buf[at] = op;
+    uint32_t v = len;
+    do { buf[--at] = (char)('0' + v % 10u); v /= 10u; } while (v);
+    s.append(buf + at, (size_t)(16 - at));
     words.push_back((len << 4) | code);
 }
 
@@ -55,6 +58,8 @@ void finish_alignment(const mpn_result& r, const uint32_t* cigar_arena, const in
     enum { OP_EQ = 7, OP_X = 8, OP_S = 4 };
     std::string& s = al->cigar_string;
     std::vector<uint32_t>& w = al->cigar;
+    s.reserve(48);
+    w.reserve((size_t)std::max(r.cigar_len, 0) * 3 + 4);
     if (al->query_begin > 0) append_run(s, w, (uint32_t)al->query_begin, 'S', OP_S);
     int mism = 0;
     // With a negative begin (not computed, or score 0) the reference walks from ref[-1]; there is no M run longer than the
@@ -178,16 +183,21 @@ bool Aligner::AlignIndexed(const std::vector<SeqView>& pool, const std::vector<P
     std::vector<int64_t> rd_start, rf_start;
     std::vector<int32_t> rd_len, rf_len, mask;
     std::vector<size_t> slot;
-    rd_start.reserve(np); rf_start.reserve(np); rd_len.reserve(np); rf_len.reserve(np); mask.reserve(np); slot.reserve(np);
     int64_t qbytes = 0, tbytes = 0;
-    for (size_t i = 0; i < np; ++i) {
-        const SeqView& q = pool[(size_t)pairs[i].query]; const SeqView& t = pool[(size_t)pairs[i].target];
-        if (q.len <= 0) continue;
-        rd_start.push_back(start[(size_t)pairs[i].query]); rd_len.push_back(q.len);
-        rf_start.push_back(start[(size_t)pairs[i].target]); rf_len.push_back(std::max(t.len, 0));
-        mask.push_back(q.len);                             // maskLen = query_len (ssw_cpp.cpp:346)
-        slot.push_back(i);
-        qbytes += q.len; tbytes += std::max(t.len, 0);
+    {
+        // positions of the live pairs first (serial, one compare per pair), then the five span arrays filled on host threads
+        slot.reserve(np);
+        for (size_t i = 0; i < np; ++i) if (pool[(size_t)pairs[i].query].len > 0) slot.push_back(i);
+        const size_t nl = slot.size();
+        rd_start.resize(nl); rf_start.resize(nl); rd_len.resize(nl); rf_len.resize(nl); mask.resize(nl);
+        mpn::parallel_for((int64_t)nl, 32768, [&](int64_t k) {
+            const size_t i = slot[(size_t)k];
+            const SeqView& q = pool[(size_t)pairs[i].query]; const SeqView& t = pool[(size_t)pairs[i].target];
+            rd_start[(size_t)k] = start[(size_t)pairs[i].query]; rd_len[(size_t)k] = q.len;
+            rf_start[(size_t)k] = start[(size_t)pairs[i].target]; rf_len[(size_t)k] = std::max(t.len, 0);
+            mask[(size_t)k] = q.len;                        // maskLen = query_len (ssw_cpp.cpp:346)
+        });
+        for (size_t k = 0; k < nl; ++k) { qbytes += rd_len[k]; tbytes += rf_len[k]; }
     }
     const int64_t n = (int64_t)slot.size();
     if (n == 0) return true;
