@@ -26,7 +26,7 @@ struct SwEnds {
     int32_t row;       // smallest row of that column holding score; 0 if score == 0
     int32_t flags;     // SW_FLAG_*
 };
-enum { SW_FLAG_NEEDS_WIDE = 1 };   // pair cannot be handled by the packed 16-bit kernel (read code >= 4): rerun in the 32-bit kernel
+enum { SW_FLAG_NEEDS_WIDE = 1 };   // pair refused by the packed 16-bit kernel (read code >= 4): redone by its N variant or by the 32-bit kernel
 
 // Scoring for the packed kernel: row t of the substitution matrix, entries for read codes 0..3, one byte each.
 struct Score16 {

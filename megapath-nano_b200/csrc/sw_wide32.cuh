@@ -1,6 +1,6 @@
 // 32-bit intra-task score kernel (sm_100a): one warp per pair, for everything the packed 16-bit kernel cannot take --
 // ONT-scale pairs whose scores reach the int16 clamp of sw_sse2_word (ssw.c:425 `_mm_adds_epi16`, result fields are
-// uint16_t), reads longer than the largest packed strip, reads containing codes >= 4 (N), and alphabets with n > 8.
+// uint16_t), reads longer than the largest packed strip, reads with codes >= 4 that the packed kernel's N variants do not take (varying N column, codes above 4, long reads), and alphabets with n > 8.
 //
 // The read is cut into strips of 32 lanes x WIDE_KR rows (16, or 8 when all reads of the batch are short); inside a strip lane L runs WIDE_KR rows of column s-L at step s
 // (anti-diagonal wavefront over the lanes).  Between strips the bottom row (H, F) and the running column maximum live in a
