@@ -110,3 +110,17 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 txt = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "oracle" not in txt, os.path.join(dirpath, f)
+
+
+def test_fastpass_and_assembler_struct_layouts(tmp_path):
+    """the structs bindings have to mirror: mpn_fp_region / mpn_placement (include/mpn_ssw_batch.h) and dbg_str_arr (include/debruijn_graph.h)"""
+    src = tmp_path / "lay2.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include <stdint.h>\n#include "mpn_ssw_batch.h"\n#include "debruijn_graph.h"\n'
+                   'int main(void){printf("%zu %zu %zu %zu %zu %zu %zu\\n", sizeof(mpn_fp_region), offsetof(mpn_fp_region, hap_first), offsetof(mpn_fp_region, suffix),'
+                   'sizeof(mpn_placement), sizeof(dbg_str_arr), offsetof(dbg_str_arr, consensus), sizeof(mpn_result)); return 0;}\n')
+    exe = tmp_path / "lay2"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)], check=True)
+    got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    assert got == [32, 8, 28, 8, 8 + 500 * 8, 8, 40]
+    D = importlib.import_module("megapath-nano_b200.debruijn")
+    assert ct.sizeof(D.DBGPointer) == got[4] and D.DBGPointer.consensus.offset == got[5]
