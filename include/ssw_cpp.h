@@ -58,6 +58,15 @@ struct PairView {
 /* AlignIndexed: a pool of distinct sequences plus pairs that name their query and target by index into the pool */
 struct SeqView { const char* text; int len; };
 struct PairIndex { int32_t query; int32_t target; };
+/* AlignIndexedCompact: what the region realigner consumes of an Alignment (realigner.cpp:336-348, :369-379), without one heap string and one
+ * vector per pair: sw_score, ref_begin and the '=' / 'X' / 'I' / 'D' / 'S' CIGAR text as (pointer, length) into buffers owned by the result */
+struct CompactAlignments {
+  std::vector<int32_t> sw_score, ref_begin, mismatches;
+  std::vector<const char*> cigar;       /* not NUL terminated */
+  std::vector<int32_t> cigar_len;
+  std::vector<std::string> text;        /* the buffers cigar[] points into (one per block of pairs) */
+  size_t size() const { return sw_score.size(); }
+};
 
 class Aligner {
  public:
@@ -83,6 +92,8 @@ class Aligner {
   /* NEW: the same for callers that already know which pairs share sequences (a haplotype met by hundreds of reads): every
    * sequence of `pool` is translated and uploaded once; pairs with an empty query or target give a cleared Alignment. */
   bool AlignIndexed(const std::vector<SeqView>& pool, const std::vector<PairIndex>& pairs, const Filter& filter, std::vector<Alignment>* out) const;
+  /* NEW: same call, compact result (see CompactAlignments); a pair with an empty query has sw_score 0, ref_begin 0 and an empty CIGAR, like a cleared Alignment */
+  bool AlignIndexedCompact(const std::vector<SeqView>& pool, const std::vector<PairIndex>& pairs, const Filter& filter, CompactAlignments* out) const;
 
   void Clear(void);
   bool ReBuild(void);
@@ -92,6 +103,8 @@ class Aligner {
                const int8_t* translation_matrix, const int& translation_matrix_size);
 
  private:
+  struct IndexedRun;
+  bool RunIndexed(const std::vector<SeqView>& pool, const std::vector<PairIndex>& pairs, const Filter& filter, IndexedRun* run) const;
   std::vector<int8_t> matrix_;       /* n x n */
   int n_ = 5;
   std::vector<int8_t> translate_;    /* ASCII -> code; empty = aligner disabled */

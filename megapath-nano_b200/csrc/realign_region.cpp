@@ -563,22 +563,23 @@ int realign_many(const mpn_region* regions, int nregions, struct_str_arr** out)
     for (const PairIndex& p : pairs) { st.pairs++; st.cells += (long long)pool[(size_t)p.query].len * pool[(size_t)p.target].len; }
     double t1 = now_s();
     // ---- 2. GPU: one batch (flag 0x0f, no filters, maskLen = query length: StripedSmithWaterman defaults, ssw_cpp.cpp:343-346)
-    std::vector<Alignment> aln;
+    // results in compact form (score, begin, CIGAR text in shared buffers): one heap string + one vector per pair would cost more to build and
+    // to destroy than the whole GPU batch takes
+    StripedSmithWaterman::CompactAlignments aln;
+    std::vector<int64_t> at(pairs.size(), -1);             // pair -> entry of aln; -1: the pair was not aligned (stays "score 0")
     {
         StripedSmithWaterman::Aligner aligner(kMatch, kMismatch, kGapOpen, kGapExtend);
         StripedSmithWaterman::Filter filter;
         // a zero-length reference makes Aligner::Align return false in the reference (ssw_cpp.cpp:330); those pairs stay cleared
-        std::vector<PairIndex> live;
-        std::vector<size_t> where;
         bool all_live = true;
         for (const PairIndex& p : pairs) if (pool[(size_t)p.target].len <= 0 || pool[(size_t)p.query].len <= 0) { all_live = false; break; }
-        if (all_live) aligner.AlignIndexed(pool, pairs, filter, &aln);
-        else {
-            for (size_t i = 0; i < pairs.size(); ++i) if (pool[(size_t)pairs[i].target].len > 0 && pool[(size_t)pairs[i].query].len > 0) { live.push_back(pairs[i]); where.push_back(i); }
-            std::vector<Alignment> got;
-            aligner.AlignIndexed(pool, live, filter, &got);
-            aln.clear(); aln.resize(pairs.size());
-            for (size_t k = 0; k < where.size(); ++k) aln[where[k]] = std::move(got[k]);
+        if (all_live) {
+            aligner.AlignIndexedCompact(pool, pairs, filter, &aln);
+            for (size_t i = 0; i < pairs.size(); ++i) at[i] = (int64_t)i;
+        } else {
+            std::vector<PairIndex> live;
+            for (size_t i = 0; i < pairs.size(); ++i) if (pool[(size_t)pairs[i].target].len > 0 && pool[(size_t)pairs[i].query].len > 0) { at[i] = (int64_t)live.size(); live.push_back(pairs[i]); }
+            aligner.AlignIndexedCompact(pool, live, filter, &aln);
         }
     }
     double t2 = now_s();
@@ -588,20 +589,21 @@ int realign_many(const mpn_region* regions, int nregions, struct_str_arr** out)
         Region& rg = rgs[r];
         size_t k = rg.first_pair;
         for (HapRecord& h : rg.haps) {                                   // realigner.cpp:336-348
-            const Alignment& a = aln[k++];
-            if (a.sw_score > 0) {
-                h.is_reference = a.cigar_string == std::to_string(rg.haplotypes[h.index].size()) + "=";
-                h.cigar = a.cigar_string;
+            const int64_t a = at[k++];
+            if (a >= 0 && aln.sw_score[(size_t)a] > 0) {
+                h.cigar.assign(aln.cigar[(size_t)a], (size_t)aln.cigar_len[(size_t)a]);
+                h.is_reference = h.cigar == std::to_string(rg.haplotypes[h.index].size()) + "=";
                 h.ops = parse_ops(h.cigar);
-                h.ref_pos = a.ref_begin;
+                h.ref_pos = aln.ref_begin[(size_t)a];
             }
             build_shift_map(h, (int)rg.haplotypes[h.index].size());
         }
         for (const auto& rh : rg.read_hap_pairs) {                       // realigner.cpp:369-379
-            const Alignment& a = aln[k++];
+            const int64_t a = at[k++];
             Placement& pl = rg.haps[rh.second].reads[rh.first];
-            if (a.sw_score > 0 && a.sw_score >= threshold && pl.score < a.sw_score) {
-                pl.score = a.sw_score; pl.cigar = a.cigar_string; pl.pos = a.ref_begin;
+            const int sc = a >= 0 ? aln.sw_score[(size_t)a] : 0;
+            if (sc > 0 && sc >= threshold && pl.score < sc) {
+                pl.score = sc; pl.cigar.assign(aln.cigar[(size_t)a], (size_t)aln.cigar_len[(size_t)a]); pl.pos = aln.ref_begin[(size_t)a];
             }
         }
         std::sort(rg.haps.begin(), rg.haps.end());                       // realigner.cpp:105-106 (same comparator, same algorithm)

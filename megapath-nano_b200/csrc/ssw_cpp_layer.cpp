@@ -159,47 +159,55 @@ bool Aligner::AlignPairs(const std::vector<PairView>& pairs, const Filter& filte
     return AlignIndexed(pool, idx, filter, out);
 }
 
-bool Aligner::AlignIndexed(const std::vector<SeqView>& pool, const std::vector<PairIndex>& pairs, const Filter& filter, std::vector<Alignment>* out) const
+// engine part shared by AlignIndexed and AlignIndexedCompact: translate the pool, build the spans of the live pairs, run the batch
+struct Aligner::IndexedRun {
+    std::unique_ptr<int8_t[]> arena_store;
+    int8_t* arena = nullptr;
+    std::vector<int64_t> rd_start, rf_start;
+    std::vector<int32_t> rd_len, rf_len, mask;
+    std::vector<size_t> slot;                    // position of live pair k in the caller's pair list
+    std::unique_ptr<mpn_result[]> res;
+    std::unique_ptr<uint32_t[]> cig;
+    int64_t n = 0;
+    double t_start = 0, t_packed = 0, t_gpu = 0;
+};
+
+static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+bool Aligner::RunIndexed(const std::vector<SeqView>& pool, const std::vector<PairIndex>& pairs, const Filter& filter, IndexedRun* run) const
 {
-    if (translate_.empty() || !out) return false;
-    static const bool timing = getenv("MPN_TIMING") != nullptr;
-    auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-    const double t_start = now();
+    IndexedRun& R = *run;
     const size_t np = pairs.size();
-    out->clear();
-    out->resize(np);
     // ---- arena: the pool back to back, translated on host threads
     std::vector<int64_t> start(pool.size() + 1, 0);
     for (size_t d = 0; d < pool.size(); ++d) start[d + 1] = start[d] + std::max(pool[d].len, 0);
     const int64_t arena_bytes = start[pool.size()];
-    std::unique_ptr<int8_t[]> arena_store(new int8_t[(size_t)arena_bytes + 16]);      // no zero fill: every byte is written below
-    int8_t* const arena = arena_store.get();
+    R.arena_store.reset(new int8_t[(size_t)arena_bytes + 16]);      // no zero fill: every byte is written below
+    int8_t* const arena = R.arena = R.arena_store.get();
     mpn::parallel_for((int64_t)pool.size(), 64, [&](int64_t d) {
         if (pool[d].len <= 0) return;
         if (pool[d].text == nullptr) memcpy(arena + start[d], reference_.data(), (size_t)pool[d].len);
         else translate_into(translate_, pool[d].text, pool[d].len, arena + start[d]);
     });
     // ---- spans of the live pairs (an empty query makes Align return false: the slot stays cleared)
-    std::vector<int64_t> rd_start, rf_start;
-    std::vector<int32_t> rd_len, rf_len, mask;
-    std::vector<size_t> slot;
     int64_t qbytes = 0, tbytes = 0;
     {
         // positions of the live pairs first (serial, one compare per pair), then the five span arrays filled on host threads
-        slot.reserve(np);
-        for (size_t i = 0; i < np; ++i) if (pool[(size_t)pairs[i].query].len > 0) slot.push_back(i);
-        const size_t nl = slot.size();
-        rd_start.resize(nl); rf_start.resize(nl); rd_len.resize(nl); rf_len.resize(nl); mask.resize(nl);
+        R.slot.reserve(np);
+        for (size_t i = 0; i < np; ++i) if (pool[(size_t)pairs[i].query].len > 0) R.slot.push_back(i);
+        const size_t nl = R.slot.size();
+        R.rd_start.resize(nl); R.rf_start.resize(nl); R.rd_len.resize(nl); R.rf_len.resize(nl); R.mask.resize(nl);
         mpn::parallel_for((int64_t)nl, 32768, [&](int64_t k) {
-            const size_t i = slot[(size_t)k];
+            const size_t i = R.slot[(size_t)k];
             const SeqView& q = pool[(size_t)pairs[i].query]; const SeqView& t = pool[(size_t)pairs[i].target];
-            rd_start[(size_t)k] = start[(size_t)pairs[i].query]; rd_len[(size_t)k] = q.len;
-            rf_start[(size_t)k] = start[(size_t)pairs[i].target]; rf_len[(size_t)k] = std::max(t.len, 0);
-            mask[(size_t)k] = q.len;                        // maskLen = query_len (ssw_cpp.cpp:346)
+            R.rd_start[(size_t)k] = start[(size_t)pairs[i].query]; R.rd_len[(size_t)k] = q.len;
+            R.rf_start[(size_t)k] = start[(size_t)pairs[i].target]; R.rf_len[(size_t)k] = std::max(t.len, 0);
+            R.mask[(size_t)k] = q.len;                      // maskLen = query_len (ssw_cpp.cpp:346)
         });
-        for (size_t k = 0; k < nl; ++k) { qbytes += rd_len[k]; tbytes += rf_len[k]; }
+        for (size_t k = 0; k < nl; ++k) { qbytes += R.rd_len[k]; tbytes += R.rf_len[k]; }
     }
-    const int64_t n = (int64_t)slot.size();
+    const int64_t n = R.n = (int64_t)R.slot.size();
+    R.t_packed = R.t_gpu = now_ms();
     if (n == 0) return true;
     uint8_t flag = 0;                                      // SetFlag, ssw_cpp.cpp:209-212
     if (filter.report_begin_position) flag |= 0x08;
@@ -207,34 +215,80 @@ bool Aligner::AlignIndexed(const std::vector<SeqView>& pool, const std::vector<P
     mpn_params pr;
     pr.mat = matrix_.data(); pr.n = n_; pr.gapO = gap_open_; pr.gapE = gap_extend_; pr.score_size = 2;
     pr.flag = flag; pr.filters = filter.score_filter; pr.filterd = filter.distance_filter;
-    std::unique_ptr<mpn_result[]> res(new mpn_result[(size_t)n]);
+    R.res.reset(new mpn_result[(size_t)n]);
     size_t cig_cap = (size_t)(n * 24 + qbytes / 4 + 4096);
-    std::unique_ptr<uint32_t[]> cig(new uint32_t[cig_cap]);
+    R.cig.reset(new uint32_t[cig_cap]);
     int rc;
-    const double t_packed = now();
     for (int attempt = 0;; ++attempt) {
         mpn::SharedEngineLock lk;
-        rc = mpn_align_batch_spans(lk.engine(), &pr, arena, arena_bytes, rd_start.data(), rd_len.data(), rf_start.data(), rf_len.data(), mask.data(), n,
-                                   res.get(), cig.get(), (int64_t)cig_cap);
+        rc = mpn_align_batch_spans(lk.engine(), &pr, arena, arena_bytes, R.rd_start.data(), R.rd_len.data(), R.rf_start.data(), R.rf_len.data(), R.mask.data(), n,
+                                   R.res.get(), R.cig.get(), (int64_t)cig_cap);
         if (rc != MPN_E_CIGAR_SPACE || attempt == 1) break;
         cig_cap = (size_t)(2 * (qbytes + tbytes) + 16 * n);             // always enough: a CIGAR has at most read + target runs
-        cig.reset(new uint32_t[cig_cap]);
+        R.cig.reset(new uint32_t[cig_cap]);
     }
     if (rc != 0) {
         fprintf(stderr, "[ssw_cpp] GPU alignment failed (code %d); this library has no CPU fallback\n", rc);
         abort();
     }
     for (int64_t k = 0; k < n; ++k)
-        if (res[k].status != MPN_ST_OK) {                  // the reference dereferences a NULL s_align here; fail loudly instead
-            fprintf(stderr, "[ssw_cpp] ssw_align returned no result for pair %lld\n", (long long)slot[k]);
+        if (R.res[k].status != MPN_ST_OK) {                // the reference dereferences a NULL s_align here; fail loudly instead
+            fprintf(stderr, "[ssw_cpp] ssw_align returned no result for pair %lld\n", (long long)R.slot[k]);
             abort();
         }
+    R.t_gpu = now_ms();
+    return true;
+}
+
+bool Aligner::AlignIndexed(const std::vector<SeqView>& pool, const std::vector<PairIndex>& pairs, const Filter& filter, std::vector<Alignment>* out) const
+{
+    if (translate_.empty() || !out) return false;
+    static const bool timing = getenv("MPN_TIMING") != nullptr;
+    IndexedRun R;
+    R.t_start = now_ms();
+    out->clear();
+    out->resize(pairs.size());
+    if (!RunIndexed(pool, pairs, filter, &R)) return false;
     // ---- '=' / 'X' CIGAR + mismatch count per pair (independent: host threads)
-    const double t_gpu = now();
-    mpn::parallel_for(n, 256, [&](int64_t k) {
-        finish_alignment(res[k], cig.get(), arena + rf_start[k], arena + rd_start[k], rd_len[k], &(*out)[slot[k]]);
+    mpn::parallel_for(R.n, 256, [&](int64_t k) {
+        finish_alignment(R.res[k], R.cig.get(), R.arena + R.rf_start[k], R.arena + R.rd_start[k], R.rd_len[k], &(*out)[R.slot[k]]);
     });
-    if (timing) fprintf(stderr, "[ssw_cpp] %lld pairs: pack %.3f ms, engine %.3f ms, post-process %.3f ms\n", (long long)n, t_packed - t_start, t_gpu - t_packed, now() - t_gpu);
+    if (timing) fprintf(stderr, "[ssw_cpp] %lld pairs: pack %.3f ms, engine %.3f ms, post-process %.3f ms\n", (long long)R.n, R.t_packed - R.t_start, R.t_gpu - R.t_packed, now_ms() - R.t_gpu);
+    return true;
+}
+
+bool Aligner::AlignIndexedCompact(const std::vector<SeqView>& pool, const std::vector<PairIndex>& pairs, const Filter& filter, CompactAlignments* out) const
+{
+    if (translate_.empty() || !out) return false;
+    static const bool timing = getenv("MPN_TIMING") != nullptr;
+    IndexedRun R;
+    R.t_start = now_ms();
+    const size_t np = pairs.size();
+    out->sw_score.assign(np, 0); out->ref_begin.assign(np, 0); out->mismatches.assign(np, 0);
+    out->cigar.assign(np, nullptr); out->cigar_len.assign(np, 0);
+    out->text.clear();
+    if (!RunIndexed(pool, pairs, filter, &R)) return false;
+    // ---- the same '=' / 'X' walk as finish_alignment, CIGAR text appended to one buffer per block of pairs (no per-pair allocation)
+    constexpr int64_t BLOCK = 1024;
+    const int64_t nblocks = (R.n + BLOCK - 1) / BLOCK;
+    out->text.resize((size_t)nblocks);
+    mpn::parallel_for(nblocks, 1, [&](int64_t blk) {
+        std::string& buf = out->text[(size_t)blk];
+        const int64_t k0 = blk * BLOCK, k1 = std::min(R.n, k0 + BLOCK);
+        buf.reserve((size_t)(k1 - k0) * 24);
+        std::vector<int32_t> at((size_t)(k1 - k0) + 1, 0);
+        Alignment tmp;
+        for (int64_t k = k0; k < k1; ++k) {
+            finish_alignment(R.res[k], R.cig.get(), R.arena + R.rf_start[k], R.arena + R.rd_start[k], R.rd_len[k], &tmp);
+            const size_t i = R.slot[(size_t)k];
+            out->sw_score[i] = tmp.sw_score; out->ref_begin[i] = tmp.ref_begin; out->mismatches[i] = tmp.mismatches;
+            at[(size_t)(k - k0)] = (int32_t)buf.size();
+            buf.append(tmp.cigar_string);
+            out->cigar_len[i] = (int32_t)tmp.cigar_string.size();
+        }
+        for (int64_t k = k0; k < k1; ++k) out->cigar[R.slot[(size_t)k]] = buf.data() + at[(size_t)(k - k0)];      // after the last append: the buffer no longer moves
+    });
+    if (timing) fprintf(stderr, "[ssw_cpp] %lld pairs (compact): pack %.3f ms, engine %.3f ms, post-process %.3f ms\n", (long long)R.n, R.t_packed - R.t_start, R.t_gpu - R.t_packed, now_ms() - R.t_gpu);
     return true;
 }
 
