@@ -105,7 +105,9 @@ def realign_regions_packed(regions, lib_path=None):
         n = min(max_region_reads_num, len(rg.reads))
         parts.append(rg.reference); parts.append(" ".join(rg.haplotypes))
         parts.extend(rg.reads[:n]); parts.extend(rg.cigars[:n])
-        nreads.append(n); geom.extend((int(rg.ref_start), int(rg.ref_prefix), int(rg.ref_suffix))); positions.extend(int(p) for p in rg.positions[:n])
+        nreads.append(n); geom.extend((int(rg.ref_start), int(rg.ref_prefix), int(rg.ref_suffix)))
+        pos = rg.positions[:n]
+        positions.extend(pos if all(type(p) is int for p in pos) else [int(p) for p in pos])     # plain ints go in without per-item conversion
     text = ("\0".join(parts) + "\0").encode() if parts else b""
     total = len(positions)
     out_pos = (ctypes.c_int * max(total, 1))()
