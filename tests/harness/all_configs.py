@@ -1,11 +1,11 @@
 """One JSON line per BASELINE config (1-5): GPU GCUPS (kernel phases with inputs resident + the public call with host buffers), the compiled
 reference ssw.c on all host cores over a bounded sample of the SAME pairs, and the parity count of that sample (mismatching pairs / sample).
-    python tools/all_configs.py            # on the GPU box; needs oracle/_ref (travels with gpurun) for the reference column
+    python tests/harness/all_configs.py            # on the GPU box; needs oracle/_ref (travels with gpurun) for the reference column
 Sizes: config 1 and 3 at full size, config 2 at 1 M pairs, config 4 at 1024 pairs (flag 0 and flag 1), config 5 on a 20 000-pair sample of its
 length distribution (the full 10 M pairs are ~4.5e14 cells: generated per chunk in a production run, not held in memory)."""
 import dataclasses, importlib, json, os, subprocess, sys, time
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 w = importlib.import_module("megapath-nano_b200.workloads")
 B = importlib.import_module("megapath-nano_b200.batch")

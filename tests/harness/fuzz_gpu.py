@@ -1,8 +1,8 @@
 """Large differential run on the GPU box: seeded adversarial batches (workloads.fuzz_pairs + long-read mixes) through the C ABI against
-the compiled reference ssw.c.  python tools/fuzz_gpu.py [seeds] [pairs_per_seed]  -> one JSON line (mismatches must be 0)."""
+the compiled reference ssw.c.  python tests/harness/fuzz_gpu.py [seeds] [pairs_per_seed]  -> one JSON line (mismatches must be 0)."""
 import importlib, json, os, sys, time
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 w = importlib.import_module("megapath-nano_b200.workloads")
 B = importlib.import_module("megapath-nano_b200.batch")

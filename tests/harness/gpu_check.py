@@ -1,6 +1,6 @@
-"""Ad-hoc GPU parity run: python tools/gpu_check.py [nseeds] -- compares the CUDA engine with the compiled reference (oracle/_ref)."""
+"""Ad-hoc GPU parity run: python tests/harness/gpu_check.py [nseeds] -- compares the CUDA engine with the compiled reference (oracle/_ref)."""
 import importlib, sys, time, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 w = importlib.import_module("megapath-nano_b200.workloads")
 B = importlib.import_module("megapath-nano_b200.batch")

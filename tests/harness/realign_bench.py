@@ -1,8 +1,8 @@
-"""BASELINE configs[2] (realigner amplicon workload) timing: python tools/realign_bench.py [regions] [seed]
+"""BASELINE configs[2] (realigner amplicon workload) timing: python tests/harness/realign_bench.py [regions] [seed]
 Per-region realign_reads latency and whole-set mpn_realign_regions throughput on the GPU, the compiled reference realigner
 (oracle/_ref/realigner_ref, clean subprocess, one core) beside it."""
 import dataclasses, importlib, json, os, subprocess, sys, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 w = importlib.import_module("megapath-nano_b200.workloads")
 R = importlib.import_module("megapath-nano_b200.realigner")

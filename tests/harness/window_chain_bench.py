@@ -1,9 +1,9 @@
 """BASELINE configs[2] one step earlier (SURVEY.md section 8f N4 -> N3 -> hot path): windows -> haplotype assembly on the host threads
 (realign/debruijn_graph) -> realigner inputs -> every Smith-Waterman pair of all regions in one GPU batch (realign/realigner).
-python tools/window_chain_bench.py [windows] [max_reads] [oracle_sample]  -> two JSON lines (assembler alone, then the whole chain).  The assembler's CPU baseline is the Python
+python tests/harness/window_chain_bench.py [windows] [max_reads] [oracle_sample]  -> two JSON lines (assembler alone, then the whole chain).  The assembler's CPU baseline is the Python
 restatement oracle/dbg_oracle.py on a sample of the windows (the reference's own assembler needs Boost and cannot be built here)."""
 import importlib, json, os, sys, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 w = importlib.import_module("megapath-nano_b200.workloads")
 D = importlib.import_module("megapath-nano_b200.debruijn")
 R = importlib.import_module("megapath-nano_b200.realigner")
