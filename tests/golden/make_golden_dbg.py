@@ -11,7 +11,7 @@ from oracle import dbg_oracle
 wins = w.dbg_windows(14, seed=7001, max_reads=60) + w.dbg_windows(6, seed=7002, max_reads=40, repeat_frac=1.0) + [
     ("ACGTACGTAC", ["ACGTACGTACGT"], [""]),
     ("A" * 120, ["A" * 90], [""]),
-    (w.dbg_windows(1, seed=7003, max_reads=5)[0][0], [""], [""]),
+    (w.dbg_windows(1, seed=7003, max_reads=30)[0][0], [""], [""]),
 ]
 doc = []
 for ref, reads, lowq in wins:

@@ -135,3 +135,17 @@ def test_assembled_regions_through_the_realigner_host_logic():
     assert not bad, bad[:5]
     moved = sum(c != f"{len(r)}M" for rg, (p, cs) in zip(regions, got) for r, c in zip(rg.reads, cs))
     assert moved > 0                                              # reads of the alternative haplotypes get new CIGARs
+
+
+def test_golden_windows():
+    """committed fixtures (tests/golden/dbg_golden.json.gz, made by tests/golden/make_golden_dbg.py from the restatement): both the product and
+    the restatement still give them"""
+    import gzip, json
+    with gzip.open(os.path.join(ROOT, "tests", "golden", "dbg_golden.json.gz"), "rt") as f:
+        doc = json.load(f)
+    assert len(doc) >= 20
+    got, ks = D.consensus_windows([(d["ref"], d["reads"], d["lowq"]) for d in doc], with_k=True)
+    for d, g, k in zip(doc, got, ks):
+        assert g == d["haplotypes"] and k == d["k"]
+        assert oracle(d["ref"], d["reads"], d["lowq"]) == (d["haplotypes"], d["k"])
+    assert sum(len(d["haplotypes"]) > 1 for d in doc) >= 5
