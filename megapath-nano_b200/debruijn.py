@@ -67,7 +67,9 @@ def consensus_windows(windows, lib_path=None, with_k=False):
     for ref, reads, lowq in windows:
         parts.extend((ref, ",".join(reads), ",".join(lowq)))
     nw = len(parts) // 3
-    text = ("\0".join(parts) + "\0").encode() if parts else b""
+    if parts:
+        parts.append("")
+    text = "\0".join(parts).encode() if parts else b""
     counts, ks = array.array("i", [0] * max(nw, 1)), array.array("i", [0] * max(nw, 1))
     out, out_bytes = ctypes.c_void_p(), ctypes.c_longlong(0)
     rc = L.mpn_dbg_consensus_packed(text, len(text), nw, ctypes.c_void_p(counts.buffer_info()[0]), ctypes.c_void_p(ks.buffer_info()[0]),

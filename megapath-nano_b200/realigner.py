@@ -108,7 +108,9 @@ def realign_regions_packed(regions, lib_path=None):
         nreads.append(n); geom.extend((int(rg.ref_start), int(rg.ref_prefix), int(rg.ref_suffix)))
         pos = rg.positions[:n]
         positions.extend(pos if all(type(p) is int for p in pos) else [int(p) for p in pos])     # plain ints go in without per-item conversion
-    text = ("\0".join(parts) + "\0").encode() if parts else b""
+    if parts:
+        parts.append("")                                                # the join then ends with the last terminator: no second 20 MB copy
+    text = "\0".join(parts).encode() if parts else b""
     total = len(positions)
     out_pos = (ctypes.c_int * max(total, 1))()
     out_cig = ctypes.c_void_p(); out_bytes = ctypes.c_longlong(0)
