@@ -15,6 +15,9 @@
  * Errors: functions return 0 on success, a negative MPN_E_* otherwise; CUDA failures abort() with a message on stderr
  * (the reference's callers never check for NULL, SURVEY.md section 8b, so failing loudly is the only safe behaviour).
  * There is no CPU fallback.
+ *
+ * Threading: an mpn_engine is NOT re-entrant -- one thread at a time per engine (it owns one device, its streams and its
+ * staging buffers).  Use one engine per thread, or an mpn_pool (below), which owns one engine + one host thread per device.
  */
 #ifndef MPN_SSW_BATCH_H
 #define MPN_SSW_BATCH_H
@@ -47,11 +50,12 @@ typedef struct {
     int32_t read_end1;
     int32_t ref_end2;
     int32_t cigar_len;
-    int32_t status;         /* 0 ok; MPN_ST_NULL: ssw_align would have returned NULL for this pair */
+    int32_t status;         /* 0 ok; MPN_ST_NULL / MPN_ST_NULL_TRACE: ssw_align would have returned NULL for this pair */
     int64_t cigar_off;
 } mpn_result;
 
-enum { MPN_ST_OK = 0, MPN_ST_NULL = 1 };
+/* MPN_ST_NULL: 8-bit scores saturated and no 16-bit profile was asked for (ssw.c:793-796); MPN_ST_NULL_TRACE: banded traceback failed (ssw.c:840-843) */
+enum { MPN_ST_OK = 0, MPN_ST_NULL = 1, MPN_ST_NULL_TRACE = 2 };
 enum { MPN_E_ARG = -1, MPN_E_NOGPU = -2, MPN_E_CIGAR_SPACE = -3, MPN_E_UNSUPPORTED = -4 };
 
 /* engine = one CUDA device + one stream + reusable device/pinned buffers.  device < 0: current device. */

@@ -107,6 +107,14 @@ void build_strip_table()
         while (g_strips[k].cap < len) ++k;
         g_bin_of_len[len] = (int16_t)k;
     }
+    // resident blocks per SM of every instantiation (all devices of a box are the same part): queried once, under the call_once of
+    // mpn_engine_create, so that engines created concurrently (one per device, mpn_pool) never write the table while another launches
+    for (int c = 0; c < N_STRIPS; ++c) {
+        int nb = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, g_strips[c].fn, STRIP_BLOCK_THREADS, g_strips[c].smem));
+        g_strips[c].blocks_per_sm = nb > 0 ? nb : 1;
+        if (getenv("MPN_VERBOSE")) fprintf(stderr, "[mpn_ssw] strip G=%d KR=%d cap=%d smem=%zu blocks/SM=%d\n", g_strips[c].G, g_strips[c].KR, g_strips[c].cap, g_strips[c].smem, nb);
+    }
 }
 
 }  // namespace
@@ -191,12 +199,6 @@ extern "C" mpn_engine* mpn_engine_create(int device)
     CK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
     static std::once_flag once;
     std::call_once(once, build_strip_table);
-    for (int c = 0; c < N_STRIPS; ++c) {
-        int nb = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, g_strips[c].fn, STRIP_BLOCK_THREADS, g_strips[c].smem));
-        g_strips[c].blocks_per_sm = nb > 0 ? nb : 1;
-        if (getenv("MPN_VERBOSE")) fprintf(stderr, "[mpn_ssw] strip G=%d KR=%d cap=%d smem=%zu blocks/SM=%d\n", g_strips[c].G, g_strips[c].KR, g_strips[c].cap, g_strips[c].smem, nb);
-    }
     return e;
 }
 
@@ -259,6 +261,9 @@ extern "C" void mpn_batch_free(mpn_batch* b)
 {
     if (!b) return;
     cudaSetDevice(b->e->device);
+    // the blocks go back to a pool that batches on OTHER streams draw from: nothing of this batch may still be in flight (a batch freed
+    // after run but before a successful fetch, or on an error path).  After a fetch the stream is already idle and this returns at once.
+    if (b->st) cudaStreamSynchronize(b->st);
     DevBuf* bufs[] = {&b->seq, &b->mask, &b->tasks_fwd, &b->tasks_rev, &b->ends_fwd, &b->ends_rev,
                       &b->colrec, &b->fwdres, &b->finalres, &b->counters, &b->dmat, &b->scratch, &b->cig, &b->wide_boundary, &b->long_boundary, &b->warp_dir, &b->bandrec, &b->flaglist, &b->bandq_items, &b->bandq_meta, &b->relist};
     for (DevBuf* d : bufs) b->e->pool.give(*d);
@@ -737,12 +742,12 @@ static int fetch_impl(mpn_batch* b, mpn_result* out, uint32_t* cigar, int64_t ci
         r.score1 = (uint16_t)f.score1; r.score2 = (uint16_t)f.score2;
         r.ref_end1 = f.ref_end1; r.read_end1 = f.read_end1; r.ref_end2 = f.ref_end2;
         r.ref_begin1 = -1; r.read_begin1 = -1; r.cigar_len = 0; r.cigar_off = 0;
-        r.status = f.status ? MPN_ST_NULL : MPN_ST_OK;
+        r.status = f.status ? MPN_ST_NULL : MPN_ST_OK;      // forward pass: 8-bit overflow without a 16-bit profile (ssw.c:793-796)
         if (any_rev && f.status == 0) {
             const FinalResult& g = h_fin[i];
             r.ref_begin1 = g.ref_begin1; r.read_begin1 = g.read_begin1;
             r.cigar_len = g.cigar_len; r.cigar_off = g.cigar_len > 0 ? g.cigar_off + cigar_base : 0;
-            if (g.status == 3) r.status = MPN_ST_NULL;
+            if (g.status == 3) r.status = MPN_ST_NULL_TRACE;   // traceback met an invalid direction (ssw.c:840-843)
             else if (g.status != 0) {
                 long long none = -1;
                 if (report || (g.status != 5 && g.status != 6)) first_bad.compare_exchange_strong(none, (long long)i);

@@ -68,7 +68,7 @@ extern "C" s_align* ssw_align(const s_profile* prof, const int8_t* ref, int32_t 
     }
     if (res.status != MPN_ST_OK) {
         // the cases in which the reference returns NULL: 8-bit overflow without a 16-bit profile (ssw.c:793-796), traceback error (ssw.c:840-843)
-        if (prof->score_size == 0)
+        if (res.status == MPN_ST_NULL && prof->score_size == 0)
             fprintf(stderr, "Please set 2 to the score_size parameter of the function ssw_init, otherwise the alignment results will be incorrect.\n");
         free(cig);
         return NULL;

@@ -63,6 +63,20 @@ def have_ref():
     return os.path.exists(_REF_SO)
 
 
+def require_ref():
+    """GPU-tier parity is only ever claimed against the compiled UNMODIFIED reference: build it when the sources are present, otherwise
+    raise (tests call pytest.fail on this; nothing degrades to the restatement)."""
+    if not (os.path.exists(_REF_SO) and os.path.exists(_REALIGNER_REF)):
+        try:
+            build()
+        except Exception:
+            pass
+    if not (os.path.exists(_REF_SO) and os.path.exists(_REALIGNER_REF)):
+        raise RuntimeError("oracle/_ref/{libssw_ref.so,realigner_ref} missing: run `make -C oracle ref` where /root/reference exists "
+                           "(the prebuilt files travel to the GPU box); the GPU parity tier never falls back to the restatement")
+    return _REF_SO
+
+
 def ref_lib():
     global _ref
     if _ref is None:

@@ -30,7 +30,8 @@ def gpu_table(eng, b, cap=CAP):
 
 def oracle_table(b, cap=CAP, threads=8):
     from oracle import oracle
-    impl = "ref" if oracle.have_ref() else "port"
+    oracle.require_ref()
+    impl = "ref"
     return oracle.run_batch(b.reads, b.read_off, b.refs, b.ref_off, b.masklen, b.mat, b.n, gapO=b.gapO, gapE=b.gapE, flag=b.flag, filters=b.filters,
                             filterd=b.filterd, score_size=b.score_size, threads=threads, impl=impl, cigar_cap=cap)[:2]
 
@@ -170,10 +171,9 @@ def test_pyssw_mirror(eng):
         assert score > 0 and beg >= 0 and cigar
     # cross-check one against the reference library when it is available
     from oracle import oracle
-    if oracle.have_ref():
-        r = pyssw.SSW(lib_path=oracle.ref_path())
-        r.set_reference_sequence(ref)
-        assert [r.align(q) for q in queries[:6]] == single[:6]
+    r = pyssw.SSW(lib_path=oracle.require_ref())
+    r.set_reference_sequence(ref)
+    assert [r.align(q) for q in queries[:6]] == single[:6]
 
 
 @pytest.mark.parametrize("flag,match,mismatch", [(0, 4, 6), (1, 4, 6), (1, 2, 3)])

@@ -33,8 +33,7 @@ def test_batched_regions_match_golden_and_single_calls():
 def test_config3_live_against_compiled_reference(seed, n_frac):
     """BASELINE configs[2]: per-region haplotypes x overlapping reads, variable small batches"""
     from oracle import oracle
-    if not oracle.have_ref():
-        pytest.skip("compiled reference realigner not present")
+    oracle.require_ref()
     regions = w.config3(24, seed=seed, max_reads=400, max_haps=16, n_frac=n_frac)
     want = run_reference(regions, oracle.realigner_ref_path())
     got = R.realign_regions(regions)
@@ -48,8 +47,7 @@ def test_assembled_haplotypes_through_the_gpu_realigner():
     """SURVEY.md section 8f N4 -> N3 -> hot path: haplotypes assembled by realign/debruijn_graph from the reads of each window, then
     realign_regions on the GPU == the compiled reference realigner on the same inputs"""
     from oracle import oracle
-    if not oracle.have_ref():
-        pytest.skip("compiled reference realigner not present")
+    oracle.require_ref()
     D = importlib.import_module("megapath-nano_b200.debruijn")
     regions, kept = D.regions_from_windows(w.config3_windows(12, seed=71, max_reads=150))
     assert len(regions) >= 8

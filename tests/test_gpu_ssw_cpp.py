@@ -76,7 +76,8 @@ def test_aligner_class_against_reference(tmp_path):
     reads = [enc(q) for q in queries]
     ro = np.concatenate([[0], np.cumsum([len(r) for r in reads])]).astype(np.int64)
     refs = np.tile(enc(ref), len(queries)); fo = np.arange(len(queries) + 1, dtype=np.int64) * len(ref)
-    impl = "ref" if oracle.have_ref() else "port"
+    oracle.require_ref()
+    impl = "ref"
     res, cig, _ = oracle.run_batch(np.concatenate(reads), ro, refs, fo, np.array([len(q) for q in queries], np.int32), w.dna_matrix(4, 6), 5, gapO=8, gapE=2,
                                    flag=0x0f, filters=0, filterd=32767, threads=4, impl=impl, cigar_cap=256)
     for k, q in enumerate(queries):
