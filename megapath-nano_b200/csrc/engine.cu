@@ -77,7 +77,7 @@ struct PinBuf {
 };
 
 constexpr int STRIP_BLOCK_THREADS = 128;   // = STRIP_BLOCK of sw_strip16.cuh (the kernels are compiled in strip_inst_*.cu)
-struct StripCfg { int G, KR, cap; StripFn fn; StripFn fn_rev; size_t smem; int blocks_per_sm; };
+struct StripCfg { int G, KR, cap; StripFn fn; StripFn fn_rev; size_t smem, smem_rev; int blocks_per_sm, blocks_per_sm_rev; };
 
 // all instantiations of the packed kernel, sorted by the number of read rows one strip covers (cap = 2 * G * KR)
 std::vector<StripCfg> g_strips;
@@ -87,6 +87,8 @@ int LONG_BIN = 0;                        // pseudo-bin of the multi-strip clampe
 int WIDE_BIN = 0;                        // pseudo-bin of the 32-bit kernel
 constexpr int LONG_KR = 16;
 
+void set_strip_attributes();
+
 void build_strip_table()
 {
     if (!g_strips.empty()) return;
@@ -95,7 +97,7 @@ void build_strip_table()
     for (int p = 0; p < 4; ++p)
         for (int k = 0; k < counts[p]; ++k) {
             const StripEntry& e = parts[p][k];
-            g_strips.push_back(StripCfg{e.G, e.KR, 2 * e.G * e.KR, e.fn, e.fn_rev, e.smem, 1});
+            g_strips.push_back(StripCfg{e.G, e.KR, 2 * e.G * e.KR, e.fn, e.fn_rev, e.smem, e.smem_rev, 1, 1});
         }
     std::stable_sort(g_strips.begin(), g_strips.end(), [](const StripCfg& a, const StripCfg& b) { return a.cap < b.cap; });
     N_STRIPS = (int)g_strips.size();
@@ -107,14 +109,29 @@ void build_strip_table()
         while (g_strips[k].cap < len) ++k;
         g_bin_of_len[len] = (int16_t)k;
     }
+    set_strip_attributes();
     // resident blocks per SM of every instantiation (all devices of a box are the same part): queried once, under the call_once of
     // mpn_engine_create, so that engines created concurrently (one per device, mpn_pool) never write the table while another launches
     for (int c = 0; c < N_STRIPS; ++c) {
-        int nb = 0;
+        int nb = 0, nbr = 0;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, g_strips[c].fn, STRIP_BLOCK_THREADS, g_strips[c].smem));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nbr, g_strips[c].fn_rev, STRIP_BLOCK_THREADS, g_strips[c].smem_rev));
         g_strips[c].blocks_per_sm = nb > 0 ? nb : 1;
-        if (getenv("MPN_VERBOSE")) fprintf(stderr, "[mpn_ssw] strip G=%d KR=%d cap=%d smem=%zu blocks/SM=%d\n", g_strips[c].G, g_strips[c].KR, g_strips[c].cap, g_strips[c].smem, nb);
+        g_strips[c].blocks_per_sm_rev = nbr > 0 ? nbr : 1;
+        if (getenv("MPN_VERBOSE")) fprintf(stderr, "[mpn_ssw] strip G=%d KR=%d cap=%d smem=%zu/%zu blocks/SM=%d/%d\n", g_strips[c].G, g_strips[c].KR, g_strips[c].cap, g_strips[c].smem, g_strips[c].smem_rev, nb, nbr);
     }
+}
+
+// the forward instantiations keep two checkpoint slots per thread in shared memory (sw_strip16.cuh): above the 48 KB default, so the
+// limit is raised and the carve-out set to all-shared per kernel; attributes are per device -> once per engine
+void set_strip_attributes()
+{
+    auto one = [](StripFn fn, size_t smem) {
+        if (smem > 48 * 1024) CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    };
+    for (int c = 0; c < N_STRIPS; ++c) { one(g_strips[c].fn, g_strips[c].smem); one(g_strips[c].fn_rev, g_strips[c].smem_rev); }
+    for (const StripEntry* e : {&g_strip_n_a, &g_strip_n_b, &g_strip_n_c, &g_strip_n_d}) { one(e->fn, e->smem); one(e->fn_rev, e->smem_rev); }
 }
 
 }  // namespace
@@ -199,6 +216,7 @@ extern "C" mpn_engine* mpn_engine_create(int device)
     CK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
     static std::once_flag once;
     std::call_once(once, build_strip_table);
+    set_strip_attributes();                       // function attributes are per device
     return e;
 }
 
@@ -560,8 +578,8 @@ static void launch_strips(mpn_batch* b, const SwTask* tasks, bool forward, SwEnd
             const StripCfg& c = g_strips[bl.cfg];
             const int groups_per_block = STRIP_BLOCK_THREADS / c.G;
             int64_t blocks = (bl.count + groups_per_block - 1) / groups_per_block;
-            blocks = std::min<int64_t>(blocks, (int64_t)e->sm_count * c.blocks_per_sm);
-            (forward ? c.fn : c.fn_rev)<<<(unsigned)blocks, STRIP_BLOCK_THREADS, c.smem, st>>>(tasks + bl.first, (int)bl.count, counter, b->seq.as<int8_t>(), b->sc16,
+            blocks = std::min<int64_t>(blocks, (int64_t)e->sm_count * (forward ? c.blocks_per_sm : c.blocks_per_sm_rev));
+            (forward ? c.fn : c.fn_rev)<<<(unsigned)blocks, STRIP_BLOCK_THREADS, forward ? c.smem : c.smem_rev, st>>>(tasks + bl.first, (int)bl.count, counter, b->seq.as<int8_t>(), b->sc16,
                                                                   forward ? b->colrec.as<uint32_t>() : nullptr, ends, relist_of(b, forward), (int)bl.first);
         }
         CK(cudaGetLastError());
@@ -588,7 +606,7 @@ static void launch_n_variants(mpn_batch* b, const SwTask* tasks, bool forward, S
         const int cap = 2 * c.G * c.KR;
         if (b->max_rd > min_len) {
             int* counter = reinterpret_cast<int*>(b->counters.as<unsigned long long>() + counter_base + k);
-            (forward ? c.fn : c.fn_rev)<<<(unsigned)(e->sm_count * 2), STRIP_BLOCK_THREADS, c.smem, b->st>>>(tasks, 0, counter, b->seq.as<int8_t>(), b->sc16,
+            (forward ? c.fn : c.fn_rev)<<<(unsigned)(e->sm_count * 2), STRIP_BLOCK_THREADS, forward ? c.smem : c.smem_rev, b->st>>>(tasks, 0, counter, b->seq.as<int8_t>(), b->sc16,
                                                                   forward ? b->colrec.as<uint32_t>() : nullptr, ends, relist, min_len);
             CK(cudaGetLastError());
             e->launches++;

@@ -80,6 +80,15 @@ __device__ __forceinline__ uint32_t max2_track(uint32_t a, uint32_t b, bool& a_g
     a_ge_hi = ph != 0; a_ge_lo = pl != 0;
     return val;
 }
+// c ? x : y as a PREDICATED MOVE (which ptxas may place on the fma pipe as IMAD.MOV) instead of a SEL (alu pipe, the busy one)
+__device__ __forceinline__ uint32_t mov_if(bool c, uint32_t x, uint32_t y)
+{
+    asm("{.reg .pred p;\n\t"
+        "setp.ne.u32 p, %1, 0;\n\t"
+        "@p mov.b32 %0, %2;}"
+        : "+r"(y) : "r"((uint32_t)c), "r"(x));
+    return y;
+}
 __device__ __forceinline__ uint32_t max3(uint32_t a, uint32_t b, uint32_t c) { return __vimax3_s16x2(a, b, c); }             // VIMNMX3.S16x2
 __device__ __forceinline__ uint32_t addmax_relu(uint32_t a, uint32_t b, uint32_t c) { return __viaddmax_s16x2_relu(a, b, c); } // VIADDMNMX.S16x2.RELU
 

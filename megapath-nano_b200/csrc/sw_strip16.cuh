@@ -30,17 +30,30 @@ namespace mpn {
 constexpr int STRIP_BLOCK = 128;
 
 #ifndef MPN_STRIP_UNROLL
-#define MPN_STRIP_UNROLL 2
+#define MPN_STRIP_UNROLL 2          // wavefront steps unrolled inside a block of STRIP_CK steps (8: all of them)
 #endif
 constexpr int STRIP_UNROLL = MPN_STRIP_UNROLL;
 #ifndef MPN_STRIP_MINB
 #define MPN_STRIP_MINB 4
 #endif
 
-// shared memory: H-column snapshots [2 halves][ceil(KR/4)][STRIP_BLOCK] uint4, the column-record staging [G][STRIP_BLOCK] words and, in
-// the N variant only, the per-row score fix-up selectors [KR][STRIP_BLOCK]
-template <int KR, int G, bool NM = false>
-__host__ __device__ constexpr size_t strip16_smem_bytes() { return (size_t)2 * ((KR + 3) / 4) * STRIP_BLOCK * sizeof(uint4) + (size_t)(G + (NM ? KR : 0)) * STRIP_BLOCK * sizeof(uint32_t); }
+// Row of the winning cell (ssw.c:284-293: smallest row of the saved column holding the maximum).
+//   reverse passes: a stage that REACHES the terminating score stores its H column (a handful of times per pair, behind a warp-uniform branch);
+//   forward passes: checkpoint + replay.  Every STRIP_CK steps a thread stores its state (H, E of its rows, the boundary entering its
+//   stages) into a scratch slot, and every step the 2 x 16 bits it receives from the thread above into the slot's log; when the block of
+//   steps ends and the thread's better stage improved in it, scratch and committed slot swap.  At the end of the pass the thread that owns
+//   the winning stage restores the committed slot and re-runs at most STRIP_CK steps on its own (the log replaces the shuffles) to get the
+//   column again.  This replaces the per-improvement H-column snapshots of round 1 (8 predicated STS.128 + 15 register moves per step).
+__host__ __device__ constexpr int strip_ck(int G) { return G < 8 ? G : 8; }
+template <int KR, int G>
+__host__ __device__ constexpr size_t strip16_slot_bytes() { return ((size_t)2 * ((KR + 3) / 4) * 16 + 8 + (size_t)strip_ck(G) * 4) * STRIP_BLOCK; }
+// shared memory.  Forward: 2 checkpoint slots, the column-record staging [G][STRIP_BLOCK] words and, in the N variant only, the per-row
+// score fix-up selectors [KR][STRIP_BLOCK].  Reverse: H-column snapshots [2 halves][ceil(KR/4)][STRIP_BLOCK] uint4 instead of the slots.
+template <int KR, int G, bool NM = false, bool REV = false>
+__host__ __device__ constexpr size_t strip16_smem_bytes()
+{
+    return (REV ? (size_t)2 * ((KR + 3) / 4) * STRIP_BLOCK * sizeof(uint4) : 2 * strip16_slot_bytes<KR, G>()) + (size_t)(G + (NM ? KR : 0)) * STRIP_BLOCK * sizeof(uint32_t);
+}
 
 // REV = false: forward passes (column records written, no early end).  REV = true: reverse passes (ssw.c:820-832): no column records, the
 // pass ends once the terminating score has been seen, and only a stage that REACHES that score can be the winner, so the H-column
@@ -63,15 +76,21 @@ sw_strip16_kernel(const SwTask* __restrict__ tasks, int ntasks, int* __restrict_
     constexpr int KRQ = (KR + 3) / 4;             // snapshot quads per half
     static_assert(G == 2 || G == 4 || G == 8 || G == 16 || G == 32, "G must divide 32");
     constexpr int CAP = 2 * G * KR;               // rows covered by one strip
-    extern __shared__ uint4 snap[];               // [2 halves][KRQ][STRIP_BLOCK]: H column of a stage at its last improvement
-    uint32_t* const crow = reinterpret_cast<uint32_t*>(snap + 2 * KRQ * STRIP_BLOCK);   // [G][STRIP_BLOCK]: column records of the last G steps
+    constexpr int CK = strip_ck(G);               // forward: steps between checkpoints
+    constexpr uint32_t SLOT = (uint32_t)strip16_slot_bytes<KR, G>();
+    constexpr uint32_t SLOT_FH = 2 * KRQ * 16 * STRIP_BLOCK, SLOT_LOG = SLOT_FH + 8 * STRIP_BLOCK;     // byte offsets inside a slot
+    extern __shared__ uint4 snap[];               // reverse: [2 halves][KRQ][STRIP_BLOCK] H column of a stage when it reached the terminating score; forward: 2 slots
+    unsigned char* const smem0 = reinterpret_cast<unsigned char*>(snap);
+    uint32_t* const crow = reinterpret_cast<uint32_t*>(smem0 + (REV ? (size_t)2 * KRQ * STRIP_BLOCK * sizeof(uint4) : (size_t)2 * SLOT));   // [G][STRIP_BLOCK]: column records of the last G steps
     uint32_t* const nfix = crow + G * STRIP_BLOCK;                                        // NM only: [KR][STRIP_BLOCK] fix-up selectors
 
     // the 8 matrix rows are looked up by a run-time target code: shared memory (one LDS) instead of the by-value parameter struct
     // (which ptxas can only index with a chain of predicated constant loads)
-    __shared__ uint32_t smatrow[8];
-    if (threadIdx.x < 8) smatrow[threadIdx.x] = sc.matrow[threadIdx.x];
+    // entries 8..15 are 0: the code of a column past the end of the target (TB_NONE) looks up an all-zero row
+    __shared__ uint32_t smatrow[16];
+    if (threadIdx.x < 16) smatrow[threadIdx.x] = threadIdx.x < 8 ? sc.matrow[threadIdx.x] : 0u;
     __syncthreads();
+    constexpr uint32_t TB_NONE = 8;
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int t = lane % G;                       // thread index inside the group
@@ -79,22 +98,52 @@ sw_strip16_kernel(const SwTask* __restrict__ tasks, int ntasks, int* __restrict_
     // merge selector for (value received from thread t-1, own value): low half <- received.high, high half <- own.low.
     // For the first thread of a group the low half must be the matrix boundary (0): select the sign byte of own byte 7
     // (all merged quantities are >= 0, so that byte replicates to 0x00).
-    const uint32_t mergeSel = (t == 0) ? 0x54ffu : 0x5432u;
+    const uint32_t mergeHi = (t == 0) ? 0x54ffu : 0x5432u;       // received.high | own.low
+    const uint32_t mergeLo = (t == 0) ? 0x54ffu : 0x5410u;       // received.low  | own.low
+    const bool first = t == 0;
 
     uint32_t H[KR], E[KR], sel[KR];
     uint32_t Ftop = 0, Hdtop = 0, cmin = 0;       // boundary values entering this thread's two stages at the next step
     uint32_t a = 0, b = 0;                        // matrix rows of the target bases under the low / high stage
     uint32_t best = 0, cvlo = 0, cvhi = 0;        // per-stage best score (packed) and the step at which it was first reached
-    uint32_t tchunk = 0, tnext = 0;               // matrix rows of target bases [kG + t] of the current / next chunk
+    uint32_t tchunk = 0, tnext = 0;               // matrix rows of target bases [kG + t] of the current / next chunk (tchunk rotates down the group by one lane per step)
+    uint32_t tbyte = TB_NONE;                     // code of target base [(k+2)G + t]: loaded two chunks ahead, looked up one chunk ahead, so neither latency is waited for
     int s = 0, nsteps = 0, dead = 0;
     int rf_len = 0, tdir = 1, tout = 0, wide = 0;
     uint32_t stop2 = 0;                           // reverse passes: score at which the pass may end, in both halves (0: never)
     int64_t rf_base = 0, cm_off = -1;
+    uint32_t ck_off = 0, cstart = 0;              // forward: byte offset of the scratch slot (the committed one is the other), first step of the committed block
     bool active = true;                           // group still has (or may fetch) a task
     const int relist_n = NM ? relist[0] : 0;      // NM: number of flagged pairs to walk
 
 #pragma unroll
     for (int j = 0; j < KR; ++j) { H[j] = 0; E[j] = 0; sel[j] = 0x8888u | 0x4400u; }
+
+    // One target column for this thread's two stages: KR packed cells.  aa / bb: matrix rows of the target bases under the low / high stage.
+    // In: H, E (previous column), Ftop, Hdtop.  Out: H, E (this column), F = F leaving the bottom row, Hdtop = bottom H of the PREVIOUS
+    // column (the diagonal for the stage below), m = maximum over the rows.
+    auto dp_column = [&](const uint32_t aa, const uint32_t bb, uint32_t& F, uint32_t& m) {
+        auto score = [&](const int j) -> uint32_t {
+            const uint32_t v = prmt(aa, bb, sel[j]);
+            return NM ? prmt(v, sc.ncol2, nfix[j * STRIP_BLOCK + tid]) : v;      // N variant: rows holding an N take the N column's constant
+        };
+        F = Ftop; m = 0;
+        uint32_t h = add2(Hdtop, score(0));
+#pragma unroll
+        for (int j = 0; j < KR; ++j) {
+            uint32_t hnext = 0;
+            if (j + 1 < KR) hnext = add2(H[j], score(j + 1));   // uses H(j) of the previous column: diagonal of row j+1
+            else Hdtop = H[j];                                            // bottom H of the previous column: diagonal for the next stage
+            const uint32_t Hn = max3_relu(h, E[j], F);
+            const uint32_t Hg = add2(Hn, sc.mgapO2);
+            E[j] = addmax_relu(E[j], sc.mgapE2, Hg);
+            F = addmax_relu(F, sc.mgapE2, Hg);
+            H[j] = Hn;
+            if (j & 1) m = max3(m, H[j - 1], Hn);
+            else if (j == KR - 1) m = max2(m, Hn);                        // odd KR: the last row has no partner
+            h = hnext;
+        }
+    };
 
     for (;;) {
         // ------------------------------------------------------------------ task boundary (every G steps) -------------
@@ -139,14 +188,50 @@ sw_strip16_kernel(const SwTask* __restrict__ tasks, int ntasks, int* __restrict_
                     int row = -999;
                     if (wscore > 0) {
                         const int half = wstage & 1;
-                        const uint4* sp = snap + (size_t)half * KRQ * STRIP_BLOCK + tid;
-                        for (int k = KRQ - 1; k >= 0; --k) {
-                            uint4 v = sp[(size_t)k * STRIP_BLOCK];
-                            uint32_t w[4] = {v.x, v.y, v.z, v.w};
+                        if (REV) {
+                            const uint4* sp = snap + (size_t)half * KRQ * STRIP_BLOCK + tid;
+                            for (int k = KRQ - 1; k >= 0; --k) {
+                                uint4 v = sp[(size_t)k * STRIP_BLOCK];
+                                uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-                            for (int q = 3; q >= 0; --q) {
-                                int hv = half ? (int)(int16_t)(w[q] >> 16) : (int)(int16_t)(w[q] & 0xffffu);
-                                if (4 * k + q < KR && hv == wscore) row = wstage * KR + 4 * k + q - dead;
+                                for (int q = 3; q >= 0; --q) {
+                                    int hv = half ? (int)(int16_t)(w[q] >> 16) : (int)(int16_t)(w[q] & 0xffffu);
+                                    if (4 * k + q < KR && hv == wscore) row = wstage * KR + 4 * k + q - dead;
+                                }
+                            }
+                        } else {
+                            // ---- replay: restore the committed checkpoint and redo the steps cstart .. s_w of this thread's two stages (the log
+                            //      stands in for the thread above), then read the winning stage's column (ssw.c:284-293: smallest row wins)
+                            const int s_w = (int)(half ? cvhi : cvlo);
+                            const unsigned char* const cs = smem0 + (SLOT - ck_off);
+                            const uint4* const cq = reinterpret_cast<const uint4*>(cs) + tid;
+#pragma unroll
+                            for (int k = 0; k < KRQ; ++k) {
+                                const uint4 hq = cq[(size_t)k * STRIP_BLOCK], eq = cq[(size_t)(KRQ + k) * STRIP_BLOCK];
+                                const uint32_t hw[4] = {hq.x, hq.y, hq.z, hq.w}, ew[4] = {eq.x, eq.y, eq.z, eq.w};
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) if (4 * k + q < KR) { H[4 * k + q] = hw[q]; E[4 * k + q] = ew[q]; }
+                            }
+                            {
+                                const uint2 fh = reinterpret_cast<const uint2*>(cs + SLOT_FH)[tid];
+                                Ftop = fh.x; Hdtop = fh.y;
+                            }
+                            const uint32_t* const lg = reinterpret_cast<const uint32_t*>(cs + SLOT_LOG) + tid;
+                            for (int sr = (int)cstart, k = 0; k < CK; ++sr, ++k) {
+                                const int ia = sr - 2 * t, ib = ia - 1;
+                                const uint32_t ra = (ia >= 0 && ia < rf_len) ? smatrow[seq[rf_base + (int64_t)tdir * ia] & 7] : 0u;
+                                const uint32_t rb = (ib >= 0 && ib < rf_len) ? smatrow[seq[rf_base + (int64_t)tdir * ib] & 7] : 0u;
+                                uint32_t F, m;
+                                dp_column(ra, rb, F, m);
+                                if (sr >= s_w) break;
+                                const uint32_t lw = lg[(size_t)k * STRIP_BLOCK];
+                                Ftop = prmt(lw, F, mergeLo);          // low half <- F the thread above handed down, high half <- own low stage
+                                Hdtop = prmt(lw, Hdtop, mergeHi);     // same for the diagonal H
+                            }
+#pragma unroll
+                            for (int j = KR - 1; j >= 0; --j) {
+                                const int hv = half ? (int)(int16_t)(H[j] >> 16) : (int)(int16_t)(H[j] & 0xffffu);
+                                if (hv == wscore) row = wstage * KR + j - dead;
                             }
                         }
                     }
@@ -185,7 +270,7 @@ sw_strip16_kernel(const SwTask* __restrict__ tasks, int ntasks, int* __restrict_
                 rf_len = 0; nsteps = 0; cm_off = -1; stop2 = 0;
 #pragma unroll
                 for (int j = 0; j < KR; ++j) { H[j] = 0; E[j] = 0; sel[j] = 0x8888u | 0x4400u; }
-                Ftop = Hdtop = cmin = a = b = best = 0; tnext = 0; tchunk = 0;
+                Ftop = Hdtop = cmin = a = b = best = 0; tnext = 0; tchunk = 0; tbyte = TB_NONE;
             } else {
                 const SwTask tk = tasks[ti];
                 const int rd_len = tk.rd_len;
@@ -250,68 +335,39 @@ sw_strip16_kernel(const SwTask* __restrict__ tasks, int ntasks, int* __restrict_
                         if (!NM && relist != nullptr && lane == __ffs((int)refused) - 1) relist[1 + atomicAdd(&relist[0], 1)] = aux + ti;
                     }
                 }
-                {   // matrix rows of target chunk 0
-                    const int idx = t;
+                {   // matrix rows of target chunk 0, code of chunk 1
                     uint32_t mr = 0;
-                    if (idx < rf_len) mr = smatrow[seq[rf_base + (int64_t)tdir * idx] & 7];
+                    if (t < rf_len) mr = smatrow[seq[rf_base + (int64_t)tdir * t] & 7];
                     tnext = mr;
+                    tbyte = (G + t < rf_len) ? (uint32_t)(seq[rf_base + (int64_t)tdir * (G + t)] & 7) : TB_NONE;
                 }
+                ck_off = 0; cstart = 0;
             }
         }
         if (!__any_sync(0xffffffffu, active)) break;
 
-        // rotate the target chunk: tchunk <- chunk s/G, prefetch chunk s/G + 1
+        // rotate the target chunk: tchunk <- chunk s/G, look up chunk s/G + 1, load the codes of chunk s/G + 2
         tchunk = tnext;
+        tnext = smatrow[tbyte];
         {
-            const int idx = s + G + t;
-            uint32_t mr = 0;
-            if (idx < rf_len) mr = smatrow[seq[rf_base + (int64_t)tdir * idx] & 7];
-            tnext = mr;
+            const int idx = s + 2 * G + t;
+            tbyte = idx < rf_len ? (uint32_t)(seq[rf_base + (int64_t)tdir * idx] & 7) : TB_NONE;
         }
 
         // ------------------------------------------------------------------ G wavefront steps ---------------------------
         auto step = [&](const int u) {
-            auto score = [&](const int j) -> uint32_t {
-                const uint32_t v = prmt(a, b, sel[j]);
-                return NM ? prmt(v, sc.ncol2, nfix[j * STRIP_BLOCK + tid]) : v;      // N variant: rows holding an N take the N column's constant
-            };
-            {   // the first stage takes the next target base from the chunk, the others got theirs by shuffle last step
-                const uint32_t a0 = __shfl_sync(0xffffffffu, tchunk, u, G);
-                a = (t == 0) ? a0 : a;
-            }
-            uint32_t F = Ftop, m = 0;
-            uint32_t h = add2(Hdtop, score(0));
-#pragma unroll
-            for (int j = 0; j < KR; ++j) {
-                uint32_t hnext = 0;
-                if (j + 1 < KR) hnext = add2(H[j], score(j + 1));   // uses H(j) of the previous column: diagonal of row j+1
-                else Hdtop = H[j];                                            // bottom H of the previous column: diagonal for the next stage
-                const uint32_t Hn = max3_relu(h, E[j], F);
-                const uint32_t Hg = add2(Hn, sc.mgapO2);
-                E[j] = addmax_relu(E[j], sc.mgapE2, Hg);
-                F = addmax_relu(F, sc.mgapE2, Hg);
-                H[j] = Hn;
-                if (j & 1) m = max3(m, H[j - 1], Hn);
-                else if (j == KR - 1) m = max2(m, Hn);                        // odd KR: the last row has no partner
-                h = hnext;
-            }
+            // the first stage takes the next target base from the chunk (which moves down the group by one lane per step, so the base is
+            // always in the thread's own register), the others got theirs by shuffle last step
+            a = mov_if(first, tchunk, a);
+            tchunk = __shfl_down_sync(0xffffffffu, tchunk, 1, G);
+            uint32_t F, m;
+            dp_column(a, b, F, m);
             // ---- per-stage best tracking: strict improvement keeps the first column (ssw.c:269 / :474)
             bool ge_hi, ge_lo;
             best = max2_track(best, m, ge_hi, ge_lo);
-            if (!REV) {
-                if (!ge_lo) {
-                    cvlo = (uint32_t)s;
-#pragma unroll
-                    for (int k = 0; k < KRQ; ++k) snap[(size_t)k * STRIP_BLOCK + tid] = make_uint4(H[4 * k], H[min(4 * k + 1, KR - 1)], H[min(4 * k + 2, KR - 1)], H[min(4 * k + 3, KR - 1)]);
-                }
-                if (!ge_hi) {
-                    cvhi = (uint32_t)s;
-#pragma unroll
-                    for (int k = 0; k < KRQ; ++k) snap[(size_t)(KRQ + k) * STRIP_BLOCK + tid] = make_uint4(H[4 * k], H[min(4 * k + 1, KR - 1)], H[min(4 * k + 2, KR - 1)], H[min(4 * k + 3, KR - 1)]);
-                }
-            } else {
-                if (!ge_lo) cvlo = (uint32_t)s;
-                if (!ge_hi) cvhi = (uint32_t)s;
+            cvlo = mov_if(!ge_lo, (uint32_t)s, cvlo);
+            cvhi = mov_if(!ge_hi, (uint32_t)s, cvhi);
+            if (REV) {
                 const uint32_t x = best ^ stop2;
                 const bool win_lo = !ge_lo && (x & 0xffffu) == 0u, win_hi = !ge_hi && (x >> 16) == 0u;
                 if (__any_sync(0xffffffffu, win_lo || win_hi)) {
@@ -333,20 +389,44 @@ sw_strip16_kernel(const SwTask* __restrict__ tasks, int ntasks, int* __restrict_
                 crow[u * STRIP_BLOCK + tid] = prmt(cmout, H[KR - 1], 0x7632u);
             }
             // ---- hand the boundary to the next stage
-            const uint32_t rF = __shfl_up_sync(0xffffffffu, F, 1, G);
-            const uint32_t rH = __shfl_up_sync(0xffffffffu, Hdtop, 1, G);
+            //      only the high halves (the thread's second stage) leave the thread: F and the diagonal H travel in one word
+            const uint32_t rX = __shfl_up_sync(0xffffffffu, prmt(F, Hdtop, 0x7632u), 1, G);
             const uint32_t rA = __shfl_up_sync(0xffffffffu, b, 1, G);
-            Ftop = prmt(rF, F, mergeSel);
-            Hdtop = prmt(rH, Hdtop, mergeSel);
+            if (!REV)   // log what came from the thread above: the replay of this block runs without shuffles
+                reinterpret_cast<uint32_t*>(smem0 + ck_off + SLOT_LOG)[(u % CK) * STRIP_BLOCK + tid] = rX;
+            Ftop = prmt(rX, F, mergeLo);
+            Hdtop = prmt(rX, Hdtop, mergeHi);
             if (!REV) {
                 const uint32_t rC = __shfl_up_sync(0xffffffffu, cmout, 1, G);
-                cmin = prmt(rC, cmout, mergeSel);
+                cmin = prmt(rC, cmout, mergeHi);
             }
             b = a;
             a = rA;
         };
+        for (int u0 = 0; u0 < G; u0 += CK) {
+            if (!REV) {
+                // ---- checkpoint into the scratch slot: H / E of this thread's rows and the boundary entering its stages at step s
+                uint4* const cq = reinterpret_cast<uint4*>(smem0 + ck_off) + tid;
+#pragma unroll
+                for (int k = 0; k < KRQ; ++k) {
+                    cq[(size_t)k * STRIP_BLOCK] = make_uint4(H[4 * k], H[min(4 * k + 1, KR - 1)], H[min(4 * k + 2, KR - 1)], H[min(4 * k + 3, KR - 1)]);
+                    cq[(size_t)(KRQ + k) * STRIP_BLOCK] = make_uint4(E[4 * k], E[min(4 * k + 1, KR - 1)], E[min(4 * k + 2, KR - 1)], E[min(4 * k + 3, KR - 1)]);
+                }
+                reinterpret_cast<uint2*>(smem0 + ck_off + SLOT_FH)[tid] = make_uint2(Ftop, Hdtop);
+            }
 #pragma unroll STRIP_UNROLL
-        for (int u = 0; u < G; ++u, ++s) step(u);
+            for (int uu = 0; uu < CK; ++uu, ++s) step(u0 + uu);
+            if (!REV) {
+                // ---- commit: the block just done becomes the committed one iff the better of this thread's two stages (score, then
+                //      earlier column, then the low stage) made its last improvement inside it
+                const uint32_t s0 = (uint32_t)s - CK;
+                if (cvlo >= s0 || cvhi >= s0) {
+                    const int sc_lo = (int)(int16_t)(best & 0xffffu), sc_hi = (int)(int16_t)(best >> 16);
+                    const bool lo_wins = sc_lo > sc_hi || (sc_lo == sc_hi && cvlo + 1u <= cvhi);     // columns: cvlo - 2t against cvhi - 2t - 1, ties to the low stage
+                    if ((lo_wins ? cvlo : cvhi) >= s0) { ck_off = SLOT - ck_off; cstart = s0; }
+                }
+            }
+        }
         // ---- column records of the G steps just done: thread t of the group stores the one of step s - G + t (one 4*G-byte run per group)
         if (!REV) {
             __syncwarp();
