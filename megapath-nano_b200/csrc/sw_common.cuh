@@ -89,6 +89,14 @@ __device__ __forceinline__ uint32_t mov_if(bool c, uint32_t x, uint32_t y)
         : "+r"(y) : "r"((uint32_t)c), "r"(x));
     return y;
 }
+// f01 ? x : y for f01 in {0, 1} as two multiply-adds (fma pipe) instead of a SEL (alu pipe, the busy one): y + f01 * (x - y)
+__device__ __forceinline__ uint32_t blend_first(uint32_t y, uint32_t x, uint32_t f01)
+{
+    uint32_t d, r;
+    asm("mad.lo.u32 %0, %1, 0xffffffff, %2;" : "=r"(d) : "r"(y), "r"(x));      // x - y
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(d), "r"(f01), "r"(y));
+    return r;
+}
 __device__ __forceinline__ uint32_t max3(uint32_t a, uint32_t b, uint32_t c) { return __vimax3_s16x2(a, b, c); }             // VIMNMX3.S16x2
 __device__ __forceinline__ uint32_t addmax_relu(uint32_t a, uint32_t b, uint32_t c) { return __viaddmax_s16x2_relu(a, b, c); } // VIADDMNMX.S16x2.RELU
 

@@ -100,7 +100,7 @@ sw_strip16_kernel(const SwTask* __restrict__ tasks, int ntasks, int* __restrict_
     // (all merged quantities are >= 0, so that byte replicates to 0x00).
     const uint32_t mergeHi = (t == 0) ? 0x54ffu : 0x5432u;       // received.high | own.low
     const uint32_t mergeLo = (t == 0) ? 0x54ffu : 0x5410u;       // received.low  | own.low
-    const bool first = t == 0;
+    const uint32_t first01 = t == 0 ? 1u : 0u;
 
     uint32_t H[KR], E[KR], sel[KR];
     uint32_t Ftop = 0, Hdtop = 0, cmin = 0;       // boundary values entering this thread's two stages at the next step
@@ -112,7 +112,7 @@ sw_strip16_kernel(const SwTask* __restrict__ tasks, int ntasks, int* __restrict_
     int rf_len = 0, tdir = 1, tout = 0, wide = 0;
     uint32_t stop2 = 0;                           // reverse passes: score at which the pass may end, in both halves (0: never)
     int64_t rf_base = 0, cm_off = -1;
-    uint32_t ck_off = 0, cstart = 0;              // forward: byte offset of the scratch slot (the committed one is the other), first step of the committed block
+    uint32_t ck_off = 0, cstart = 0, best0 = 0;   // forward: byte offset of the scratch slot (the committed one is the other), first step of the committed block, best at the last commit test
     bool active = true;                           // group still has (or may fetch) a task
     const int relist_n = NM ? relist[0] : 0;      // NM: number of flagged pairs to walk
 
@@ -122,12 +122,12 @@ sw_strip16_kernel(const SwTask* __restrict__ tasks, int ntasks, int* __restrict_
     // One target column for this thread's two stages: KR packed cells.  aa / bb: matrix rows of the target bases under the low / high stage.
     // In: H, E (previous column), Ftop, Hdtop.  Out: H, E (this column), F = F leaving the bottom row, Hdtop = bottom H of the PREVIOUS
     // column (the diagonal for the stage below), m = maximum over the rows.
-    auto dp_column = [&](const uint32_t aa, const uint32_t bb, uint32_t& F, uint32_t& m) {
+    auto dp_column = [&](const uint32_t aa, const uint32_t bb, uint32_t& F, uint32_t& m, const uint32_t m0 = 0u) {
         auto score = [&](const int j) -> uint32_t {
             const uint32_t v = prmt(aa, bb, sel[j]);
             return NM ? prmt(v, sc.ncol2, nfix[j * STRIP_BLOCK + tid]) : v;      // N variant: rows holding an N take the N column's constant
         };
-        F = Ftop; m = 0;
+        F = Ftop; m = m0;
         uint32_t h = add2(Hdtop, score(0));
 #pragma unroll
         for (int j = 0; j < KR; ++j) {
@@ -163,8 +163,8 @@ sw_strip16_kernel(const SwTask* __restrict__ tasks, int ntasks, int* __restrict_
             }
         }
         if (active && s >= nsteps) {
-            if (nsteps > 0) {
-                // ---- finalize: reduce (score, first column, stage) over the 2G stages of the group
+            if (nsteps > 0 && REV) {
+                // ---- finalize (reverse): reduce (score, first column, stage) over the 2G stages of the group
                 int sc_lo = (int)(int16_t)(best & 0xffffu), sc_hi = (int)(int16_t)(best >> 16);
                 int col_lo = (int)cvlo - 2 * t, col_hi = (int)cvhi - 2 * t - 1;
                 if (sc_lo <= 0) col_lo = 0;
@@ -177,9 +177,6 @@ sw_strip16_kernel(const SwTask* __restrict__ tasks, int ntasks, int* __restrict_
                     unsigned long long o = __shfl_xor_sync(gmask, key, off);
                     key = o > key ? o : key;
                 }
-#ifdef MPN_DEBUG
-                if (tout == 0) printf("fin t=%d best=%08x cvlo=%u cvhi=%u key=%llx s=%d nsteps=%d dead=%d\n", t, best, cvlo, cvhi, key, s, nsteps, dead);
-#endif
                 const int wscore = (int)(key >> 40);
                 const int wcol = (int)(0xffffffu - (unsigned)((key >> 8) & 0xffffffu));
                 const int wstage = 255 - (int)(key & 0xffu);
@@ -188,50 +185,14 @@ sw_strip16_kernel(const SwTask* __restrict__ tasks, int ntasks, int* __restrict_
                     int row = -999;
                     if (wscore > 0) {
                         const int half = wstage & 1;
-                        if (REV) {
-                            const uint4* sp = snap + (size_t)half * KRQ * STRIP_BLOCK + tid;
-                            for (int k = KRQ - 1; k >= 0; --k) {
-                                uint4 v = sp[(size_t)k * STRIP_BLOCK];
-                                uint32_t w[4] = {v.x, v.y, v.z, v.w};
+                        const uint4* sp = snap + (size_t)half * KRQ * STRIP_BLOCK + tid;
+                        for (int k = KRQ - 1; k >= 0; --k) {
+                            uint4 v = sp[(size_t)k * STRIP_BLOCK];
+                            uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-                                for (int q = 3; q >= 0; --q) {
-                                    int hv = half ? (int)(int16_t)(w[q] >> 16) : (int)(int16_t)(w[q] & 0xffffu);
-                                    if (4 * k + q < KR && hv == wscore) row = wstage * KR + 4 * k + q - dead;
-                                }
-                            }
-                        } else {
-                            // ---- replay: restore the committed checkpoint and redo the steps cstart .. s_w of this thread's two stages (the log
-                            //      stands in for the thread above), then read the winning stage's column (ssw.c:284-293: smallest row wins)
-                            const int s_w = (int)(half ? cvhi : cvlo);
-                            const unsigned char* const cs = smem0 + (SLOT - ck_off);
-                            const uint4* const cq = reinterpret_cast<const uint4*>(cs) + tid;
-#pragma unroll
-                            for (int k = 0; k < KRQ; ++k) {
-                                const uint4 hq = cq[(size_t)k * STRIP_BLOCK], eq = cq[(size_t)(KRQ + k) * STRIP_BLOCK];
-                                const uint32_t hw[4] = {hq.x, hq.y, hq.z, hq.w}, ew[4] = {eq.x, eq.y, eq.z, eq.w};
-#pragma unroll
-                                for (int q = 0; q < 4; ++q) if (4 * k + q < KR) { H[4 * k + q] = hw[q]; E[4 * k + q] = ew[q]; }
-                            }
-                            {
-                                const uint2 fh = reinterpret_cast<const uint2*>(cs + SLOT_FH)[tid];
-                                Ftop = fh.x; Hdtop = fh.y;
-                            }
-                            const uint32_t* const lg = reinterpret_cast<const uint32_t*>(cs + SLOT_LOG) + tid;
-                            for (int sr = (int)cstart, k = 0; k < CK; ++sr, ++k) {
-                                const int ia = sr - 2 * t, ib = ia - 1;
-                                const uint32_t ra = (ia >= 0 && ia < rf_len) ? smatrow[seq[rf_base + (int64_t)tdir * ia] & 7] : 0u;
-                                const uint32_t rb = (ib >= 0 && ib < rf_len) ? smatrow[seq[rf_base + (int64_t)tdir * ib] & 7] : 0u;
-                                uint32_t F, m;
-                                dp_column(ra, rb, F, m);
-                                if (sr >= s_w) break;
-                                const uint32_t lw = lg[(size_t)k * STRIP_BLOCK];
-                                Ftop = prmt(lw, F, mergeLo);          // low half <- F the thread above handed down, high half <- own low stage
-                                Hdtop = prmt(lw, Hdtop, mergeHi);     // same for the diagonal H
-                            }
-#pragma unroll
-                            for (int j = KR - 1; j >= 0; --j) {
-                                const int hv = half ? (int)(int16_t)(H[j] >> 16) : (int)(int16_t)(H[j] & 0xffffu);
-                                if (hv == wscore) row = wstage * KR + j - dead;
+                            for (int q = 3; q >= 0; --q) {
+                                int hv = half ? (int)(int16_t)(w[q] >> 16) : (int)(int16_t)(w[q] & 0xffffu);
+                                if (4 * k + q < KR && hv == wscore) row = wstage * KR + 4 * k + q - dead;
                             }
                         }
                     }
@@ -242,7 +203,75 @@ sw_strip16_kernel(const SwTask* __restrict__ tasks, int ntasks, int* __restrict_
                     e.flags = anywide ? SW_FLAG_NEEDS_WIDE : 0;
                     // a reverse pass that did not reach its terminating score has no snapshot to read the row from (cannot happen for a
                     // symmetric recurrence; kept as a guard): redo the pair in the 32-bit kernel
-                    if (REV && stop2 != 0u && (uint32_t)wscore != (stop2 & 0xffffu)) e.flags = SW_FLAG_NEEDS_WIDE;
+                    if (stop2 != 0u && (uint32_t)wscore != (stop2 & 0xffffu)) e.flags = SW_FLAG_NEEDS_WIDE;
+                    out[tout] = e;
+                }
+            }
+            if (nsteps > 0 && !REV) {
+                // ---- finalize (forward).  `best` of a stage is the running maximum over its columns of the column maximum over the stages
+                //      up to and including it, so the stages holding the global maximum S are a suffix.  Every thread holding S replays its
+                //      committed block (the log stands in for the thread above) and looks for the first step at which one of its OWN cells
+                //      equals S; the smallest (column, stage) over the group is the cell of ssw.c:260-277, and the smallest row of that
+                //      stage's column holding S the row of ssw.c:284-293.
+                const int sc_lo = (int)(int16_t)(best & 0xffffu), sc_hi = (int)(int16_t)(best >> 16);
+                int S = max(sc_lo, sc_hi);
+#pragma unroll
+                for (int off = G / 2; off >= 1; off >>= 1) S = max(S, __shfl_xor_sync(gmask, S, off));
+                const unsigned anywide = __ballot_sync(gmask, wide != 0);
+                constexpr unsigned long long NOKEY = ~0ull;
+                unsigned long long key = NOKEY;          // (column << 8 | stage) of this thread's first own cell equal to S
+                int row = 0;
+                if (S > 0 && (sc_lo == S || sc_hi == S)) {
+                    const unsigned char* const cs = smem0 + (SLOT - ck_off);
+                    const uint4* const cq = reinterpret_cast<const uint4*>(cs) + tid;
+#pragma unroll
+                    for (int k = 0; k < KRQ; ++k) {
+                        const uint4 hq = cq[(size_t)k * STRIP_BLOCK], eq = cq[(size_t)(KRQ + k) * STRIP_BLOCK];
+                        const uint32_t hw[4] = {hq.x, hq.y, hq.z, hq.w}, ew[4] = {eq.x, eq.y, eq.z, eq.w};
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) if (4 * k + q < KR) { H[4 * k + q] = hw[q]; E[4 * k + q] = ew[q]; }
+                    }
+                    {
+                        const uint2 fh = reinterpret_cast<const uint2*>(cs + SLOT_FH)[tid];
+                        Ftop = fh.x; Hdtop = fh.y;
+                    }
+                    const uint32_t* const lg = reinterpret_cast<const uint32_t*>(cs + SLOT_LOG) + tid;
+                    // the first hit is the best one of this thread: later steps mean larger columns (a hit in both stages at once: the high
+                    // stage is one column behind, so it wins)
+                    for (int sr = (int)cstart, k = 0; k < CK; ++sr, ++k) {
+                        const int ia = sr - 2 * t, ib = ia - 1;
+                        const uint32_t ra = (ia >= 0 && ia < rf_len) ? smatrow[seq[rf_base + (int64_t)tdir * ia] & 7] : 0u;
+                        const uint32_t rb = (ib >= 0 && ib < rf_len) ? smatrow[seq[rf_base + (int64_t)tdir * ib] & 7] : 0u;
+                        uint32_t F, m;
+                        dp_column(ra, rb, F, m);
+                        const bool hit_lo = (int)(int16_t)(m & 0xffffu) == S, hit_hi = (int)(int16_t)(m >> 16) == S;
+                        if (hit_lo || hit_hi) {
+                            key = hit_hi ? (((unsigned long long)(unsigned)ib << 8) | (unsigned)(2 * t + 1)) : (((unsigned long long)(unsigned)ia << 8) | (unsigned)(2 * t));
+#pragma unroll
+                            for (int j = KR - 1; j >= 0; --j) {
+                                const int hv = hit_hi ? (int)(int16_t)(H[j] >> 16) : (int)(int16_t)(H[j] & 0xffffu);
+                                if (hv == S) row = (2 * t + (hit_hi ? 1 : 0)) * KR + j - dead;
+                            }
+                            break;
+                        }
+                        const uint32_t lw = lg[(size_t)k * STRIP_BLOCK];
+                        Ftop = prmt(lw, F, mergeLo);          // low half <- F the thread above handed down, high half <- own low stage
+                        Hdtop = prmt(lw, Hdtop, mergeHi);     // same for the diagonal H
+                    }
+                }
+                unsigned long long wkey = key;
+#pragma unroll
+                for (int off = G / 2; off >= 1; off >>= 1) {
+                    const unsigned long long o = __shfl_xor_sync(gmask, wkey, off);
+                    wkey = o < wkey ? o : wkey;
+                }
+                if (S <= 0 ? t == 0 : (wkey == NOKEY ? t == 0 : key == wkey)) {
+                    SwEnds e;
+                    e.score = S;
+                    e.col = S > 0 ? (int)(wkey >> 8) : -1;
+                    e.row = S > 0 ? row : 0;
+                    e.flags = anywide ? SW_FLAG_NEEDS_WIDE : 0;
+                    if (S > 0 && wkey == NOKEY) e.flags = SW_FLAG_NEEDS_WIDE;      // guard: no cell found in the committed blocks -> redo the pair in the 32-bit kernel
                     out[tout] = e;
                 }
             }
@@ -339,35 +368,37 @@ sw_strip16_kernel(const SwTask* __restrict__ tasks, int ntasks, int* __restrict_
                     uint32_t mr = 0;
                     if (t < rf_len) mr = smatrow[seq[rf_base + (int64_t)tdir * t] & 7];
                     tnext = mr;
-                    tbyte = (G + t < rf_len) ? (uint32_t)(seq[rf_base + (int64_t)tdir * (G + t)] & 7) : TB_NONE;
+                    tbyte = (G + t < rf_len) ? (uint32_t)(uint8_t)seq[rf_base + (int64_t)tdir * (G + t)] : TB_NONE;
                 }
-                ck_off = 0; cstart = 0;
+                ck_off = 0; cstart = 0; best0 = 0;
             }
         }
         if (!__any_sync(0xffffffffu, active)) break;
 
         // rotate the target chunk: tchunk <- chunk s/G, look up chunk s/G + 1, load the codes of chunk s/G + 2
+        //      (the loaded byte is not touched until the next rotation: nothing here waits for the load)
         tchunk = tnext;
-        tnext = smatrow[tbyte];
+        tnext = smatrow[tbyte & 15u];
         {
             const int idx = s + 2 * G + t;
-            tbyte = idx < rf_len ? (uint32_t)(seq[rf_base + (int64_t)tdir * idx] & 7) : TB_NONE;
+            tbyte = TB_NONE;
+            if (idx < rf_len) tbyte = (uint32_t)(uint8_t)seq[rf_base + (int64_t)tdir * idx];
         }
 
         // ------------------------------------------------------------------ G wavefront steps ---------------------------
         auto step = [&](const int u) {
             // the first stage takes the next target base from the chunk (which moves down the group by one lane per step, so the base is
             // always in the thread's own register), the others got theirs by shuffle last step
-            a = mov_if(first, tchunk, a);
+            a = blend_first(a, tchunk, first01);
             tchunk = __shfl_down_sync(0xffffffffu, tchunk, 1, G);
             uint32_t F, m;
-            dp_column(a, b, F, m);
-            // ---- per-stage best tracking: strict improvement keeps the first column (ssw.c:269 / :474)
-            bool ge_hi, ge_lo;
-            best = max2_track(best, m, ge_hi, ge_lo);
-            cvlo = mov_if(!ge_lo, (uint32_t)s, cvlo);
-            cvhi = mov_if(!ge_hi, (uint32_t)s, cvhi);
+            dp_column(a, b, F, m, REV ? 0u : cmin);
             if (REV) {
+                // ---- per-stage best tracking: strict improvement keeps the first column (ssw.c:269 / :474)
+                bool ge_hi, ge_lo;
+                best = max2_track(best, m, ge_hi, ge_lo);
+                cvlo = mov_if(!ge_lo, (uint32_t)s, cvlo);
+                cvhi = mov_if(!ge_hi, (uint32_t)s, cvhi);
                 const uint32_t x = best ^ stop2;
                 const bool win_lo = !ge_lo && (x & 0xffffu) == 0u, win_hi = !ge_hi && (x >> 16) == 0u;
                 if (__any_sync(0xffffffffu, win_lo || win_hi)) {
@@ -383,7 +414,10 @@ sw_strip16_kernel(const SwTask* __restrict__ tasks, int ntasks, int* __restrict_
             }
             uint32_t cmout = 0;
             if (!REV) {
-                cmout = max2(cmin, m);
+                // forward: m already holds the column maximum over the stages up to this one (dp_column starts from cmin); the best of a
+                // stage is tracked on that, without positions -- the replay finds them (see finalize)
+                cmout = m;
+                best = max2(best, m);
                 // ---- (column maximum, bottom-row H) of this step: staged in shared memory by every thread, only the last stage's
                 //      entry is a finished column (s - (2G-1)); the group writes G of them to global memory after the loop
                 crow[u * STRIP_BLOCK + tid] = prmt(cmout, H[KR - 1], 0x7632u);
@@ -419,11 +453,16 @@ sw_strip16_kernel(const SwTask* __restrict__ tasks, int ntasks, int* __restrict_
             if (!REV) {
                 // ---- commit: the block just done becomes the committed one iff the better of this thread's two stages (score, then
                 //      earlier column, then the low stage) made its last improvement inside it
-                const uint32_t s0 = (uint32_t)s - CK;
-                if (cvlo >= s0 || cvhi >= s0) {
+                //      (cvlo / cvhi hold the first step of the block in which the stage last improved; best0 = best at the last look)
+                const uint32_t imp = best ^ best0;
+                if (imp != 0u) {
+                    const uint32_t s0 = (uint32_t)s - CK;
+                    if (imp & 0xffffu) cvlo = s0;
+                    if (imp >> 16) cvhi = s0;
                     const int sc_lo = (int)(int16_t)(best & 0xffffu), sc_hi = (int)(int16_t)(best >> 16);
-                    const bool lo_wins = sc_lo > sc_hi || (sc_lo == sc_hi && cvlo + 1u <= cvhi);     // columns: cvlo - 2t against cvhi - 2t - 1, ties to the low stage
-                    if ((lo_wins ? cvlo : cvhi) >= s0) { ck_off = SLOT - ck_off; cstart = s0; }
+                    const bool lo_wins = sc_lo > sc_hi || (sc_lo == sc_hi && cvlo <= cvhi);          // same block: the replay looks at both stages
+                    if ((lo_wins ? cvlo : cvhi) == s0) { ck_off = SLOT - ck_off; cstart = s0; }
+                    best0 = best;
                 }
             }
         }

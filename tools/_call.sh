@@ -1,3 +1,2 @@
-set -x
-MPN_VERBOSE=1 python tools/phase_bench.py 400000 2 2>&1 | tail -45
+python tools/phase_bench.py 400000 2 2>&1 | tail -1
 python -m pytest tests/test_gpu_parity.py -x -q 2>&1 | tail -15
