@@ -110,7 +110,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    w = importlib.import_module(PKG + ".workloads")
+    w = importlib.import_module("workloads")
     ncores = os.cpu_count() or 1
     wl_name = {1: "configs[0]: 250bp reads x 500bp targets, flag 0", 2: "configs[1]: U{150..300}bp reads x 1kb haplotypes, flag 1 (begin + banded traceback + CIGAR)"}[args.config]
 

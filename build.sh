@@ -14,7 +14,7 @@ OBJ=build/obj${MPN_BUILD_TAG:+_$MPN_BUILD_TAG}
 OUT=${MPN_SSW_OUT:-megapath-nano_b200/libmpn_ssw.so}
 mkdir -p $OBJ
 pids=()
-for f in engine ssw_abi strip_inst_a strip_inst_b strip_inst_c strip_inst_d; do
+for f in engine pool ssw_abi strip_inst_a strip_inst_b strip_inst_c strip_inst_d; do
     nvcc $NVCC_FLAGS -c -o $OBJ/$f.o megapath-nano_b200/csrc/$f.cu &
     pids+=($!)
 done
@@ -24,7 +24,7 @@ for f in ssw_cpp_layer realign_region; do
     pids+=($!)
 done
 for p in "${pids[@]}"; do wait $p; done
-nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $OUT $OBJ/engine.o $OBJ/ssw_abi.o $OBJ/strip_inst_a.o $OBJ/strip_inst_b.o $OBJ/strip_inst_c.o $OBJ/strip_inst_d.o $OBJ/ssw_cpp_layer.o $OBJ/realign_region.o
+nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $OUT $OBJ/engine.o $OBJ/pool.o $OBJ/ssw_abi.o $OBJ/strip_inst_a.o $OBJ/strip_inst_b.o $OBJ/strip_inst_c.o $OBJ/strip_inst_d.o $OBJ/ssw_cpp_layer.o $OBJ/realign_region.o
 [ -n "$MPN_SSW_OUT" ] && exit 0
 cp megapath-nano_b200/libmpn_ssw.so megapath-nano_b200/realign/libssw.so
 # the reference builds `realigner` as a shared object without suffix (README.md:45 of the reference); same file, all symbols

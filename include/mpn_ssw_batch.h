@@ -107,6 +107,33 @@ int mpn_batch_io_bytes(const mpn_batch* b, int64_t* h2d, int64_t* d2h);
 void mpn_batch_free(mpn_batch* b);
 
 /*
+ * ---- one batch over several GPUs of a box ---------------------------------------------------------------
+ * Replaces the reference's process fan-out (bin/realignment/realignment.sh:34-39, 50-60: GNU parallel, one process per chromosome /
+ * candidate position) inside one process: a pool owns one engine and one host thread per device.  A batch is cut, in the caller's
+ * order, into ranges of about equal cost (forward cells x relative cost of the score kernel a pair takes), heaviest first, that the
+ * device threads pull from one queue; inside a range the engine bins by read length and sorts by target length as for any batch.
+ * No collective: every device copies its ranges from the caller's buffers and writes its records into out[] at the range's position;
+ * CIGAR words go to per-range regions of the caller's arena (not compact; mpn_result.cigar_off is the absolute index as everywhere).
+ * Results are identical to mpn_align_batch on one device, pair by pair.
+ *
+ *   devices / ndev   device ordinals; devices == NULL: 0 .. ndev-1; ndev <= 0: every visible device.  NULL without a CUDA device.
+ * A pool runs one batch at a time (calls from several threads serialise).
+ */
+typedef struct mpn_pool mpn_pool;
+mpn_pool* mpn_pool_create(const int* devices, int ndev);
+void mpn_pool_destroy(mpn_pool* pl);
+int mpn_pool_ndev(const mpn_pool* pl);
+mpn_engine* mpn_pool_engine(mpn_pool* pl, int k);      /* the engine of device k (statistics); owned by the pool */
+int mpn_pool_align_batch(mpn_pool* pl, const mpn_params* p, const int8_t* reads, const int64_t* read_off, const int8_t* refs,
+                         const int64_t* ref_off, const int32_t* masklen, int64_t npairs, mpn_result* out, uint32_t* cigar, int64_t cigar_cap);
+/* spans form (pairs sharing sequences): one range per device, every device uploads the arena once */
+int mpn_pool_align_batch_spans(mpn_pool* pl, const mpn_params* p, const int8_t* seq, int64_t seq_bytes, const int64_t* rd_start, const int32_t* rd_len,
+                               const int64_t* rf_start, const int32_t* rf_len, const int32_t* masklen, int64_t npairs,
+                               mpn_result* out, uint32_t* cigar, int64_t cigar_cap);
+/* per device, for the last batch: host wall milliseconds of its share, pairs and forward cells it processed (arrays of mpn_pool_ndev entries, any may be NULL) */
+int mpn_pool_last_shares(const mpn_pool* pl, double* ms, int64_t* pairs, int64_t* cells);
+
+/*
  * ---- k-mer fast pass of the region realigner on the GPU ----------------------------------------
  * Replaces, for many regions at once, the reference's BuildIndex + FastAlignReadsToHaplotype + FastAlignStrings
  * (realigner.cpp:429-451, :170-230, :232-253): every read of a region against every haplotype of that region, ungapped, at most

@@ -44,6 +44,17 @@ def lib():
                                       ct.c_void_p, ct.c_void_p, ct.c_int64]
         L.mpn_align_batch_spans.argtypes = [ct.c_void_p, ct.POINTER(MpnParams), ct.c_void_p, ct.c_int64, ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_void_p,
                                             ct.c_void_p, ct.c_int64, ct.c_void_p, ct.c_void_p, ct.c_int64]
+        L.mpn_pool_create.restype = ct.c_void_p
+        L.mpn_pool_create.argtypes = [ct.c_void_p, ct.c_int]
+        L.mpn_pool_destroy.argtypes = [ct.c_void_p]
+        L.mpn_pool_ndev.argtypes = [ct.c_void_p]
+        L.mpn_pool_engine.restype = ct.c_void_p
+        L.mpn_pool_engine.argtypes = [ct.c_void_p, ct.c_int]
+        L.mpn_pool_align_batch.argtypes = [ct.c_void_p, ct.POINTER(MpnParams), ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_int64,
+                                           ct.c_void_p, ct.c_void_p, ct.c_int64]
+        L.mpn_pool_align_batch_spans.argtypes = [ct.c_void_p, ct.POINTER(MpnParams), ct.c_void_p, ct.c_int64, ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_void_p,
+                                                 ct.c_void_p, ct.c_int64, ct.c_void_p, ct.c_void_p, ct.c_int64]
+        L.mpn_pool_last_shares.argtypes = [ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_void_p]
         assert ct.sizeof(MpnParams) == 40 and RESULT_DTYPE.itemsize == 40, (ct.sizeof(MpnParams), RESULT_DTYPE.itemsize)
         _lib = L
     return _lib
@@ -139,6 +150,74 @@ class Engine:
         if rc:
             raise RuntimeError(f"mpn_align_batch -> {rc}")
         return out, cig
+
+
+class Pool:
+    """One batch over several GPUs of the box (mpn_pool_*): an engine + a host thread per device, ranges of about equal cost pulled from
+    one queue, records written straight into the caller's arrays -- no collective.  devices: list of ordinals,
+    an int (the first n devices) or None (every visible device)."""
+
+    def __init__(self, devices=None):
+        self.L = lib()
+        if devices is None:
+            self.h = self.L.mpn_pool_create(None, 0)
+        elif isinstance(devices, int):
+            self.h = self.L.mpn_pool_create(None, int(devices))
+        else:
+            arr = (ct.c_int * len(devices))(*[int(d) for d in devices])
+            self.h = self.L.mpn_pool_create(arr, len(devices))
+        if not self.h:
+            raise RuntimeError("mpn_pool_create failed: no CUDA device / bad device list (there is no CPU fallback)")
+        self.ndev = self.L.mpn_pool_ndev(self.h)
+
+    def close(self):
+        if self.h:
+            self.L.mpn_pool_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def align(self, b, cigar_cap=None, out=None, cig=None):
+        n = int(b.npairs)
+        if cigar_cap is None:
+            cigar_cap = n * 24 + int(len(b.reads)) // 4 + 4096 + 2048 * max(self.ndev, 1) * 16
+        out = np.zeros(n, dtype=RESULT_DTYPE) if out is None else out
+        cig = np.zeros(max(cigar_cap, 1), dtype=np.uint32) if cig is None else cig
+        keep = []
+        p = Engine._params(self, b, keep)
+        rc = self.L.mpn_pool_align_batch(self.h, ct.byref(p), _ptr(b.reads), _ptr(b.read_off), _ptr(b.refs), _ptr(b.ref_off), _ptr(b.masklen), n,
+                                         _ptr(out), _ptr(cig), int(cigar_cap))
+        if rc:
+            raise RuntimeError(f"mpn_pool_align_batch -> {rc}")
+        return out, cig
+
+    def align_spans(self, b, seq, rd_start, rd_len, rf_start, rf_len, masklen, cigar_cap=None):
+        seq = np.ascontiguousarray(seq, dtype=np.int8)
+        rd_start = np.ascontiguousarray(rd_start, dtype=np.int64); rf_start = np.ascontiguousarray(rf_start, dtype=np.int64)
+        rd_len = np.ascontiguousarray(rd_len, dtype=np.int32); rf_len = np.ascontiguousarray(rf_len, dtype=np.int32)
+        masklen = np.ascontiguousarray(masklen, dtype=np.int32)
+        n = len(rd_start)
+        if cigar_cap is None:
+            cigar_cap = int(rd_len.sum() + rf_len.sum()) + 16 * n + 4096
+        out = np.zeros(n, dtype=RESULT_DTYPE)
+        cig = np.zeros(max(cigar_cap, 1), dtype=np.uint32)
+        keep = []
+        p = Engine._params(self, b, keep)
+        rc = self.L.mpn_pool_align_batch_spans(self.h, ct.byref(p), _ptr(seq), len(seq), _ptr(rd_start), _ptr(rd_len), _ptr(rf_start), _ptr(rf_len), _ptr(masklen), n,
+                                               _ptr(out), _ptr(cig), int(cigar_cap))
+        if rc:
+            raise RuntimeError(f"mpn_pool_align_batch_spans -> {rc}")
+        return out, cig
+
+    def last_shares(self):
+        """per device: (host wall ms, pairs, forward cells) of its share of the last batch"""
+        ms = np.zeros(self.ndev, dtype=np.float64); pr = np.zeros(self.ndev, dtype=np.int64); ce = np.zeros(self.ndev, dtype=np.int64)
+        self.L.mpn_pool_last_shares(self.h, _ptr(ms), _ptr(pr), _ptr(ce))
+        return [dict(ms=float(ms[k]), pairs=int(pr[k]), cells=int(ce[k])) for k in range(self.ndev)]
 
 
 def _align_spans(self, b, seq, rd_start, rd_len, rf_start, rf_len, masklen, cigar_cap=None):

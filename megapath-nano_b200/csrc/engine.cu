@@ -13,6 +13,7 @@
 #include "sw_trace_rows.cuh"
 #include "fastpass.cuh"
 #include "host_shared.h"
+#include "engine_internal.h"
 
 #include <algorithm>
 #include <atomic>
@@ -287,40 +288,6 @@ extern "C" void mpn_batch_free(mpn_batch* b)
     for (DevBuf* d : bufs) b->e->pool.give(*d);
     delete b;
 }
-
-// Where the sequences of a batch come from.  Both forms end up as one device arena plus (start, length) spans per pair.
-//   CsrPairs   reads / refs as two CSR arrays (mpn_batch_upload): arena = [reads | refs], copied straight from the caller's buffers
-//   SpanPairs  one caller arena + explicit spans (mpn_batch_upload_spans): pairs may share sequences (a haplotype aligned to many reads)
-struct CsrPairs {
-    const int8_t* reads; const int64_t* read_off; const int8_t* refs; const int64_t* ref_off; int64_t npairs;
-    int64_t reads_total() const { return npairs ? read_off[npairs] - read_off[0] : 0; }
-    int64_t refs_total() const { return npairs ? ref_off[npairs] - ref_off[0] : 0; }
-    int64_t rl(int64_t i) const { return read_off[i + 1] - read_off[i]; }
-    int64_t fl(int64_t i) const { return ref_off[i + 1] - ref_off[i]; }
-    int64_t rd_base(int64_t i) const { return read_off[i] - read_off[0]; }
-    int64_t rf_base(int64_t i) const { return reads_total() + (ref_off[i] - ref_off[0]); }
-    bool valid() const { return npairs == 0 || (reads && read_off && refs && ref_off); }
-    bool span_ok(int64_t) const { return true; }
-    size_t arena_bytes() const { return (size_t)(reads_total() + refs_total()); }
-    void copy_arena(int8_t* dst, cudaStream_t st) const {
-        if (!npairs) return;
-        if (reads_total()) cudaMemcpyAsync(dst, reads + read_off[0], (size_t)reads_total(), cudaMemcpyHostToDevice, st);
-        if (refs_total()) cudaMemcpyAsync(dst + reads_total(), refs + ref_off[0], (size_t)refs_total(), cudaMemcpyHostToDevice, st);
-    }
-    int64_t read_bases() const { return reads_total(); }
-};
-struct SpanPairs {
-    const int8_t* seq; int64_t seq_bytes; const int64_t* rd_start; const int32_t* rd_len; const int64_t* rf_start; const int32_t* rf_len; int64_t npairs;
-    int64_t rl(int64_t i) const { return rd_len[i]; }
-    int64_t fl(int64_t i) const { return rf_len[i]; }
-    int64_t rd_base(int64_t i) const { return rd_start[i]; }
-    int64_t rf_base(int64_t i) const { return rf_start[i]; }
-    bool valid() const { return seq_bytes >= 0 && (npairs == 0 || (seq && rd_start && rd_len && rf_start && rf_len)); }
-    bool span_ok(int64_t i) const { return rd_start[i] >= 0 && rf_start[i] >= 0 && rd_start[i] + rd_len[i] <= seq_bytes && rf_start[i] + rf_len[i] <= seq_bytes; }
-    size_t arena_bytes() const { return (size_t)seq_bytes; }
-    void copy_arena(int8_t* dst, cudaStream_t st) const { if (seq_bytes) cudaMemcpyAsync(dst, seq, (size_t)seq_bytes, cudaMemcpyHostToDevice, st); }
-    int64_t read_bases() const { int64_t t = 0; for (int64_t i = 0; i < npairs; ++i) t += rd_len[i]; return t; }
-};
 
 template <class Pairs>
 static mpn_batch* upload_impl(mpn_engine* e, int slot_id, const mpn_params* p, const Pairs& src, const int32_t* masklen, int64_t npairs)
@@ -849,50 +816,77 @@ extern "C" int mpn_align_batch(mpn_engine* e, const mpn_params* p, const int8_t*
         for (size_t k = tail_sizes.size(); k-- > 0;) { at += tail_sizes[k]; bounds.push_back(at); }
     }
     const int64_t nchunks = (int64_t)bounds.size() - 1;
-    // ring of in-flight chunks, one pipeline slot each (own stream + own pinned staging).  Several chunks are queued on the GPU at any
-    // time, so the persistent grids of chunk k+1 fill the SMs that the tail of chunk k leaves idle, and the host work of a chunk
-    // (scheduling, H2D enqueue, D2H + record conversion) hides behind the kernels of the others.  Fetch order = chunk order (CIGAR offsets).
+    int64_t c = 0;
+    return mpn::run_ranges(e, p, CsrPairs{reads, read_off, refs, ref_off, npairs}, masklen,
+                           [&](mpn::RangeJob& r) { if (c >= nchunks) return false; r.first = bounds[c]; r.count = bounds[c + 1] - bounds[c]; r.cig_base = -1; ++c; return r.count > 0; },
+                           out, cigar, cigar_cap, nullptr, nullptr);
+}
+
+template <class Pairs>
+int mpn::run_ranges(mpn_engine* e, const mpn_params* p, const Pairs& all, const int32_t* masklen, const std::function<bool(RangeJob&)>& next,
+                    mpn_result* out, uint32_t* cigar, int64_t cigar_cap, int64_t* pairs_done, int64_t* cells_done)
+{
+    // ring of in-flight ranges, one pipeline slot each (own stream + own pinned staging).  Several ranges are queued on the GPU at any
+    // time, so the persistent grids of range k+1 fill the SMs that the tail of range k leaves idle, and the host work of a range
+    // (scheduling, H2D enqueue, D2H + record conversion) hides behind the kernels of the others.  Fetch order = issue order.
     constexpr int DEPTH = mpn_engine::NSLOT - 1;
     static const bool timing = getenv("MPN_TIMING") != nullptr;
     auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double t_begin = now();
     double t_upload = 0, t_run = 0, t_drain = 0, t_first = 0;
     mpn_batch* inflight[DEPTH] = {};
-    int64_t start_of[DEPTH] = {};
-    int64_t cig_base = 0;
+    RangeJob job_of[DEPTH];
+    int64_t cig_cursor = 0, npairs = 0, ncells = 0;
     int rc = 0;
     auto drain = [&](int s) {
         if (!inflight[s]) return;
         const double td = now();
         int64_t words = 0;
-        const int r2 = fetch_impl(inflight[s], out + start_of[s], cigar ? cigar + cig_base : nullptr, cigar_cap - cig_base, cig_base, &words);
+        const RangeJob& j = job_of[s];
+        const int64_t base = j.cig_base < 0 ? cig_cursor : j.cig_base, cap = j.cig_base < 0 ? cigar_cap - cig_cursor : j.cig_cap;
+        const int r2 = fetch_impl(inflight[s], out + j.first, cigar ? cigar + base : nullptr, cap, base, &words);
         if (r2 != 0 && rc == 0) rc = r2;
-        cig_base += words;
+        if (j.cig_base < 0) cig_cursor += words;
+        npairs += inflight[s]->npairs; ncells += inflight[s]->total_cells;
         mpn_batch_free(inflight[s]);
         inflight[s] = nullptr;
         t_drain += now() - td;
     };
     int64_t issued = 0;
-    for (int64_t c = 0; c < nchunks; ++c, ++issued) {
-        const int s = (int)(c % DEPTH);
-        drain(s);                                   // the oldest chunk (c - DEPTH) used this slot
-        const int64_t c0 = bounds[c], n_c = bounds[c + 1] - c0;
-        if (n_c <= 0) break;
+    for (;; ++issued) {
+        const int s = (int)(issued % DEPTH);
+        drain(s);                                   // the oldest range (issued - DEPTH) used this slot
+        RangeJob j;
+        if (rc != 0 || !next(j)) break;
         const double tu = now();
-        mpn_batch* b = upload_impl(e, 1 + s, p, CsrPairs{reads, read_off + c0, refs, ref_off + c0, n_c}, masklen + c0, n_c);
+        mpn_batch* b = upload_impl(e, 1 + s, p, all.slice(j.first, j.count), masklen + j.first, j.count);
         if (!b) { rc = MPN_E_ARG; break; }
         const double tr = now();
         mpn_batch_run(b);
-        inflight[s] = b; start_of[s] = c0;
+        inflight[s] = b; job_of[s] = j;
         t_upload += tr - tu; t_run += now() - tr;
-        if (c == 0) t_first = now() - t_begin;
+        if (issued == 0) t_first = now() - t_begin;
     }
     const double t_issued = now();
-    // the remaining chunks, oldest first
+    // the remaining ranges, oldest first
     for (int64_t c = std::max<int64_t>(0, issued - DEPTH); c < issued + DEPTH; ++c) drain((int)(c % DEPTH));
-    if (timing) fprintf(stderr, "[mpn_ssw] align_batch %lld pairs in %lld chunks: total %.2f ms (first chunk enqueued at %.2f, all issued at %.2f); host: upload %.2f, enqueue %.2f, drain (wait + copy + convert) %.2f\n",
-                        (long long)npairs, (long long)nchunks, now() - t_begin, t_first, t_issued - t_begin, t_upload, t_run, t_drain);
+    if (timing) fprintf(stderr, "[mpn_ssw] device %d: %lld pairs in %lld ranges: total %.2f ms (first range enqueued at %.2f, all issued at %.2f); host: upload %.2f, enqueue %.2f, drain (wait + copy + convert) %.2f\n",
+                        e->device, (long long)npairs, (long long)issued, now() - t_begin, t_first, t_issued - t_begin, t_upload, t_run, t_drain);
+    if (pairs_done) *pairs_done = npairs;
+    if (cells_done) *cells_done = ncells;
     return rc;
+}
+template int mpn::run_ranges<mpn::CsrPairs>(mpn_engine*, const mpn_params*, const mpn::CsrPairs&, const int32_t*, const std::function<bool(mpn::RangeJob&)>&, mpn_result*, uint32_t*, int64_t, int64_t*, int64_t*);
+template int mpn::run_ranges<mpn::SpanPairs>(mpn_engine*, const mpn_params*, const mpn::SpanPairs&, const int32_t*, const std::function<bool(mpn::RangeJob&)>&, mpn_result*, uint32_t*, int64_t, int64_t*, int64_t*);
+
+int mpn::engine_device(const mpn_engine* e) { return e ? e->device : -1; }
+
+// mirror of the host classifier in upload_impl: which score kernel a pair takes, as a relative cost per cell
+double mpn::pair_cost_per_cell(int n, int maxpos, int64_t rl, int64_t fl)
+{
+    if (n > 8) return 4.0;                                                     // 32-bit kernel
+    if ((std::min(rl, fl) + 1) * (int64_t)maxpos <= 32767 && rl <= 1280) return 1.0;      // packed short-read kernel
+    return 1.55;                                                               // multi-strip kernel with the int16 clamp
 }
 
 

@@ -1,0 +1,64 @@
+// Internals of the batched engine that the multi-device pool (pool.cu) shares with engine.cu.  Not part of the C ABI.
+#pragma once
+#include "../../include/mpn_ssw_batch.h"
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <functional>
+
+namespace mpn {
+
+// Where the sequences of a batch come from.  Both forms end up as one device arena plus (start, length) spans per pair.
+//   CsrPairs   reads / refs as two CSR arrays (mpn_batch_upload): arena = [reads | refs], copied straight from the caller's buffers
+//   SpanPairs  one caller arena + explicit spans (mpn_batch_upload_spans): pairs may share sequences (a haplotype aligned to many reads)
+struct CsrPairs {
+    const int8_t* reads; const int64_t* read_off; const int8_t* refs; const int64_t* ref_off; int64_t npairs;
+    int64_t reads_total() const { return npairs ? read_off[npairs] - read_off[0] : 0; }
+    int64_t refs_total() const { return npairs ? ref_off[npairs] - ref_off[0] : 0; }
+    int64_t rl(int64_t i) const { return read_off[i + 1] - read_off[i]; }
+    int64_t fl(int64_t i) const { return ref_off[i + 1] - ref_off[i]; }
+    int64_t rd_base(int64_t i) const { return read_off[i] - read_off[0]; }
+    int64_t rf_base(int64_t i) const { return reads_total() + (ref_off[i] - ref_off[0]); }
+    bool valid() const { return npairs == 0 || (reads && read_off && refs && ref_off); }
+    bool span_ok(int64_t) const { return true; }
+    size_t arena_bytes() const { return (size_t)(reads_total() + refs_total()); }
+    void copy_arena(int8_t* dst, cudaStream_t st) const {
+        if (!npairs) return;
+        if (reads_total()) cudaMemcpyAsync(dst, reads + read_off[0], (size_t)reads_total(), cudaMemcpyHostToDevice, st);
+        if (refs_total()) cudaMemcpyAsync(dst + reads_total(), refs + ref_off[0], (size_t)refs_total(), cudaMemcpyHostToDevice, st);
+    }
+    int64_t read_bases() const { return reads_total(); }
+    CsrPairs slice(int64_t first, int64_t count) const { return CsrPairs{reads, read_off + first, refs, ref_off + first, count}; }
+};
+struct SpanPairs {
+    const int8_t* seq; int64_t seq_bytes; const int64_t* rd_start; const int32_t* rd_len; const int64_t* rf_start; const int32_t* rf_len; int64_t npairs;
+    int64_t rl(int64_t i) const { return rd_len[i]; }
+    int64_t fl(int64_t i) const { return rf_len[i]; }
+    int64_t rd_base(int64_t i) const { return rd_start[i]; }
+    int64_t rf_base(int64_t i) const { return rf_start[i]; }
+    bool valid() const { return seq_bytes >= 0 && (npairs == 0 || (seq && rd_start && rd_len && rf_start && rf_len)); }
+    bool span_ok(int64_t i) const { return rd_start[i] >= 0 && rf_start[i] >= 0 && rd_start[i] + rd_len[i] <= seq_bytes && rf_start[i] + rf_len[i] <= seq_bytes; }
+    size_t arena_bytes() const { return (size_t)seq_bytes; }
+    void copy_arena(int8_t* dst, cudaStream_t st) const { if (seq_bytes) cudaMemcpyAsync(dst, seq, (size_t)seq_bytes, cudaMemcpyHostToDevice, st); }
+    int64_t read_bases() const { int64_t t = 0; for (int64_t i = 0; i < npairs; ++i) t += rd_len[i]; return t; }
+    SpanPairs slice(int64_t first, int64_t count) const { return SpanPairs{seq, seq_bytes, rd_start + first, rd_len + first, rf_start + first, rf_len + first, count}; }
+};
+
+// A contiguous run of pairs of a caller's batch, and where its CIGAR words go in the caller's arena.
+struct RangeJob {
+    int64_t first = 0, count = 0;
+    int64_t cig_base = -1;     // < 0: append at the engine's running cursor (one engine, ranges in order); else the range owns [cig_base, cig_base + cig_cap)
+    int64_t cig_cap = 0;
+};
+
+// One engine, many ranges: keeps up to four ranges in flight (own stream + own pinned staging each), so the host work of a range
+// (scheduling, H2D enqueue, D2H + record conversion) hides behind the kernels of the others.  `next` hands out ranges until it
+// returns false (it may be shared between engines: the pool's devices pull from one queue).  Records land at out[first ..).
+template <class Pairs>
+int run_ranges(mpn_engine* e, const mpn_params* p, const Pairs& all, const int32_t* masklen, const std::function<bool(RangeJob&)>& next,
+               mpn_result* out, uint32_t* cigar, int64_t cigar_cap, int64_t* pairs_done, int64_t* cells_done);
+
+// which score kernel a pair goes to and its relative cost per cell (strip16 = 1): the pool balances ranges on cells x cost
+double pair_cost_per_cell(int n, int maxpos, int64_t rl, int64_t fl);
+int engine_device(const mpn_engine* e);
+
+}  // namespace mpn

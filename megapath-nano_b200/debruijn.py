@@ -88,12 +88,12 @@ expand_align_ref_region = 20         # realign_illumina_reads.py:18
 
 
 def regions_from_windows(windows, lib_path=None):
-    """The chain of realign_illumina_reads.py:551-593 for many windows (workloads.WindowWorkload): assemble the candidate haplotypes
+    """The chain of realign_illumina_reads.py:551-593 for many windows (anything with chrom, chrom_start, win_start, win_end, reads, positions, cigars, low_quality): assemble the candidate haplotypes
     of every window (one mpn_dbg_consensus_packed call), drop windows without an alternative haplotype (:564-566), widen the reference
     to the span of the reads + 20 bp (:567-577) and build the realigner's inputs (:593).  Returns (regions, kept window indices);
     the regions go to realigner.realign_regions."""
     import importlib
-    W = importlib.import_module(__package__ + ".workloads")
+    Region = importlib.import_module(__package__ + ".realigner").Region
     cons = consensus_windows([(w.chrom[w.win_start:w.win_end], w.reads, w.low_quality) for w in windows], lib_path)
     regions, kept = [], []
     for k, (w, consensus) in enumerate(zip(windows, cons)):
@@ -108,7 +108,7 @@ def regions_from_windows(windows, lib_path=None):
         ref_prefix = w.chrom[tmp_ref_start - w.chrom_start:w.win_start]
         ref_suffix = w.chrom[w.win_end:tmp_ref_end - w.chrom_start]
         n = min(1000, len(w.reads))
-        regions.append(W.RegionWorkload(ref_prefix + ref + ref_suffix, [ref_prefix + c + ref_suffix for c in consensus],
+        regions.append(Region(ref_prefix + ref + ref_suffix, [ref_prefix + c + ref_suffix for c in consensus],
                                         [r.upper() for r in w.reads[:n]], list(w.positions[:n]), list(w.cigars[:n]), tmp_ref_start, len(ref_prefix), len(ref_suffix)))
         kept.append(k)
     return regions, kept

@@ -6,6 +6,7 @@
 
 There is no CPU path: the shared object aborts without a CUDA device."""
 import ctypes
+import dataclasses
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -40,6 +41,19 @@ def load(path=None):
     return _libs[path]
 
 
+
+@dataclasses.dataclass
+class Region:
+    """one realigner call: the arguments of realign_reads (realigner.cpp:856, realign_illumina_reads.py:586-605) as Python values"""
+    reference: str
+    haplotypes: list
+    reads: list
+    positions: list
+    cigars: list
+    ref_start: int
+    ref_prefix: int
+    ref_suffix: int
+
 def byte(x):
     return x if isinstance(x, bytes) else x.encode()
 
@@ -54,7 +68,7 @@ def _marshal(region):
 
 def realign_reads(region, lib_path=None):
     """region: anything with reference, haplotypes (list), reads, positions, cigars, ref_start, ref_prefix, ref_suffix
-    (workloads.RegionWorkload).  Same call sequence as realign_illumina_reads.py:586-612; works against the reference's own
+    (realigner.Region).  Same call sequence as realign_illumina_reads.py:586-612; works against the reference's own
     `realigner` as well (lib_path) -- that is how the parity tests drive both."""
     L = load(lib_path)
     n, seq_list, position_list, cigars_list = _marshal(region)

@@ -5,7 +5,7 @@ import gzip, importlib, json, os, sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
-w = importlib.import_module("megapath-nano_b200.workloads")
+w = importlib.import_module("workloads")
 from oracle import dbg_oracle
 
 wins = w.dbg_windows(14, seed=7001, max_reads=60) + w.dbg_windows(6, seed=7002, max_reads=40, repeat_frac=1.0) + [

@@ -18,7 +18,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT)
 from oracle import oracle  # noqa: E402
 
-w = importlib.import_module("megapath-nano_b200.workloads")
+w = importlib.import_module("workloads")
 
 
 def edge_regions():

@@ -5,7 +5,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-w = importlib.import_module("megapath-nano_b200.workloads")
+w = importlib.import_module("workloads")
 CAP = 192
 
 

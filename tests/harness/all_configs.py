@@ -7,7 +7,7 @@ import dataclasses, importlib, json, os, subprocess, sys, time
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
-w = importlib.import_module("megapath-nano_b200.workloads")
+w = importlib.import_module("workloads")
 B = importlib.import_module("megapath-nano_b200.batch")
 R = importlib.import_module("megapath-nano_b200.realigner")
 from oracle import oracle

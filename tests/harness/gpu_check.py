@@ -2,7 +2,7 @@
 import importlib, sys, time, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
-w = importlib.import_module("megapath-nano_b200.workloads")
+w = importlib.import_module("workloads")
 B = importlib.import_module("megapath-nano_b200.batch")
 from oracle import oracle
 

@@ -4,7 +4,7 @@ Per-region realign_reads latency and whole-set mpn_realign_regions throughput on
 import dataclasses, importlib, json, os, subprocess, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
-w = importlib.import_module("megapath-nano_b200.workloads")
+w = importlib.import_module("workloads")
 R = importlib.import_module("megapath-nano_b200.realigner")
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 200
 seed = int(sys.argv[2]) if len(sys.argv) > 2 else 13

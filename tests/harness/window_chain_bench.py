@@ -4,7 +4,7 @@ python tests/harness/window_chain_bench.py [windows] [max_reads] [oracle_sample]
 restatement oracle/dbg_oracle.py on a sample of the windows (the reference's own assembler needs Boost and cannot be built here)."""
 import importlib, json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
-w = importlib.import_module("megapath-nano_b200.workloads")
+w = importlib.import_module("workloads")
 D = importlib.import_module("megapath-nano_b200.debruijn")
 R = importlib.import_module("megapath-nano_b200.realigner")
 nwin = int(sys.argv[1]) if len(sys.argv) > 1 else 200

@@ -9,7 +9,7 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-w = importlib.import_module("megapath-nano_b200.workloads")
+w = importlib.import_module("workloads")
 
 
 def golden_regions():

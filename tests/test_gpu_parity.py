@@ -11,7 +11,7 @@ from golden_util import golden_cases, diff, CAP
 
 pytestmark = pytest.mark.gpu
 
-w = importlib.import_module("megapath-nano_b200.workloads")
+w = importlib.import_module("workloads")
 B = importlib.import_module("megapath-nano_b200.batch")
 pyssw = importlib.import_module("megapath-nano_b200.pyssw")
 

@@ -9,7 +9,7 @@ from realign_util import golden_regions, run_reference, mismatches
 
 pytestmark = pytest.mark.gpu
 
-w = importlib.import_module("megapath-nano_b200.workloads")
+w = importlib.import_module("workloads")
 R = importlib.import_module("megapath-nano_b200.realigner")
 
 

@@ -12,7 +12,7 @@ pytestmark = pytest.mark.gpu
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PKG = os.path.join(ROOT, "megapath-nano_b200")
-w = importlib.import_module("megapath-nano_b200.workloads")
+w = importlib.import_module("workloads")
 
 
 def expected(ref, q, res, cig):

@@ -9,7 +9,7 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
-w = importlib.import_module("megapath-nano_b200.workloads")
+w = importlib.import_module("workloads")
 pyssw = importlib.import_module("megapath-nano_b200.pyssw")
 
 

@@ -8,7 +8,7 @@ import pytest
 from oracle import oracle
 from golden_util import golden_cases, diff, CAP
 
-w = importlib.import_module("megapath-nano_b200.workloads")
+w = importlib.import_module("workloads")
 
 
 def run(b, impl, threads=4):

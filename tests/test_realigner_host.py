@@ -13,7 +13,7 @@ import pytest
 from oracle import oracle
 from realign_util import golden_regions, run_reference, mismatches
 
-w = importlib.import_module("megapath-nano_b200.workloads")
+w = importlib.import_module("workloads")
 R = importlib.import_module("megapath-nano_b200.realigner")
 
 

@@ -18,7 +18,7 @@ def _worker(rank, world, port, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    w = importlib.import_module("megapath-nano_b200.workloads")
+    w = importlib.import_module("workloads")
     full = w.config2(2000, seed=5)
     mine = full.shard(rank, world)
     t = torch.tensor([10.0 + rank, 20.0 - rank], dtype=torch.float64)
@@ -49,7 +49,7 @@ def test_world_size_2_gloo_sharding_and_reduction():
 
 
 def test_generators_are_deterministic_and_shaped():
-    w = importlib.import_module("megapath-nano_b200.workloads")
+    w = importlib.import_module("workloads")
     a, b = w.config2(500, seed=9), w.config2(500, seed=9)
     assert np.array_equal(a.reads, b.reads) and np.array_equal(a.refs, b.refs)
     assert a.read_len.min() >= 150 and a.read_len.max() <= 300 and (a.ref_len == 1000).all() and a.flag == 1

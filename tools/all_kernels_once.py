@@ -3,7 +3,7 @@ one realigner region): a quick target for a debugger or a profiler capture.  pyt
 import importlib, os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-w = importlib.import_module("megapath-nano_b200.workloads")
+w = importlib.import_module("workloads")
 B = importlib.import_module("megapath-nano_b200.batch")
 R = importlib.import_module("megapath-nano_b200.realigner")
 eng = B.Engine(0)

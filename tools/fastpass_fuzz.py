@@ -3,7 +3,7 @@ adversarial + config-3 regions.  python tools/fastpass_fuzz.py [seeds] [lib]  ->
 With lib = oracle/_hosttest/realigner_hosttest.so the scalar stand-in of the kernel's formulation is checked instead (no GPU needed)."""
 import importlib, json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-w = importlib.import_module("megapath-nano_b200.workloads")
+w = importlib.import_module("workloads")
 R = importlib.import_module("megapath-nano_b200.realigner")
 nseeds = int(sys.argv[1]) if len(sys.argv) > 1 else 40
 lib = sys.argv[2] if len(sys.argv) > 2 else None

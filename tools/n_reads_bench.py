@@ -4,7 +4,7 @@ whose N column varies (mat[4][4] changed: such reads are flagged and redone by t
 import importlib, sys
 import os; sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
-w = importlib.import_module("megapath-nano_b200.workloads")
+w = importlib.import_module("workloads")
 B = importlib.import_module("megapath-nano_b200.batch")
 pairs = int(sys.argv[1]) if len(sys.argv) > 1 else 400000
 eng = B.Engine(0); eng.set_profile(True)

@@ -2,7 +2,7 @@
 (CUDA events inside the engine) and forward-pass GCUPS.  MPN_SSW_LIB selects a kernel-variant build for A/B runs."""
 import importlib, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-w = importlib.import_module("megapath-nano_b200.workloads")
+w = importlib.import_module("workloads")
 B = importlib.import_module("megapath-nano_b200.batch")
 pairs = int(sys.argv[1]) if len(sys.argv) > 1 else 300000
 cfg = int(sys.argv[2]) if len(sys.argv) > 2 else 2

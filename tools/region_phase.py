@@ -3,7 +3,7 @@ pairs plus reads x haplotypes, flag 0x0f, as realign_region.cpp submits them.  p
 import importlib, sys, os
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-w = importlib.import_module("megapath-nano_b200.workloads")
+w = importlib.import_module("workloads")
 B = importlib.import_module("megapath-nano_b200.batch")
 rg = w.config3(3, seed=int(sys.argv[1]) if len(sys.argv) > 1 else 13)[2]
 enc = lambda s: np.frombuffer(s.encode(), dtype=np.uint8)

@@ -1,6 +1,6 @@
 import importlib, sys, time
 sys.path.insert(0, "/root/repo")
-w = importlib.import_module("megapath-nano_b200.workloads")
+w = importlib.import_module("workloads")
 R = importlib.import_module("megapath-nano_b200.realigner")
 regions = w.config3(60, seed=13)
 R.realign_reads(regions[0])

@@ -1,4 +1,4 @@
-"""Seeded synthetic inputs for the five BASELINE.json configs.
+"""Seeded synthetic inputs for the five BASELINE.json configs.  Test / bench infrastructure: not part of the product package.
 
 Every generator returns a `PairBatch`: CSR-packed int8 code arrays (A0 C1 G2 T3 N4, as ssw_cpp.cpp:8-21 /
 pyssw.py:86-98 translate them) plus per-pair maskLen and the scoring that the reference callers use
@@ -240,16 +240,8 @@ def fuzz_pairs(npairs, seed, max_read=700, max_ref=500, alphabet=4, flag=1, rand
 # haplotypes (flank + consensus + flank, space separated) and the reads overlapping the window with their current
 # position and CIGAR.  The de Bruijn assembly that proposes haplotypes is out of scope, so haplotypes are the window with
 # 1-3 planted SNVs / small indels; reads are sampled from a few "true" haplotypes with 0.5 % error.
-@dataclass
-class RegionWorkload:
-    reference: str
-    haplotypes: list
-    reads: list
-    positions: list
-    cigars: list
-    ref_start: int
-    ref_prefix: int
-    ref_suffix: int
+import importlib as _importlib
+RegionWorkload = _importlib.import_module("megapath-nano_b200.realigner").Region      # the product's input record of realign_reads / realign_regions
 
 
 def _rand_dna(rng, n):
