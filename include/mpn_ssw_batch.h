@@ -67,6 +67,8 @@ int mpn_engine_set_stream(mpn_engine* e, void* cuda_stream);
  * {forward score kernels, second-best/mode epilogue, reverse score kernels, traceback+CIGAR} of the last mpn_batch_run */
 int mpn_engine_set_profile(mpn_engine* e, int on);
 int mpn_engine_phase_ms(mpn_engine* e, float* ms4);
+/* the same averaged over the profiled runs since profiling was switched on (at most the last 16 runs); *nruns receives the count */
+int mpn_engine_phase_ms_mean(mpn_engine* e, float* ms4, int* nruns);
 /* counters since creation: kernel launches, pairs, forward cells, pairs re-run in the 32-bit kernel */
 int mpn_engine_stats(const mpn_engine* e, int64_t* launches, int64_t* pairs, int64_t* cells, int64_t* wide_pairs);
 

@@ -35,6 +35,7 @@ def lib():
         L.mpn_engine_stats.argtypes = [ct.c_void_p] + [ct.POINTER(ct.c_int64)] * 4
         L.mpn_engine_set_profile.argtypes = [ct.c_void_p, ct.c_int]
         L.mpn_engine_phase_ms.argtypes = [ct.c_void_p, ct.POINTER(ct.c_float)]
+        L.mpn_engine_phase_ms_mean.argtypes = [ct.c_void_p, ct.POINTER(ct.c_float), ct.POINTER(ct.c_int)]
         L.mpn_batch_upload.restype = ct.c_void_p
         L.mpn_batch_upload.argtypes = [ct.c_void_p, ct.POINTER(MpnParams), ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_int64]
         L.mpn_batch_run.argtypes = [ct.c_void_p]
@@ -99,6 +100,14 @@ class Engine:
         if self.L.mpn_engine_phase_ms(self.h, v):
             return None
         return dict(forward=v[0], finish=v[1], reverse=v[2], trace=v[3])
+
+    def phase_ms_mean(self):
+        """the same averaged over the runs since set_profile(True) (at most the last 16): (dict, number of runs)"""
+        v = (ct.c_float * 4)()
+        n = ct.c_int(0)
+        if self.L.mpn_engine_phase_ms_mean(self.h, v, ct.byref(n)):
+            return None, 0
+        return dict(forward=v[0], finish=v[1], reverse=v[2], trace=v[3]), n.value
 
     def stats(self):
         v = [ct.c_int64(0) for _ in range(4)]

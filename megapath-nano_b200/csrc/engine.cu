@@ -147,8 +147,11 @@ struct mpn_engine {
     static constexpr int NAUX = 3;                   // side streams: the bins of one score pass run concurrently, so the tail of one launch overlaps the next
     cudaStream_t aux[NAUX] = {nullptr, nullptr, nullptr};
     cudaEvent_t ev_fork = nullptr, ev_join[NAUX] = {nullptr, nullptr, nullptr};
-    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    static constexpr int NEVSET = 16;                // phase events of the last NEVSET runs (mpn_engine_phase_ms_mean averages them)
+    cudaEvent_t evs[NEVSET][5] = {};
+    cudaEvent_t* ev = evs[0];                        // the set of the run being enqueued
     int ev_valid = 0;
+    int64_t ev_runs = 0;                             // completed profiled runs since profiling was switched on
     DevPool pool;
     struct Slot { cudaStream_t st = nullptr; PinBuf pin_tasks, pin_fwd, pin_fin, pin_misc; };
     static constexpr int NSLOT = 5;                  // slot 0 serves the phased API on the engine stream; 1..4 are the pipeline of mpn_align_batch
@@ -236,7 +239,7 @@ extern "C" void mpn_engine_destroy(mpn_engine* e)
         sl.pin_tasks.release(); sl.pin_fwd.release(); sl.pin_fin.release(); sl.pin_misc.release();
         if (k > 0 && sl.st) cudaStreamDestroy(sl.st);
     }
-    if (e->ev[0]) for (int i = 0; i < 5; ++i) cudaEventDestroy(e->ev[i]);
+    if (e->evs[0][0]) for (int k = 0; k < mpn_engine::NEVSET; ++k) for (int i = 0; i < 5; ++i) cudaEventDestroy(e->evs[k][i]);
     delete e;
 }
 
@@ -251,9 +254,9 @@ extern "C" int mpn_engine_set_profile(mpn_engine* e, int on)
 {
     if (!e) return MPN_E_ARG;
     CK(cudaSetDevice(e->device));
-    if (on && !e->ev[0]) for (int i = 0; i < 5; ++i) CK(cudaEventCreate(&e->ev[i]));
+    if (on && !e->evs[0][0]) for (int k = 0; k < mpn_engine::NEVSET; ++k) for (int i = 0; i < 5; ++i) CK(cudaEventCreate(&e->evs[k][i]));
     e->profile = on != 0;
-    e->ev_valid = 0;
+    e->ev_valid = 0; e->ev_runs = 0; e->ev = e->evs[0];
     return 0;
 }
 
@@ -263,6 +266,22 @@ extern "C" int mpn_engine_phase_ms(mpn_engine* e, float* ms4)
     if (!e || !ms4 || !e->profile || e->ev_valid < 5) return MPN_E_ARG;
     CK(cudaEventSynchronize(e->ev[4]));
     for (int i = 0; i < 4; ++i) CK(cudaEventElapsedTime(&ms4[i], e->ev[i], e->ev[i + 1]));
+    return 0;
+}
+
+/* the same, averaged over the profiled runs since mpn_engine_set_profile(e, 1) (at most the last 16); *nruns = how many */
+extern "C" int mpn_engine_phase_ms_mean(mpn_engine* e, float* ms4, int* nruns)
+{
+    if (!e || !ms4 || !e->profile || e->ev_runs < 1) return MPN_E_ARG;
+    const int n = (int)std::min<int64_t>(e->ev_runs, mpn_engine::NEVSET);
+    double acc[4] = {0, 0, 0, 0};
+    for (int k = 0; k < n; ++k) {
+        cudaEvent_t* set = e->evs[(e->ev_runs - 1 - k) % mpn_engine::NEVSET];
+        CK(cudaEventSynchronize(set[4]));
+        for (int i = 0; i < 4; ++i) { float ms = 0; CK(cudaEventElapsedTime(&ms, set[i], set[i + 1])); acc[i] += ms; }
+    }
+    for (int i = 0; i < 4; ++i) ms4[i] = (float)(acc[i] / n);
+    if (nruns) *nruns = n;
     return 0;
 }
 
@@ -597,7 +616,7 @@ extern "C" int mpn_batch_run(mpn_batch* b)
     }
     PairArrays pa{b->mask.as<int32_t>()};
 
-    if (e->profile) { CK(cudaEventRecord(e->ev[0], st)); e->ev_valid = 1; }
+    if (e->profile) { e->ev = e->evs[e->ev_runs % mpn_engine::NEVSET]; CK(cudaEventRecord(e->ev[0], st)); e->ev_valid = 1; }
     // forward score pass -> ends + column records
     launch_strips(b, b->tasks_fwd.as<SwTask>(), true, b->ends_fwd.as<SwEnds>(), 128);
     // pairs the packed kernel refused (read code >= 4): its N variants take reads with N when the matrix's N column is constant,
@@ -672,7 +691,7 @@ extern "C" int mpn_batch_run(mpn_batch* b)
     }
     if (e->profile) {
         if (!any_rev) CK(cudaEventRecord(e->ev[3], st));
-        CK(cudaEventRecord(e->ev[4], st)); e->ev_valid = 5;
+        CK(cudaEventRecord(e->ev[4], st)); e->ev_valid = 5; e->ev_runs++;
     }
     b->ran = true;
     e->pairs += n; e->cells += b->total_cells;

@@ -57,3 +57,30 @@ def test_generators_are_deterministic_and_shaped():
     assert (c1.read_len == 250).all() and (c1.ref_len == 500).all() and (c1.masklen == 125).all() and c1.cells == 100 * 250 * 500
     f = w.fuzz_pairs(50, 3)
     assert f.gapO > f.gapE and f.reads.max() <= 4 and f.masklen.min() >= 15
+
+
+def test_mixed_stream_plan_is_deterministic_balanced_and_chunking_independent():
+    """BASELINE configs[4] as a stream (workloads.MixedStream): every rank derives the same plan, the plan covers every chunk once, the
+    ranks' cost shares are balanced, and a pair's bases depend only on (seed, global index) -- not on how the stream was chunked."""
+    import importlib
+    import numpy as np
+    w = importlib.import_module("workloads")
+    a = w.MixedStream(60_000, seed=15, world=4)
+    b = w.MixedStream(60_000, seed=15, world=4)
+    assert (a.bounds == b.bounds).all() and a.plan(4) == b.plan(4)
+    plan = a.plan(4)
+    assert sorted(k for r in plan for k in r) == list(range(a.nchunks))
+    share = np.array([a.chunk_cost[r].sum() for r in plan]) / a.chunk_cost.sum()
+    assert share.max() - share.min() < 0.06, share
+    assert int(a.chunk_cells.sum()) == a.total_cells and (np.diff(a.rl) >= 0).all()          # length-sorted
+    c = w.MixedStream(60_000, seed=15, chunk_cost=3.0e10)                                     # other chunking, same stream
+    k = a.nchunks // 2
+    lo, hi = int(a.bounds[k]), int(a.bounds[k + 1])
+    ba = a.chunk(k, threads=2)
+    kc = int(np.searchsorted(c.bounds, lo, side="right")) - 1
+    bc = c.chunk(kc, threads=3)
+    off = lo - int(c.bounds[kc])
+    n = min(hi - lo, bc.npairs - off, 50)
+    for i in range(n):
+        assert (ba.reads[ba.read_off[i]:ba.read_off[i + 1]] == bc.reads[bc.read_off[off + i]:bc.read_off[off + i + 1]]).all()
+        assert (ba.refs[ba.ref_off[i]:ba.ref_off[i + 1]] == bc.refs[bc.ref_off[off + i]:bc.ref_off[off + i + 1]]).all()

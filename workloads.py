@@ -174,6 +174,95 @@ def config5(npairs=10_000_000, seed=15, lo=100, hi=20_000, flag=0):
     return PairBatch(np.concatenate(reads_l), ro, np.concatenate(refs_l), fo, ml, flag=flag, name=f"config5: mixed {lo}bp-{hi}bp x{len(rl2)}")
 
 
+_seqgen = None
+
+
+def seqgen():
+    """tools/libseqgen.so (tools/seqgen.c): pairs as a pure function of (seed, global pair index), generated at memory speed on host threads"""
+    global _seqgen
+    if _seqgen is None:
+        import ctypes as ct, os, subprocess
+        here = os.path.dirname(os.path.abspath(__file__))
+        so, src = os.path.join(here, "tools", "libseqgen.so"), os.path.join(here, "tools", "seqgen.c")
+        if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+            subprocess.run(["gcc", "-O2", "-shared", "-fPIC", "-pthread", "-o", so, src], check=True)
+        L = ct.CDLL(so)
+        L.seqgen_pairs.argtypes = [ct.c_uint64, ct.c_int64, ct.c_int64, ct.c_void_p, ct.c_void_p, ct.c_double, ct.c_void_p, ct.c_void_p, ct.c_int]
+        L.seqgen_pairs.restype = None
+        _seqgen = L
+    return _seqgen
+
+
+def gen_pairs_fast(rl, fl, seed, first_index=0, err=0.05, threads=4, flag=0, name="", reads_out=None, refs_out=None, **kw):
+    """PairBatch for the given per-pair lengths through tools/seqgen.c.  reads_out / refs_out: optional preallocated int8 buffers
+    (e.g. views of pinned torch tensors) that are filled in place."""
+    rl = np.ascontiguousarray(rl, dtype=np.int64); fl = np.ascontiguousarray(fl, dtype=np.int64)
+    n = len(rl)
+    ro = np.zeros(n + 1, dtype=np.int64); np.cumsum(rl, out=ro[1:])
+    fo = np.zeros(n + 1, dtype=np.int64); np.cumsum(fl, out=fo[1:])
+    reads = np.empty(int(ro[-1]), dtype=np.int8) if reads_out is None else reads_out[:int(ro[-1])]
+    refs = np.empty(int(fo[-1]), dtype=np.int8) if refs_out is None else refs_out[:int(fo[-1])]
+    seqgen().seqgen_pairs(int(seed), int(first_index), n, ro.ctypes.data, fo.ctypes.data, float(err), reads.ctypes.data, refs.ctypes.data, int(threads))
+    ml = np.maximum(rl // 2, 15).astype(np.int32)
+    return PairBatch(reads, ro, refs, fo, ml, flag=flag, name=name, **kw)
+
+
+class MixedStream:
+    """BASELINE configs[4] -- 10 M mixed-length pairs, read length log-uniform on [lo, hi], target = 1.2 x read, 5 % errors -- as a stream
+    of LENGTH-SORTED CHUNKS that never sits in RAM at once (~80 GB of bases at full size).  The pairs are sorted by read length once
+    (the lengths alone are 80 MB); chunk k is a contiguous run of that order holding about `chunk_cost` cost units (forward cells x the
+    relative cost of the score kernel the pairs take) and at most `max_pairs` pairs; its bases are a pure function of (seed, global
+    index).  plan(world) deals the chunks to ranks, heaviest first, each to the least loaded rank (length-sorted
+    chunks dealt by cells, no collective)."""
+
+    def __init__(self, npairs=10_000_000, seed=15, lo=100, hi=20_000, flag=0, err=0.05, chunk_cost=None, max_pairs=400_000, match=4, world=1):
+        rng = np.random.default_rng(seed)
+        rl = np.exp(rng.uniform(np.log(lo), np.log(hi), size=npairs)).astype(np.int64)
+        rl.sort()
+        self.rl = rl
+        self.fl = np.maximum((rl * 1.2).astype(np.int64), rl + 8)
+        self.npairs, self.seed, self.flag, self.err = npairs, seed, flag, err
+        cells = self.rl * self.fl
+        # the engine's classifier (engine.cu pair_cost_per_cell): packed short-read kernel up to 1280 rows while no H can reach the int16 clamp
+        short = ((np.minimum(self.rl, self.fl) + 1) * match <= 32767) & (self.rl <= 1280)
+        cost = cells * np.where(short, 1.0, 1.55) + 4096.0
+        self.total_cells = int(cells.sum())
+        if chunk_cost is None:
+            # a chunk must fill a GPU (thousands of long pairs: the multi-strip kernel runs one warp per pair) -> 2.5e12 cost units (~0.7 s);
+            # smaller workloads still give every rank about a dozen chunks to balance on
+            chunk_cost = min(2.5e12, max(2.0e11, float(cost.sum()) / (12.0 * world)))
+        cum = np.cumsum(cost)
+        bounds = [0]
+        while bounds[-1] < npairs:
+            a = bounds[-1]
+            base = cum[a - 1] if a else 0.0
+            b = int(np.searchsorted(cum, base + chunk_cost, side="left")) + 1
+            bounds.append(min(npairs, max(a + 1, min(b, a + max_pairs))))
+        self.bounds = np.array(bounds, dtype=np.int64)
+        self.nchunks = len(bounds) - 1
+        self.chunk_cost = np.add.reduceat(cost, self.bounds[:-1])
+        self.chunk_cells = np.add.reduceat(cells, self.bounds[:-1])
+
+    def plan(self, world):
+        """chunk ids per rank: heaviest chunk first, each to the least loaded rank (deterministic: every rank derives the same plan)"""
+        order = np.argsort(-self.chunk_cost, kind="stable")
+        load = np.zeros(world)
+        out = [[] for _ in range(world)]
+        for k in order:
+            r = int(np.argmin(load))
+            out[r].append(int(k)); load[r] += self.chunk_cost[k]
+        return out
+
+    def chunk(self, k, threads=4, reads_out=None, refs_out=None):
+        a, b = int(self.bounds[k]), int(self.bounds[k + 1])
+        return gen_pairs_fast(self.rl[a:b], self.fl[a:b], self.seed, first_index=a, err=self.err, threads=threads, flag=self.flag,
+                              name=f"config5 chunk {k}: pairs {a}..{b}", reads_out=reads_out, refs_out=refs_out)
+
+    def chunk_bytes(self, k):
+        a, b = int(self.bounds[k]), int(self.bounds[k + 1])
+        return int(self.rl[a:b].sum()), int(self.fl[a:b].sum())
+
+
 def fuzz_pairs(npairs, seed, max_read=700, max_ref=500, alphabet=4, flag=1, random_matrix=True, with_n=True):
     """The adversarial distribution of SURVEY.md section 8c: random 5x5 matrices, gapE 1..3, gapO > gapE, low-complexity
     alphabets (ties), reads derived from the target with jumps / random blocks / substitutions, occasional N, lengths from 1,
