@@ -10,6 +10,7 @@
 //     per-range region of the caller's arena, mpn_result::cigar_off is the absolute index as everywhere.
 // No CPU alignment code here either: a pool without a CUDA device is NULL.
 #include "engine_internal.h"
+#include "host_shared.h"
 #include <algorithm>
 #include <atomic>
 #include <chrono>
@@ -129,55 +130,65 @@ extern "C" int mpn_pool_last_shares(const mpn_pool* pl, double* ms, int64_t* pai
     return 0;
 }
 
-// cut [0, npairs) into ranges of about equal cost, in the caller's order; CIGAR regions proportional to the pairs and read bases of a range
+// cut [0, npairs) into ranges of about equal cost, in the caller's order; CIGAR regions proportional to the pairs and read bases of a range.
+// Costs are summed per block of PLAN_BLOCK pairs on host threads (a 1 M-pair batch is planned in about a millisecond); range boundaries fall
+// on block boundaries (4096 pairs, fewer in small batches).
 template <class Pairs>
 static int plan_ranges(const mpn_pool* pl, const mpn_params* p, const Pairs& all, int64_t npairs, int64_t cigar_cap, bool one_per_device, std::vector<RangeJob>& ranges)
 {
     const int ndev = (int)pl->eng.size();
     int maxpos = 0;
     for (int i = 0; i < p->n * p->n; ++i) maxpos = std::max<int>(maxpos, p->mat[i]);
-    std::vector<double> cost((size_t)npairs);
+    const int64_t PLAN_BLOCK = std::max<int64_t>(16, std::min<int64_t>(4096, npairs / (64 * (int64_t)ndev)));      // small batches: finer boundaries
+    const int64_t nblocks = (npairs + PLAN_BLOCK - 1) / PLAN_BLOCK;
+    std::vector<double> bcost((size_t)nblocks, 0.0);
+    std::vector<int64_t> bbases((size_t)nblocks, 0);
+    std::atomic<int> bad{0};
+    const int n = p->n;
+    parallel_for(nblocks, 8, [&](int64_t blk) {
+        const int64_t lo = blk * PLAN_BLOCK, hi = std::min(npairs, lo + PLAN_BLOCK);
+        double c = 0; int64_t bases = 0;
+        for (int64_t i = lo; i < hi; ++i) {
+            const int64_t rl = all.rl(i), fl = all.fl(i);
+            if (rl < 0 || fl < 0) { bad.store(1); continue; }
+            // a pair is never free: scheduling, copies and the record cost about as much as a few thousand cells
+            c += (double)rl * (double)fl * pair_cost_per_cell(n, maxpos, rl, fl) + 4096.0;
+            bases += rl;
+        }
+        bcost[(size_t)blk] = c; bbases[(size_t)blk] = bases;
+    }, 8);
+    if (bad.load()) return MPN_E_ARG;
     double total = 0;
-    for (int64_t i = 0; i < npairs; ++i) {
-        const int64_t rl = all.rl(i), fl = all.fl(i);
-        if (rl < 0 || fl < 0) return MPN_E_ARG;
-        // a pair is never free: scheduling, copies and the record cost about as much as a few thousand cells
-        cost[(size_t)i] = (double)rl * (double)fl * pair_cost_per_cell(p->n, maxpos, rl, fl) + 4096.0;
-        total += cost[(size_t)i];
-    }
+    for (double c : bcost) total += c;
     // ranges: enough of them that the queue balances the devices (about 12 per device), small enough for the engine's pipeline
     // (at most 192 k pairs)
     const int64_t max_pairs = 196608;
     int64_t want = one_per_device ? ndev : std::max<int64_t>((int64_t)ndev * 12, (npairs + max_pairs - 1) / max_pairs);
     // ... and a range must be worth a launch sequence: at least ~1.5e9 cost units (a fraction of a millisecond of one GPU)
     want = std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)(total / 1.5e9)));
-    want = std::min<int64_t>(want, npairs);
     if (ndev == 1 && !one_per_device) want = std::max<int64_t>(1, (npairs + max_pairs - 1) / max_pairs);
+    want = std::min<int64_t>(want, nblocks);
     const double per = total / (double)want;
-    std::vector<double> rcost;
-    int64_t first = 0; double acc = 0;
-    for (int64_t i = 0; i < npairs; ++i) {
-        acc += cost[(size_t)i];
-        const bool last = i + 1 == npairs;
-        if (last || (acc >= per && (int64_t)ranges.size() + 1 < want) || (!one_per_device && i + 1 - first >= max_pairs)) {
-            RangeJob r; r.first = first; r.count = i + 1 - first;
+    std::vector<double> rcost, rneed;
+    int64_t first_blk = 0; double acc = 0; int64_t bases = 0;
+    for (int64_t blk = 0; blk < nblocks; ++blk) {
+        acc += bcost[(size_t)blk]; bases += bbases[(size_t)blk];
+        const int64_t end_pair = std::min(npairs, (blk + 1) * PLAN_BLOCK), first_pair = first_blk * PLAN_BLOCK;
+        const bool last = blk + 1 == nblocks;
+        if (last || (acc >= per && (int64_t)ranges.size() + 1 < want) || (!one_per_device && end_pair + PLAN_BLOCK - first_pair > max_pairs)) {
+            RangeJob r; r.first = first_pair; r.count = end_pair - first_pair;
             ranges.push_back(r); rcost.push_back(acc);
-            first = i + 1; acc = 0;
+            rneed.push_back(24.0 * (double)r.count + (double)bases / 4.0 + 1024.0);
+            first_blk = blk + 1; acc = 0; bases = 0;
         }
     }
     // CIGAR regions
     if ((p->flag & 7) != 0 && cigar_cap > 0) {
-        std::vector<double> need(ranges.size());
         double need_total = 0;
-        for (size_t k = 0; k < ranges.size(); ++k) {
-            int64_t bases = 0;
-            for (int64_t i = ranges[k].first; i < ranges[k].first + ranges[k].count; ++i) bases += all.rl(i);
-            need[k] = 24.0 * (double)ranges[k].count + (double)bases / 4.0 + 1024.0;
-            need_total += need[k];
-        }
+        for (double v : rneed) need_total += v;
         int64_t at = 0;
         for (size_t k = 0; k < ranges.size(); ++k) {
-            const int64_t cap = (int64_t)((double)cigar_cap * (need[k] / need_total));
+            const int64_t cap = (int64_t)((double)cigar_cap * (rneed[k] / need_total));
             ranges[k].cig_base = at; ranges[k].cig_cap = cap; at += cap;
         }
     } else {
