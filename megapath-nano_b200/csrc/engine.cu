@@ -464,7 +464,7 @@ static mpn_batch* upload_impl(mpn_engine* e, int slot_id, const mpn_params* p, c
     const bool want_cigar = (p->flag & 7) != 0;
     if ((p->flag & 0xff) != 0) {
         pool.take(b->bandrec, sizeof(BandRec) * (size_t)(npairs + 1)); pool.take(b->flaglist, sizeof(int) * (size_t)(npairs + 1));
-        pool.take(b->bandq_items, sizeof(int2) * (size_t)ROWS_CLASSES * (size_t)(npairs + 1));     // one work queue per band-width class
+        pool.take(b->bandq_items, sizeof(BandItem) * (size_t)ROWS_CLASSES * (size_t)(npairs + 1));     // one work queue per band-width class
         pool.take(b->bandq_meta, 64 * sizeof(int));
     }
     if (want_cigar) {
@@ -657,7 +657,7 @@ extern "C" int mpn_batch_run(mpn_batch* b)
             // narrow bands: setup (begin positions, filters, one queue per band-width class), then one lane-persistent row kernel per
             // class in increasing order (a failed attempt re-queues the pair for the doubled band = a later class), then one-thread-per-pair traceback
             CK(cudaMemsetAsync(b->bandq_meta.p, 0, 64 * sizeof(int), st));
-            BandQueues bq{b->bandq_items.as<int2>(), b->bandq_meta.as<int>(), b->bandq_meta.as<int>() + 16, (int)n};
+            BandQueues bq{b->bandq_items.as<BandItem>(), b->bandq_meta.as<int>(), b->bandq_meta.as<int>() + 16, (int)n};
             sw_band_setup_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(b->tasks_fwd.as<SwTask>(), (int)n, b->fwdres.as<FwdResult>(), b->ends_rev.as<SwEnds>(), tp,
                 b->cig.as<uint32_t>(), b->cig_cap, b->counters.as<unsigned long long>() + 65, b->finalres.as<FinalResult>(), b->bandrec.as<BandRec>(), b->flaglist.as<int>(),
                 reinterpret_cast<int*>(b->counters.as<unsigned long long>() + 103), bq);

@@ -61,34 +61,6 @@ __device__ __forceinline__ uint32_t max3_relu(uint32_t h, uint32_t e, uint32_t f
     asm("max.s16x2.relu %0, %1, %2;" : "=r"(d) : "r"(t), "r"(h));
     return d;
 }
-// max(a, b) per half plus "a was already >= b" per half -> one VIMNMX.S16x2 with two predicate outputs.
-// (Own asm instead of __vibmax_s16x2: the CUDA 12.9 header omits the early-clobber on its output, so an in-place
-//  update `x = __vibmax_s16x2(x, ...)` compares the result with itself and always reports "no improvement".)
-__device__ __forceinline__ uint32_t max2_track(uint32_t a, uint32_t b, bool& a_ge_hi, bool& a_ge_lo)
-{
-    uint32_t val, ph, pl;
-    asm("{.reg .pred pu, pv;\n\t"
-        ".reg .s16 t0, t1, t2, t3;\n\t"
-        "max.s16x2 %0, %3, %4;\n\t"
-        "mov.b32 {t0, t1}, %0;\n\t"
-        "mov.b32 {t2, t3}, %3;\n\t"
-        "setp.eq.s16 pv, t0, t2;\n\t"
-        "setp.eq.s16 pu, t1, t3;\n\t"
-        "selp.b32 %1, 1, 0, pu;\n\t"
-        "selp.b32 %2, 1, 0, pv;}"
-        : "=&r"(val), "=&r"(ph), "=&r"(pl) : "r"(a), "r"(b));
-    a_ge_hi = ph != 0; a_ge_lo = pl != 0;
-    return val;
-}
-// c ? x : y as a PREDICATED MOVE (which ptxas may place on the fma pipe as IMAD.MOV) instead of a SEL (alu pipe, the busy one)
-__device__ __forceinline__ uint32_t mov_if(bool c, uint32_t x, uint32_t y)
-{
-    asm("{.reg .pred p;\n\t"
-        "setp.ne.u32 p, %1, 0;\n\t"
-        "@p mov.b32 %0, %2;}"
-        : "+r"(y) : "r"((uint32_t)c), "r"(x));
-    return y;
-}
 // f01 ? x : y for f01 in {0, 1} as two multiply-adds (fma pipe) instead of a SEL (alu pipe, the busy one): y + f01 * (x - y)
 __device__ __forceinline__ uint32_t blend_first(uint32_t y, uint32_t x, uint32_t f01)
 {

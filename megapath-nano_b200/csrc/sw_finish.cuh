@@ -89,7 +89,8 @@ sw_finish_kernel(const SwTask* __restrict__ fwd_tasks, int ntasks, const SwEnds*
                 const int cmj = (int)(w & 0xffffu), Bj = (int)(w >> 16);
                 if (j < e1) offer(kL, cmj, j);
                 else if (j >= e2) offer(kR, cmj, j);
-                if (P > 0 && Bj > 0) {
+                // pad candidates carry at most Bj: skipped unless Bj can still beat (or tie, at a smaller column) what this lane holds
+                if (P > 0 && Bj > 0 && ((e1 > 0 && (uint32_t)Bj >= (kL >> 16)) || (e2 < rf_len && (uint32_t)Bj >= (kR >> 16)))) {
                     if (j + 1 < e1) offer(kL, Bj, j + 1);
                     if (j + P + 1 < e1) offer(kL, Bj - fp.gapO, j + P + 1);
                     const int c2 = max(j + 1, e2);
@@ -105,6 +106,15 @@ sw_finish_kernel(const SwTask* __restrict__ fwd_tasks, int ntasks, const SwEnds*
                 for (int q = 0; q < 8; ++q) { const int j = c0 + 32 * q + lane; w8[q] = j < rf_len ? rec[j] : 0u; }
 #pragma unroll
                 for (int q = 0; q < 8; ++q) { const int j = c0 + 32 * q + lane; if (j < rf_len) column(j, w8[q]); }
+                // share the keys across the warp (the result is their maximum anyway): from the second block on, the test that skips the pad
+                // candidates is then nearly warp-uniform and whole warps jump over that code
+                if (c0 + 256 < rf_len) {
+#pragma unroll
+                    for (int off = 16; off >= 1; off >>= 1) {
+                        kL = max(kL, __shfl_xor_sync(0xffffffffu, kL, off));
+                        kR = max(kR, __shfl_xor_sync(0xffffffffu, kR, off));
+                    }
+                }
             }
 #pragma unroll
             for (int off = 16; off >= 1; off >>= 1) {

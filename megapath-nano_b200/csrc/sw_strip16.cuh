@@ -37,9 +37,8 @@ constexpr int STRIP_UNROLL = MPN_STRIP_UNROLL;
 #define MPN_STRIP_MINB 4
 #endif
 
-// Row of the winning cell (ssw.c:284-293: smallest row of the saved column holding the maximum).
-//   reverse passes: a stage that REACHES the terminating score stores its H column (a handful of times per pair, behind a warp-uniform branch);
-//   forward passes: checkpoint + replay.  Every STRIP_CK steps a thread stores its state (H, E of its rows, the boundary entering its
+// Cell of the maximum (ssw.c:260-277: first column holding it; ssw.c:284-293: smallest row of that column): checkpoint + replay, in
+// forward and reverse passes alike.  Every STRIP_CK steps a thread stores its state (H, E of its rows, the boundary entering its
 //   stages) into a scratch slot, and every step the 2 x 16 bits it receives from the thread above into the slot's log; when the block of
 //   steps ends and the thread's better stage improved in it, scratch and committed slot swap.  At the end of the pass the thread that owns
 //   the winning stage restores the committed slot and re-runs at most STRIP_CK steps on its own (the log replaces the shuffles) to get the
@@ -47,17 +46,16 @@ constexpr int STRIP_UNROLL = MPN_STRIP_UNROLL;
 __host__ __device__ constexpr int strip_ck(int G) { return G < 8 ? G : 8; }
 template <int KR, int G>
 __host__ __device__ constexpr size_t strip16_slot_bytes() { return ((size_t)2 * ((KR + 3) / 4) * 16 + 8 + (size_t)strip_ck(G) * 4) * STRIP_BLOCK; }
-// shared memory.  Forward: 2 checkpoint slots, the column-record staging [G][STRIP_BLOCK] words and, in the N variant only, the per-row
-// score fix-up selectors [KR][STRIP_BLOCK].  Reverse: H-column snapshots [2 halves][ceil(KR/4)][STRIP_BLOCK] uint4 instead of the slots.
+// shared memory: 2 checkpoint slots, the column-record staging [G][STRIP_BLOCK] words (forward passes only) and, in the N variant only, the
+// per-row score fix-up selectors [KR][STRIP_BLOCK]
 template <int KR, int G, bool NM = false, bool REV = false>
 __host__ __device__ constexpr size_t strip16_smem_bytes()
 {
-    return (REV ? (size_t)2 * ((KR + 3) / 4) * STRIP_BLOCK * sizeof(uint4) : 2 * strip16_slot_bytes<KR, G>()) + (size_t)(G + (NM ? KR : 0)) * STRIP_BLOCK * sizeof(uint32_t);
+    return 2 * strip16_slot_bytes<KR, G>() + (size_t)((REV ? 0 : G) + (NM ? KR : 0)) * STRIP_BLOCK * sizeof(uint32_t);
 }
 
-// REV = false: forward passes (column records written, no early end).  REV = true: reverse passes (ssw.c:820-832): no column records, the
-// pass ends once the terminating score has been seen, and only a stage that REACHES that score can be the winner, so the H-column
-// snapshots sit behind a warp-uniform branch that is taken a handful of times per pair instead of being issued (predicated off) every step.
+// REV = false: forward passes (column records written, no early end).  REV = true: reverse passes (ssw.c:820-832): no column records, no
+// column-maximum chain between the stages, and the pass ends once every stage is past the first column that reached the terminating score.
 //
 // NM = false: the kernel every pair goes through.  A read that contains N (code 4) cannot be scored by the one-PRMT lookup (the 4-byte
 // matrix rows have no slot for a fifth read code): the pair is flagged and its task index appended to `relist` (relist[0] = count).
@@ -65,24 +63,24 @@ __host__ __device__ constexpr size_t strip16_smem_bytes()
 // ssw_cpp.cpp:23-48, pyssw.py:61-79) every row gets a second PRMT that swaps its half of the looked-up score for c where the read has
 // an N (selector in shared memory, identity elsewhere).  This variant walks `relist` instead of a task range (`tasks` is then the whole
 // task array and `aux` the largest read length a smaller N variant already took); pairs it cannot take either (codes above 4) stay
-// flagged for the int32 kernel.  Keeping the N code out of the main instantiation keeps its inner loop at the 146 instructions per step
-// it had before (the switchable version cost 3 % on reads without N).
+// flagged for the int32 kernel.  Keeping the N code out of the main instantiation keeps its inner loop free of the second PRMT
+// (a switchable version cost 3 % on reads without N).
 template <int KR, int G, bool REV, bool NM = false>
 __global__ void __launch_bounds__(STRIP_BLOCK, MPN_STRIP_MINB)
 sw_strip16_kernel(const SwTask* __restrict__ tasks, int ntasks, int* __restrict__ counter, const int8_t* __restrict__ seq,
                   const Score16 sc, uint32_t* __restrict__ colrec, SwEnds* __restrict__ out, int* __restrict__ relist, int aux)
 {
     static_assert(KR >= 2, "KR too small");
-    constexpr int KRQ = (KR + 3) / 4;             // snapshot quads per half
+    constexpr int KRQ = (KR + 3) / 4;             // 16-byte words per checkpointed array
     static_assert(G == 2 || G == 4 || G == 8 || G == 16 || G == 32, "G must divide 32");
     constexpr int CAP = 2 * G * KR;               // rows covered by one strip
     constexpr int CK = strip_ck(G);               // forward: steps between checkpoints
     constexpr uint32_t SLOT = (uint32_t)strip16_slot_bytes<KR, G>();
     constexpr uint32_t SLOT_FH = 2 * KRQ * 16 * STRIP_BLOCK, SLOT_LOG = SLOT_FH + 8 * STRIP_BLOCK;     // byte offsets inside a slot
-    extern __shared__ uint4 snap[];               // reverse: [2 halves][KRQ][STRIP_BLOCK] H column of a stage when it reached the terminating score; forward: 2 slots
-    unsigned char* const smem0 = reinterpret_cast<unsigned char*>(snap);
-    uint32_t* const crow = reinterpret_cast<uint32_t*>(smem0 + (REV ? (size_t)2 * KRQ * STRIP_BLOCK * sizeof(uint4) : (size_t)2 * SLOT));   // [G][STRIP_BLOCK]: column records of the last G steps
-    uint32_t* const nfix = crow + G * STRIP_BLOCK;                                        // NM only: [KR][STRIP_BLOCK] fix-up selectors
+    extern __shared__ uint4 slots[];              // 2 checkpoint slots
+    unsigned char* const smem0 = reinterpret_cast<unsigned char*>(slots);
+    uint32_t* const crow = reinterpret_cast<uint32_t*>(smem0 + (size_t)2 * SLOT);         // forward only: [G][STRIP_BLOCK] column records of the last G steps
+    uint32_t* const nfix = crow + (REV ? 0 : G) * STRIP_BLOCK;                            // NM only: [KR][STRIP_BLOCK] fix-up selectors
 
     // the 8 matrix rows are looked up by a run-time target code: shared memory (one LDS) instead of the by-value parameter struct
     // (which ptxas can only index with a chain of predicated constant loads)
@@ -148,68 +146,25 @@ sw_strip16_kernel(const SwTask* __restrict__ tasks, int ntasks, int* __restrict_
     for (;;) {
         // ------------------------------------------------------------------ task boundary (every G steps) -------------
         if (REV) {   // early end of a reverse pass (ssw.c:281 / :483): once some stage has seen the terminating score in column c, every
-            // stage has passed column c after at most 2G-1 further steps; the usual first-column / first-row selection then applies.
+            // stage has passed column c after at most 2G-1 further steps.  A stage knows the BLOCK of steps in which it reached the score
+            // (cvlo / cvhi = first step of that block), so the bound below is up to STRIP_CK - 1 steps late -- harmless, the smallest
+            // (column, stage) wins whatever else is computed.
             const uint32_t x = best ^ stop2;
             const bool hit_lo = stop2 != 0u && (x & 0xffffu) == 0u, hit_hi = stop2 != 0u && (x >> 16) == 0u;
             const unsigned hits = __ballot_sync(0xffffffffu, hit_lo || hit_hi) & gmask;
             if (hits != 0u) {
-                // the terminating column is the smallest column in which a stage reached the score; every stage is past it at step col + 2G - 1
                 int col = 0x3fffffff;
-                if (hit_lo) col = (int)cvlo - 2 * t;
-                if (hit_hi) col = min(col, (int)cvhi - 2 * t - 1);
+                if (hit_lo) col = (int)cvlo + CK - 1 - 2 * t;
+                if (hit_hi) col = min(col, (int)cvhi + CK - 1 - 2 * t - 1);
 #pragma unroll
                 for (int off = G / 2; off >= 1; off >>= 1) col = min(col, __shfl_xor_sync(gmask, col, off));
                 nsteps = min(nsteps, col + 2 * G);
             }
         }
         if (active && s >= nsteps) {
-            if (nsteps > 0 && REV) {
-                // ---- finalize (reverse): reduce (score, first column, stage) over the 2G stages of the group
-                int sc_lo = (int)(int16_t)(best & 0xffffu), sc_hi = (int)(int16_t)(best >> 16);
-                int col_lo = (int)cvlo - 2 * t, col_hi = (int)cvhi - 2 * t - 1;
-                if (sc_lo <= 0) col_lo = 0;
-                if (sc_hi <= 0) col_hi = 0;
-                unsigned long long k_lo = ((unsigned long long)(unsigned)sc_lo << 40) | ((unsigned long long)(0xffffffu - (unsigned)col_lo) << 8) | (unsigned)(255 - 2 * t);
-                unsigned long long k_hi = ((unsigned long long)(unsigned)sc_hi << 40) | ((unsigned long long)(0xffffffu - (unsigned)col_hi) << 8) | (unsigned)(254 - 2 * t);
-                unsigned long long key = k_lo > k_hi ? k_lo : k_hi;
-#pragma unroll
-                for (int off = G / 2; off >= 1; off >>= 1) {
-                    unsigned long long o = __shfl_xor_sync(gmask, key, off);
-                    key = o > key ? o : key;
-                }
-                const int wscore = (int)(key >> 40);
-                const int wcol = (int)(0xffffffu - (unsigned)((key >> 8) & 0xffffffu));
-                const int wstage = 255 - (int)(key & 0xffu);
-                const unsigned anywide = __ballot_sync(gmask, wide != 0);
-                if (t == (wstage >> 1)) {
-                    int row = -999;
-                    if (wscore > 0) {
-                        const int half = wstage & 1;
-                        const uint4* sp = snap + (size_t)half * KRQ * STRIP_BLOCK + tid;
-                        for (int k = KRQ - 1; k >= 0; --k) {
-                            uint4 v = sp[(size_t)k * STRIP_BLOCK];
-                            uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                            for (int q = 3; q >= 0; --q) {
-                                int hv = half ? (int)(int16_t)(w[q] >> 16) : (int)(int16_t)(w[q] & 0xffffu);
-                                if (4 * k + q < KR && hv == wscore) row = wstage * KR + 4 * k + q - dead;
-                            }
-                        }
-                    }
-                    SwEnds e;
-                    e.score = wscore;
-                    e.col = wscore > 0 ? wcol : -1;
-                    e.row = wscore > 0 ? row : 0;
-                    e.flags = anywide ? SW_FLAG_NEEDS_WIDE : 0;
-                    // a reverse pass that did not reach its terminating score has no snapshot to read the row from (cannot happen for a
-                    // symmetric recurrence; kept as a guard): redo the pair in the 32-bit kernel
-                    if (stop2 != 0u && (uint32_t)wscore != (stop2 & 0xffffu)) e.flags = SW_FLAG_NEEDS_WIDE;
-                    out[tout] = e;
-                }
-            }
-            if (nsteps > 0 && !REV) {
-                // ---- finalize (forward).  `best` of a stage is the running maximum over its columns of the column maximum over the stages
-                //      up to and including it, so the stages holding the global maximum S are a suffix.  Every thread holding S replays its
+            if (nsteps > 0) {
+                // ---- finalize.  Forward: `best` of a stage is the running maximum over its columns of the column maximum over the stages up
+                //      to and including it (reverse: over its own rows only).  Every thread holding the global maximum S replays its
                 //      committed block (the log stands in for the thread above) and looks for the first step at which one of its OWN cells
                 //      equals S; the smallest (column, stage) over the group is the cell of ssw.c:260-277, and the smallest row of that
                 //      stage's column holding S the row of ssw.c:284-293.
@@ -272,6 +227,8 @@ sw_strip16_kernel(const SwTask* __restrict__ tasks, int ntasks, int* __restrict_
                     e.row = S > 0 ? row : 0;
                     e.flags = anywide ? SW_FLAG_NEEDS_WIDE : 0;
                     if (S > 0 && wkey == NOKEY) e.flags = SW_FLAG_NEEDS_WIDE;      // guard: no cell found in the committed blocks -> redo the pair in the 32-bit kernel
+                    // a reverse pass that did not reach its terminating score (cannot happen for a symmetric recurrence; kept as a guard): same
+                    if (REV && stop2 != 0u && (uint32_t)S != (stop2 & 0xffffu)) e.flags = SW_FLAG_NEEDS_WIDE;
                     out[tout] = e;
                 }
             }
@@ -393,25 +350,7 @@ sw_strip16_kernel(const SwTask* __restrict__ tasks, int ntasks, int* __restrict_
             tchunk = __shfl_down_sync(0xffffffffu, tchunk, 1, G);
             uint32_t F, m;
             dp_column(a, b, F, m, REV ? 0u : cmin);
-            if (REV) {
-                // ---- per-stage best tracking: strict improvement keeps the first column (ssw.c:269 / :474)
-                bool ge_hi, ge_lo;
-                best = max2_track(best, m, ge_hi, ge_lo);
-                cvlo = mov_if(!ge_lo, (uint32_t)s, cvlo);
-                cvhi = mov_if(!ge_hi, (uint32_t)s, cvhi);
-                const uint32_t x = best ^ stop2;
-                const bool win_lo = !ge_lo && (x & 0xffffu) == 0u, win_hi = !ge_hi && (x >> 16) == 0u;
-                if (__any_sync(0xffffffffu, win_lo || win_hi)) {
-                    if (win_lo) {
-#pragma unroll
-                        for (int k = 0; k < KRQ; ++k) snap[(size_t)k * STRIP_BLOCK + tid] = make_uint4(H[4 * k], H[min(4 * k + 1, KR - 1)], H[min(4 * k + 2, KR - 1)], H[min(4 * k + 3, KR - 1)]);
-                    }
-                    if (win_hi) {
-#pragma unroll
-                        for (int k = 0; k < KRQ; ++k) snap[(size_t)(KRQ + k) * STRIP_BLOCK + tid] = make_uint4(H[4 * k], H[min(4 * k + 1, KR - 1)], H[min(4 * k + 2, KR - 1)], H[min(4 * k + 3, KR - 1)]);
-                    }
-                }
-            }
+            if (REV) best = max2(best, m);      // own rows only; positions come from the replay
             uint32_t cmout = 0;
             if (!REV) {
                 // forward: m already holds the column maximum over the stages up to this one (dp_column starts from cmin); the best of a
@@ -426,8 +365,8 @@ sw_strip16_kernel(const SwTask* __restrict__ tasks, int ntasks, int* __restrict_
             //      only the high halves (the thread's second stage) leave the thread: F and the diagonal H travel in one word
             const uint32_t rX = __shfl_up_sync(0xffffffffu, prmt(F, Hdtop, 0x7632u), 1, G);
             const uint32_t rA = __shfl_up_sync(0xffffffffu, b, 1, G);
-            if (!REV)   // log what came from the thread above: the replay of this block runs without shuffles
-                reinterpret_cast<uint32_t*>(smem0 + ck_off + SLOT_LOG)[(u % CK) * STRIP_BLOCK + tid] = rX;
+            // log what came from the thread above: the replay of this block runs without shuffles
+            reinterpret_cast<uint32_t*>(smem0 + ck_off + SLOT_LOG)[(u % CK) * STRIP_BLOCK + tid] = rX;
             Ftop = prmt(rX, F, mergeLo);
             Hdtop = prmt(rX, Hdtop, mergeHi);
             if (!REV) {
@@ -438,7 +377,7 @@ sw_strip16_kernel(const SwTask* __restrict__ tasks, int ntasks, int* __restrict_
             a = rA;
         };
         for (int u0 = 0; u0 < G; u0 += CK) {
-            if (!REV) {
+            {
                 // ---- checkpoint into the scratch slot: H / E of this thread's rows and the boundary entering its stages at step s
                 uint4* const cq = reinterpret_cast<uint4*>(smem0 + ck_off) + tid;
 #pragma unroll
@@ -450,7 +389,7 @@ sw_strip16_kernel(const SwTask* __restrict__ tasks, int ntasks, int* __restrict_
             }
 #pragma unroll STRIP_UNROLL
             for (int uu = 0; uu < CK; ++uu, ++s) step(u0 + uu);
-            if (!REV) {
+            {
                 // ---- commit: the block just done becomes the committed one iff the better of this thread's two stages (score, then
                 //      earlier column, then the low stage) made its last improvement inside it
                 //      (cvlo / cvhi hold the first step of the block in which the stage last improved; best0 = best at the last look)

@@ -26,10 +26,12 @@ sw_band_trace_kernel(const SwTask* __restrict__ order, int ntasks, const FwdResu
                      uint32_t* __restrict__ cig, unsigned long long cig_cap, unsigned long long* __restrict__ cig_used, FinalResult* __restrict__ out)
 {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= ntasks) return;
-    const int i = order[k].out;
-    const BandRec br = recs[i];
-    if (br.kind != 2) return;
+    const bool live = k < ntasks;
+    const int i = order[live ? k : 0].out;
+    BandRec br = recs[i];
+    if (!live) br.kind = 0;
+    // whole warps stay until the CIGAR arena has been claimed: one atomic per warp for the sum of its lengths
+    const bool walk = br.kind == 2;
     const FwdResult f = fr[i];
     FinalResult r = out[i];
     const int sub_ref = f.ref_end1 - r.ref_begin1 + 1, sub_read = f.read_end1 - r.read_begin1 + 1;
@@ -41,11 +43,13 @@ sw_band_trace_kernel(const SwTask* __restrict__ order, int ntasks, const FwdResu
     // in a local buffer: a short-read CIGAR (a handful of runs) is then written from the buffer and the second walk is skipped.
     constexpr int SHORT = 24;
     uint32_t buf[SHORT];
+    bool failed = false;
     for (int pass = 0; pass < 2; ++pass) {
-        int ti = sub_read - 1, tj = sub_ref - 1, state = 2, run = 0, cnt = 0;
+        if (pass == 1 && (!walk || failed || l <= SHORT)) break;
+        int ti = walk && !failed ? sub_read - 1 : 0, tj = sub_ref - 1, state = 2, run = 0, cnt = 0;
         int op = 0, prev = 0;                               // BAM codes: 0 = M, 1 = I, 2 = D
         int cur_row = ti;
-        unsigned long long cur = dirrow[ti], nxt = ti > 0 ? dirrow[ti - 1] : 0ull;      // row ti and, prefetched, row ti-1
+        unsigned long long cur = walk ? dirrow[ti] : 0ull, nxt = ti > 0 ? dirrow[ti - 1] : 0ull;      // row ti and, prefetched, row ti-1
         auto emit = [&](uint32_t word) {
             if (pass) cig[coff + (unsigned)(l - 1 - cnt)] = word;
             else if (cnt < SHORT) buf[cnt] = word;
@@ -75,24 +79,35 @@ sw_band_trace_kernel(const SwTask* __restrict__ order, int ntasks, const FwdResu
                 case 3: --ti; state = 2; op = 1; break;
                 case 4: --tj; state = 1; op = 2; break;
                 case 5: --tj; state = 2; op = 2; break;
-                default: r.status = 3; r.cigar_len = 0; out[i] = r; return;
+                default: failed = true; ti = 0; break;          // invalid direction: the reference returns NULL (ssw.c:657-665, 840-843)
             }
+            if (failed) break;
             if (ti != cur_row) { cur = nxt; cur_row = ti; nxt = ti > 0 ? dirrow[ti - 1] : 0ull; }
             if (op == prev) ++run;
             else { emit(((uint32_t)run << 4) | (uint32_t)prev); prev = op; run = 1; }
         }
-        if (op == 0) emit((uint32_t)(run + 1) << 4);
-        else { emit(((uint32_t)run << 4) | (uint32_t)op); emit(1u << 4); }
+        if (walk && !failed) {
+            if (op == 0) emit((uint32_t)(run + 1) << 4);
+            else { emit(((uint32_t)run << 4) | (uint32_t)op); emit(1u << 4); }
+        }
         if (!pass) {
-            l = cnt;
-            coff = atomicAdd(cig_used, (unsigned long long)l);
-            if (coff + (unsigned long long)l > cig_cap) { r.status = 6; out[i] = r; return; }
-            if (l <= SHORT) {
+            l = walk && !failed ? cnt : 0;
+            // warp-aggregated claim: inclusive scan of the lengths, one atomicAdd by the last lane, base broadcast
+            const int lane = threadIdx.x & 31;
+            int incl = l;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += v; }
+            unsigned long long base = 0;
+            if (lane == 31 && incl > 0) base = atomicAdd(cig_used, (unsigned long long)incl);
+            base = __shfl_sync(0xffffffffu, base, 31);
+            coff = base + (unsigned long long)(incl - l);
+            if (walk && !failed && coff + (unsigned long long)l > cig_cap) { r.status = 6; out[i] = r; failed = true; l = 0; }
+            if (walk && !failed && l <= SHORT)
                 for (int q = 0; q < l; ++q) cig[coff + (unsigned)(l - 1 - q)] = buf[q];
-                break;
-            }
         }
     }
+    if (!walk) return;
+    if (failed) { if (r.status != 6) { r.status = 3; r.cigar_len = 0; out[i] = r; } return; }
     r.cigar_len = l;
     r.cigar_off = (int64_t)coff;
     out[i] = r;

@@ -21,17 +21,28 @@ constexpr int ROWS_CLASSES = 4;                       // register rows of 3, 5, 
 __host__ __device__ constexpr int rows_class_of(int bw) { return bw <= 1 ? 0 : (bw == 2 ? 1 : (bw <= 4 ? 2 : 3)); }
 __host__ __device__ constexpr int rows_class_cells(int cls) { return cls == 0 ? 3 : (cls == 1 ? 5 : (cls == 2 ? 9 : 15)); }
 
+// One queued banded-DP attempt: everything a lane needs to run it, in two 16-byte words, so that taking a pair costs ONE dependent load
+// after the queue claim (round 1 chased queue -> task -> forward record -> begin positions: four round trips per pair and lane).
+struct __align__(16) BandItem {
+    long long rf_off, rd_off;   // arena index of the first target / read base of the sub-rectangle (ssw.c:836-839)
+    int32_t out_i, k;           // result slot, index in the sorted task list
+    uint32_t dims;              // sub_ref | sub_read << 16   (both <= NARROW_MAX_ROWS + NARROW_BW)
+    uint32_t score_bw;          // score1 | band half-width << 16
+};
+static_assert(sizeof(BandItem) == 32, "two uint4");
+
 struct BandQueues {
-    int2* items;             // [ROWS_CLASSES][capacity] (task index in the sorted task list, band half-width)
+    BandItem* items;         // [ROWS_CLASSES][capacity]
     int* count;              // [ROWS_CLASSES] filled entries per queue
     int* head;               // [ROWS_CLASSES] consumed entries per queue
     int capacity;
 };
 
-__device__ __forceinline__ void band_enqueue(const BandQueues& q, int k, int bw)
+__device__ __forceinline__ void band_enqueue(const BandQueues& q, BandItem it, int bw)
 {
     const int cls = rows_class_of(bw);
-    q.items[(size_t)cls * q.capacity + atomicAdd(q.count + cls, 1)] = make_int2(k, bw);
+    it.score_bw = (it.score_bw & 0xffffu) | ((uint32_t)bw << 16);
+    q.items[(size_t)cls * q.capacity + atomicAdd(q.count + cls, 1)] = it;
 }
 
 __global__ void __launch_bounds__(128)
@@ -40,14 +51,17 @@ sw_band_setup_kernel(const SwTask* __restrict__ order, int ntasks, const FwdResu
                      BandRec* __restrict__ recs, int* __restrict__ flag_list, int* __restrict__ nflag, BandQueues q)
 {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= ntasks) return;
-    const SwTask tk = order[k];
+    const bool live = k < ntasks;                      // whole warps stay: the queue appends below are warp-aggregated (one atomic per warp and queue)
+    const SwTask tk = order[live ? k : 0];
     const int i = tk.out;
     const FwdResult f = fr[i];
     FinalResult r;
     r.ref_begin1 = -1; r.read_begin1 = -1; r.cigar_len = 0; r.status = 0; r.cigar_off = 0;
     BandRec br; br.dir_off = 0; br.bw = 0; br.kind = 0;
-    if (f.want_rev) {
+    int dest = -1;                                     // -1 nothing, 0..3 band queue of that class, 4 warp-kernel list
+    BandItem it;
+    it.rf_off = 0; it.rd_off = 0; it.out_i = i; it.k = k; it.dims = 0; it.score_bw = 0;
+    if (live && f.want_rev) {
         if (f.score1 > 0) {
             const SwEnds e = rev[i];
             r.ref_begin1 = f.ref_end1 - e.col;
@@ -67,14 +81,31 @@ sw_band_setup_kernel(const SwTask* __restrict__ order, int ntasks, const FwdResu
                 else { cig[o] = 1u << 4; r.cigar_off = (int64_t)o; r.cigar_len = 1; }
             } else if (tp.n > 8 || bw > ROWS_MAXBW || sub_read > tp.lane_max_rows) {
                 // wide bands, and reads so long that one lane would serialise millions of cells: one warp per pair instead
-                r.status = 7; br.bw = bw; flag_list[atomicAdd(nflag, 1)] = k;
+                r.status = 7; br.bw = bw; dest = ROWS_CLASSES;
             } else {
-                band_enqueue(q, k, bw);
+                it.rf_off = tk.rf_base + r.ref_begin1; it.rd_off = tk.rd_base + r.read_begin1;
+                it.dims = (uint32_t)sub_ref | ((uint32_t)sub_read << 16);
+                it.score_bw = (uint32_t)f.score1 | ((uint32_t)bw << 16);
+                dest = rows_class_of(bw);
             }
         }
     }
-    out[i] = r;
-    recs[i] = br;
+    // one atomic per warp and destination instead of one per pair (a million same-address atomics cost as much as the DP of a band class)
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int d = 0; d <= ROWS_CLASSES; ++d) {
+        const unsigned m = __ballot_sync(0xffffffffu, dest == d);
+        if (m == 0u) continue;
+        int base = 0;
+        if (lane == __ffs((int)m) - 1) base = atomicAdd(d < ROWS_CLASSES ? q.count + d : nflag, __popc(m));
+        base = __shfl_sync(0xffffffffu, base, __ffs((int)m) - 1);
+        if (dest == d) {
+            const int at = base + __popc(m & ((1u << lane) - 1u));
+            if (d < ROWS_CLASSES) q.items[(size_t)d * q.capacity + at] = it;
+            else flag_list[at] = k;
+        }
+    }
+    if (live) { out[i] = r; recs[i] = br; }
 }
 
 // eight consecutive sequence bytes starting at p[from], zero beyond `len`.  Two aligned 64-bit loads + a funnel shift instead of eight
@@ -108,7 +139,7 @@ sw_band_rows_kernel(const SwTask* __restrict__ order, const int8_t* __restrict__
     }
     __syncthreads();
     const int total = q.count[CLS];                    // complete: every producer of this queue ran in an earlier launch
-    const int2* items = q.items + (size_t)CLS * q.capacity;
+    const uint4* items = reinterpret_cast<const uint4*>(q.items + (size_t)CLS * q.capacity);
     const uint8_t* useq = reinterpret_cast<const uint8_t*>(seq);
 
     bool busy = false, drained = false;
@@ -119,30 +150,38 @@ sw_band_rows_kernel(const SwTask* __restrict__ order, const int8_t* __restrict__
     unsigned long long tq_cur = 0, tq_nxt = 0;         // the 8 + 8 target bases that enter the window next (loaded 8 slides ahead)
     unsigned long long rq_cur = 0, rq_nxt = 0;         // read bases of rows ii .. (octet end) and of the next octet (loaded 8 rows ahead)
     int H[W + 3], E[W + 3];                            // previous row in band coordinates: index 0 = left boundary, cell p lives at p + 1
+    // The NEXT pair of this lane is taken while the current one runs, one dependent step at a time, each consumed rows later:
+    //   pair start: claim a queue slot (nq);  row 6: load its item (nd0, nd1);  row 12: claim its direction words and load its first
+    //   target / read bases.  A lane therefore never waits for a chain of global round trips between pairs (only reads shorter than
+    //   13 rows fall back to doing the missing steps on the spot).
+    int nq = atomicAdd(q.head + CLS, 1);
+    int stage = 0;                                     // 0: slot claimed, 1: item loaded, 2: arena claimed + first bases loaded
+    uint4 nd0 = make_uint4(0, 0, 0, 0), nd1 = nd0;
+    unsigned long long n_o = 0, n_win_lo = 0, n_win_hi = 0, n_rq = 0;
 
     for (;;) {
         if (!busy && !drained) {
-            const int qi = atomicAdd(q.head + CLS, 1);
-            if (qi >= total) drained = true;
+            if (nq >= total) drained = true;
             else {
-                const int2 it = items[qi];
-                kcur = it.x; bw = it.y;
-                const SwTask tk = order[kcur];
-                i = tk.out;
-                const FwdResult f = fr[i];
-                const FinalResult r = out[i];
-                sub_ref = f.ref_end1 - r.ref_begin1 + 1; sub_read = f.read_end1 - r.read_begin1 + 1; score = f.score1;
-                ref = useq + tk.rf_base + r.ref_begin1; read = useq + tk.rd_base + r.read_begin1;
+                if (stage == 0) { nd0 = items[2 * (size_t)nq]; nd1 = items[2 * (size_t)nq + 1]; }
+                const long long rf_off = (long long)(((unsigned long long)nd0.y << 32) | nd0.x), rd_off = (long long)(((unsigned long long)nd0.w << 32) | nd0.z);
+                i = (int)nd1.x; kcur = (int)nd1.y;
+                sub_ref = (int)(nd1.z & 0xffffu); sub_read = (int)(nd1.z >> 16); score = (int)(nd1.w & 0xffffu); bw = (int)(nd1.w >> 16);
+                ref = useq + rf_off; read = useq + rd_off;
                 const unsigned long long need = (unsigned long long)sub_read * 8ull;
-                const unsigned long long o = atomicAdd(scratch.used, (need + 15ull) & ~15ull);
+                unsigned long long o;
+                if (stage < 2) {
+                    o = atomicAdd(scratch.used, (need + 15ull) & ~15ull);
+                    win_lo = load8(ref, 0, sub_ref); win_hi = load8(ref, 8, sub_ref); rq_cur = load8(read, 0, sub_read);
+                } else { o = n_o; win_lo = n_win_lo; win_hi = n_win_hi; rq_cur = n_rq; }
+                stage = 0;
+                nq = atomicAdd(q.head + CLS, 1);
                 if (o + need > scratch.bytes) { out[i].status = 5; }
                 else {
                     dir_off = o; dirrow = reinterpret_cast<unsigned long long*>(scratch.base + o);
 #pragma unroll
                     for (int x = 0; x < W + 3; ++x) { H[x] = 0; E[x] = 0; }
-                    win_lo = load8(ref, 0, sub_ref); win_hi = load8(ref, 8, sub_ref);
-                    tq_cur = load8(ref, 16, sub_ref); tq_nxt = load8(ref, 24, sub_ref);
-                    rq_cur = load8(read, 0, sub_read); rq_nxt = load8(read, 8, sub_read);
+                    tq_cur = load8(ref, 16, sub_ref); tq_nxt = load8(ref, 24, sub_ref); rq_nxt = load8(read, 8, sub_read);
                     wbase = 0; ii = 0; maxv = 0;
                     busy = true;
                 }
@@ -151,6 +190,15 @@ sw_band_rows_kernel(const SwTask* __restrict__ order, const int8_t* __restrict__
         // lanes leave together, once every lane has seen the queue empty (the queue of this class only shrinks while the kernel runs)
         if (!__any_sync(0xffffffffu, busy || !drained)) break;
         if (!busy) continue;
+        if (ii == 6 && stage == 0 && nq < total) { nd0 = items[2 * (size_t)nq]; nd1 = items[2 * (size_t)nq + 1]; stage = 1; }
+        else if (ii == 12 && stage == 1) {
+            const uint8_t* nref = useq + (long long)(((unsigned long long)nd0.y << 32) | nd0.x);
+            const uint8_t* nread = useq + (long long)(((unsigned long long)nd0.w << 32) | nd0.z);
+            const int n_sub_ref = (int)(nd1.z & 0xffffu), n_sub_read = (int)(nd1.z >> 16);
+            n_o = atomicAdd(scratch.used, ((unsigned long long)n_sub_read * 8ull + 15ull) & ~15ull);
+            n_win_lo = load8(nref, 0, n_sub_ref); n_win_hi = load8(nref, 8, n_sub_ref); n_rq = load8(nread, 0, n_sub_read);
+            stage = 2;
+        }
 
         // ------------------------------------------------------------------ one read row
         const int xi = max(ii - bw, 0);
@@ -207,7 +255,10 @@ sw_band_rows_kernel(const SwTask* __restrict__ order, const int8_t* __restrict__
             if (maxv >= score) {                                                              // ssw.c:614-615
                 BandRec br; br.dir_off = dir_off; br.bw = bw; br.kind = 2; recs[i] = br;
             } else if (2 * bw <= ROWS_MAXBW) {
-                band_enqueue(q, kcur, 2 * bw);         // always a later class: the launches go through the classes in increasing order
+                BandItem it;
+                it.rf_off = (long long)(ref - useq); it.rd_off = (long long)(read - useq); it.out_i = i; it.k = kcur;
+                it.dims = (uint32_t)sub_ref | ((uint32_t)sub_read << 16); it.score_bw = (uint32_t)score;
+                band_enqueue(q, it, 2 * bw);           // always a later class: the launches go through the classes in increasing order
             } else {
                 out[i].status = 7; BandRec br; br.dir_off = 0; br.bw = 2 * bw; br.kind = 0; recs[i] = br;
                 flag_list[atomicAdd(nflag, 1)] = kcur;
