@@ -45,6 +45,51 @@ def build_hosttest(force=False):
     return _HOSTTEST_SO
 
 
+_REFSRC = "/root/reference/bin/realignment"
+_CALLERS = os.path.join(HERE, "..", "baseline", "_ref")
+
+
+def callers_dir():
+    return os.path.abspath(_CALLERS)
+
+
+def build_ref_callers(force=False):
+    """The reference's OWN callers of the hot path, unmodified, for the boundary tests (tests/test_gpu_reference_callers.py):
+      baseline/_ref/{pyssw.py, fast_align_reads2ref.py}          copied as they are (they load realign/libssw.so next to them)
+      baseline/_ref/{ssw_cpp.cpp, ssw_cpp.h, realigner.cpp, realigner.h, ssw.c, ssw.h(as ssw_ref.h)}    copied as they are
+      baseline/_ref/realigner_refsrc_on_product    reference ssw_cpp.cpp + realigner.cpp compiled against include/ssw.h and LINKED TO THE PRODUCT
+                                                   libssw.so -- INTEGRATION.md section 1's recipe (reference README.md:45 with ssw.c replaced)
+      baseline/_ref/ssw_cpp_probe_ref              tests/cpp/ssw_cpp_probe_common.cpp on the reference's ssw_cpp.cpp + ssw.c (all CPU)
+    baseline/_ref is git-ignored and travels to the GPU box; nothing here is product code.  Returns the directory, or None when neither
+    the reference sources nor a previous build are present."""
+    import shutil
+    d = callers_dir()
+    root = os.path.abspath(os.path.join(HERE, ".."))
+    obj = os.path.join(d, "realigner_refsrc_on_product")
+    probe = os.path.join(d, "ssw_cpp_probe_ref")
+    have_src = os.path.exists(os.path.join(_REFSRC, "pyssw.py"))
+    if not have_src:
+        return d if os.path.exists(obj) and os.path.exists(os.path.join(d, "pyssw.py")) else None
+    os.makedirs(d, exist_ok=True)
+    for f in ("pyssw.py", "fast_align_reads2ref.py"):
+        shutil.copyfile(os.path.join(_REFSRC, f), os.path.join(d, f))
+    for f in ("ssw_cpp.cpp", "ssw_cpp.h", "realigner.cpp", "realigner.h", "ssw.c"):
+        shutil.copyfile(os.path.join(_REFSRC, "realign", f), os.path.join(d, f))
+    prod = os.path.join(root, "megapath-nano_b200", "realign")
+    if os.path.exists(os.path.join(prod, "libssw.so")) and (force or not os.path.exists(obj) or os.path.getmtime(obj) < os.path.getmtime(os.path.join(prod, "libssw.so"))):
+        # `#include "ssw.h"` in the copied sources resolves to include/ssw.h (no ssw.h is copied next to them)
+        subprocess.run(["g++", "-std=c++14", "-O1", "-shared", "-fPIC", "-w", "-I", os.path.join(root, "include"), "-o", obj,
+                        os.path.join(d, "ssw_cpp.cpp"), os.path.join(d, "realigner.cpp"), os.path.join(prod, "libssw.so"), "-Wl,-rpath," + prod], check=True)
+    src = os.path.join(root, "tests", "cpp", "ssw_cpp_probe_common.cpp")
+    if force or not os.path.exists(probe) or os.path.getmtime(probe) < os.path.getmtime(src):
+        refh = os.path.join(d, "_refhdr")
+        os.makedirs(refh, exist_ok=True)
+        shutil.copyfile(os.path.join(_REFSRC, "realign", "ssw.h"), os.path.join(refh, "ssw.h"))          # the all-CPU probe uses the reference's own header
+        subprocess.run(["gcc", "-O2", "-w", "-I", refh, "-c", "-o", os.path.join(d, "ssw_ref.o"), os.path.join(d, "ssw.c")], check=True)
+        subprocess.run(["g++", "-std=c++14", "-O1", "-w", "-I", refh, "-I", d, "-o", probe, src, os.path.join(d, "ssw_cpp.cpp"), os.path.join(d, "ssw_ref.o")], check=True)
+    return d
+
+
 _port = None
 _ref = None
 

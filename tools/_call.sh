@@ -1,2 +1,1 @@
-python tools/phase_bench.py 1000000 2 2>&1 | tail -1
-python -m pytest tests -m gpu -x -q 2>&1 | tail -5
+python -m pytest tests/test_gpu_reference_callers.py -x -q 2>&1 | tail -15
