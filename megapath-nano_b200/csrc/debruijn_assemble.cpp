@@ -107,8 +107,11 @@ public:
             return seen;
         };
         const std::vector<uint8_t> fwd = reach(source, ofirst, oto), bwd = reach(sink, ifirst, ifrom);
-        // successors among the kept vertices, ascending vertex id = order of first appearance (the reference iterates a std::set of
-        // heap node addresses, i.e. allocation order; the order only matters for WHEN the live-path cap is hit, the output is sorted)
+        // successors among the kept vertices, ascending vertex id = order of first appearance.  The reference iterates a std::set of heap
+        // node ADDRESSES (Boost listS descriptors), i.e. creation order under an allocator that hands out increasing addresses.  The output
+        // is sorted, so the order is observable in one case only: the count tested before the last pop is (all paths) - (successors of the
+        // last popped vertex - 1), so when the total exceeds 256 by less than that, the visiting order decides between "every path" and
+        // "none" (debruijn_graph.cpp:293-299) -- i.e. only when the last branching sits right before the sink / a dead end.
         std::vector<int> kfirst((size_t)nv + 1, 0), kto;
         kto.reserve(oto.size());
         for (int v = 0; v < nv; ++v) {

@@ -16,6 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 _ORACLE_SO = os.path.join(HERE, "liboracle.so")
 _REF_SO = os.path.join(HERE, "_ref", "libssw_ref.so")
 _REALIGNER_REF = os.path.join(HERE, "_ref", "realigner_ref")
+_DBG_REF = os.path.join(HERE, "_ref", "debruijn_graph_ref")
 
 FIELDS = ("score1", "score2", "ref_begin1", "ref_end1", "read_begin1", "read_end1", "ref_end2", "cigarLen")
 
@@ -27,7 +28,7 @@ def build(force=False):
     have_ref_src = os.path.exists("/root/reference/bin/realignment/realign/ssw.c")
     if need:
         subprocess.run(["make", "-C", HERE, os.path.join(HERE, "liboracle.so")], check=True, capture_output=True)
-    if have_ref_src and (force or not os.path.exists(_REF_SO) or not os.path.exists(_REALIGNER_REF)):
+    if have_ref_src and (force or not os.path.exists(_REF_SO) or not os.path.exists(_REALIGNER_REF) or not os.path.exists(_DBG_REF)):
         subprocess.run(["make", "-C", HERE, "ref"], check=True, capture_output=True)
 
 
@@ -136,6 +137,16 @@ def ref_path():
 
 def realigner_ref_path():
     return _REALIGNER_REF
+
+
+def dbg_ref_path():
+    """the reference's debruijn_graph.cpp, unmodified, compiled over oracle/boost_shim (None when not built)"""
+    if not os.path.exists(_DBG_REF):
+        try:
+            build()
+        except Exception:
+            pass
+    return _DBG_REF if os.path.exists(_DBG_REF) else None
 
 
 def _p(a, t):

@@ -1,6 +1,7 @@
-"""Window haplotype assembler (include/debruijn_graph.h): the Boost-free C++ implementation against the
-string-keyed restatement oracle/dbg_oracle.py (parity UNPINNED: the reference's debruijn_graph.cpp needs Boost and cannot be built
-here), plus properties that hold for the reference by construction.  Host code only -> runs in the CPU tier."""
+"""Window haplotype assembler (include/debruijn_graph.h): the Boost-free C++ implementation against
+(a) the reference itself -- its unmodified debruijn_graph.cpp compiled over oracle/boost_shim (oracle/_ref/debruijn_graph_ref), live and
+through the committed golden windows made from it -- (b) the string-keyed restatement oracle/dbg_oracle.py, and (c) properties that hold
+for the reference by construction.  Host code only -> runs in the CPU tier."""
 import ctypes
 import importlib
 import os
@@ -137,9 +138,29 @@ def test_assembled_regions_through_the_realigner_host_logic():
     assert moved > 0                                              # reads of the alternative haplotypes get new CIGARs
 
 
+def test_live_against_the_compiled_reference():
+    """the product and the reference object (unmodified debruijn_graph.cpp over the Boost stand-in), same ctypes call sequence, on seeded
+    windows incl. repeats / N / low-quality positions and on windows around the 256-path cap"""
+    from oracle import oracle as O
+    ref_obj = O.dbg_ref_path()
+    if ref_obj is None:
+        pytest.skip("oracle/_ref/debruijn_graph_ref not built (needs /root/reference; the prebuilt object travels to the GPU box)")
+    wins = w.dbg_windows(24, seed=7101, max_reads=120) + w.dbg_windows(8, seed=7102, max_reads=40, repeat_frac=1.0) + \
+        w.dbg_windows(8, seed=7103, max_reads=200, n_frac=0.01, lowq_frac=0.05) + [(r, rd, lq) for r, rd, lq, _ in w.dbg_cap_windows(seed=43)]
+    multi = 0
+    for ref, reads, lowq in wins:
+        want = D.get_consensus(ref, reads, lowq, lib_path=ref_obj)
+        assert D.get_consensus(ref, reads, lowq) == want
+        assert oracle(ref, reads, lowq)[0] == want                # the restatement agrees with the reference too
+        multi += len(want) > 1
+    assert multi >= 10
+    caps = w.dbg_cap_windows(seed=43)
+    assert [len(D.get_consensus(r, rd, lq)) for r, rd, lq, _ in caps] == [n if n <= 256 else 0 for _, _, _, n in caps]
+
+
 def test_golden_windows():
-    """committed fixtures (tests/golden/dbg_golden.json.gz, made by tests/golden/make_golden_dbg.py from the restatement): both the product and
-    the restatement still give them"""
+    """committed fixtures (tests/golden/dbg_golden.json.gz, made by tests/golden/make_golden_dbg.py from the compiled reference): the product
+    and the restatement still give them"""
     import gzip, json
     with gzip.open(os.path.join(ROOT, "tests", "golden", "dbg_golden.json.gz"), "rt") as f:
         doc = json.load(f)

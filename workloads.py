@@ -433,6 +433,37 @@ def dbg_windows(nwindows=32, seed=21, max_reads=400, err=0.005, repeat_frac=0.2,
     return out
 
 
+def dbg_cap_windows(seed=41):
+    """Assembler inputs around the 256-path cap of CandidatePaths (debruijn_graph.cpp:293-299): isolated multi-allelic sites, every allele
+    combination read twice, so the number of source-to-sink paths is the product of the allele counts -- 243, 256 (two shapes), 288, 324,
+    512 -- plus one window whose LAST branching sits right before the sink (the case in which the visiting order of successors decides
+    whether the cap trips).  Returns a list of (ref, reads, low_quality_fields, expected number of paths)."""
+    rng = np.random.default_rng(seed)
+    out = []
+    for alleles in ([3] * 5, [2] * 8, [4] * 4, [2] * 5 + [3] * 2, [3] * 4 + [4], [2] * 9, [2] * 7 + [3]):
+        gap = 40
+        ref = _rand_dna(rng, gap * (len(alleles) + 1))
+        sites = [gap * (k + 1) for k in range(len(alleles))]
+        if alleles == [2] * 7 + [3]:
+            sites[-1] = len(ref) - 14                      # last branching close to the sink (k is 10 or a little more)
+        reads = []
+        # every read covers two neighbouring sites (and nothing else varies), all allele pairs, twice -> every edge has weight >= 2
+        for k in range(len(sites)):
+            lo = max(0, sites[k] - 30); hi = min(len(ref), (sites[k + 1] if k + 1 < len(sites) else sites[k]) + 30)
+            for a in range(alleles[k]):
+                for b in range(alleles[k + 1] if k + 1 < len(sites) else 1):
+                    r = list(ref)
+                    r[sites[k]] = "ACGT"[("ACGT".index(ref[sites[k]]) + a) % 4]
+                    if k + 1 < len(sites):
+                        r[sites[k + 1]] = "ACGT"[("ACGT".index(ref[sites[k + 1]]) + b) % 4]
+                    reads += ["".join(r[lo:hi])] * 2
+        n = 1
+        for x in alleles:
+            n *= x
+        out.append((ref, reads, [""] * len(reads), n))
+    return out
+
+
 @dataclass
 class WindowWorkload:
     """one candidate window before assembly (realign_illumina_reads.py:532-580): `chrom` is a piece of reference sequence whose first
