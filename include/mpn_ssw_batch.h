@@ -84,6 +84,17 @@ int mpn_align_batch(mpn_engine* e, const mpn_params* p, const int8_t* reads, con
                     const int64_t* ref_off, const int32_t* masklen, int64_t npairs, mpn_result* out, uint32_t* cigar, int64_t cigar_cap);
 
 /*
+ * The same call with NIBBLE-PACKED sequences: base i of the concatenated reads (targets) is the low nibble (i even) or the high nibble
+ * (i odd) of reads4[i / 2] (refs4[i / 2]); read_off / ref_off stay in BASES.  Codes must be below 16 (n <= 16).  Half the host->device
+ * bytes of mpn_align_batch -- on a box whose GPUs share PCIe uplinks that copy is what limits short-read batches;
+ * a small kernel expands the nibbles on the device, everything after that is identical.  A caller that holds ASCII (every reference
+ * caller does: ssw_cpp.cpp:311-323, pyssw.py:86-98) can translate straight to nibbles; mpn_pack4 converts int8 codes on host threads.
+ */
+int mpn_align_batch_packed4(mpn_engine* e, const mpn_params* p, const uint8_t* reads4, const int64_t* read_off, const uint8_t* refs4,
+                            const int64_t* ref_off, const int32_t* masklen, int64_t npairs, mpn_result* out, uint32_t* cigar, int64_t cigar_cap);
+void mpn_pack4(const int8_t* codes, int64_t n, uint8_t* out /* (n + 1) / 2 bytes */);
+
+/*
  * Same call for pairs that SHARE sequences (one haplotype against many reads, realigner.cpp:351-384): one arena of int8
  * codes plus, per pair, the start and length of its read and of its target inside the arena.  Spans may overlap or repeat;
  * every distinct sequence is uploaded once.

@@ -45,6 +45,10 @@ def lib():
                                       ct.c_void_p, ct.c_void_p, ct.c_int64]
         L.mpn_align_batch_spans.argtypes = [ct.c_void_p, ct.POINTER(MpnParams), ct.c_void_p, ct.c_int64, ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_void_p,
                                             ct.c_void_p, ct.c_int64, ct.c_void_p, ct.c_void_p, ct.c_int64]
+        L.mpn_align_batch_packed4.argtypes = [ct.c_void_p, ct.POINTER(MpnParams), ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_int64,
+                                              ct.c_void_p, ct.c_void_p, ct.c_int64]
+        L.mpn_pack4.argtypes = [ct.c_void_p, ct.c_int64, ct.c_void_p]
+        L.mpn_pack4.restype = None
         L.mpn_pool_create.restype = ct.c_void_p
         L.mpn_pool_create.argtypes = [ct.c_void_p, ct.c_int]
         L.mpn_pool_destroy.argtypes = [ct.c_void_p]
@@ -159,6 +163,32 @@ class Engine:
         if rc:
             raise RuntimeError(f"mpn_align_batch -> {rc}")
         return out, cig
+
+
+def pack4(codes):
+    """int8 codes -> nibble-packed uint8 array for Engine.align_packed4 (mpn_pack4: base i in the low / high nibble of byte i // 2)"""
+    codes = np.ascontiguousarray(codes, dtype=np.int8)
+    out = np.zeros((len(codes) + 1) // 2, dtype=np.uint8)
+    lib().mpn_pack4(_ptr(codes), len(codes), _ptr(out))
+    return out
+
+
+def _align_packed4(self, b, reads4, refs4, cigar_cap=None, out=None, cig=None):
+    """mpn_align_batch_packed4: b carries offsets (in bases), maskLen and scoring as usual; reads4 / refs4 are the nibble-packed streams."""
+    n = int(b.npairs)
+    if cigar_cap is None:
+        cigar_cap = n * 24 + int(b.read_off[-1]) // 4 + 4096
+    out = np.zeros(n, dtype=RESULT_DTYPE) if out is None else out
+    cig = np.zeros(max(cigar_cap, 1), dtype=np.uint32) if cig is None else cig
+    keep = []
+    p = self._params(b, keep)
+    rc = self.L.mpn_align_batch_packed4(self.h, ct.byref(p), _ptr(reads4), _ptr(b.read_off), _ptr(refs4), _ptr(b.ref_off), _ptr(b.masklen), n, _ptr(out), _ptr(cig), int(cigar_cap))
+    if rc:
+        raise RuntimeError(f"mpn_align_batch_packed4 -> {rc}")
+    return out, cig
+
+
+Engine.align_packed4 = _align_packed4
 
 
 class Pool:

@@ -78,7 +78,7 @@ struct PinBuf {
 };
 
 constexpr int STRIP_BLOCK_THREADS = 128;   // = STRIP_BLOCK of sw_strip16.cuh (the kernels are compiled in strip_inst_*.cu)
-struct StripCfg { int G, KR, cap; StripFn fn; StripFn fn_rev; size_t smem, smem_rev; int blocks_per_sm, blocks_per_sm_rev; };
+struct StripCfg { int G, KR, cap; StripFn fn; StripFn fn_rev; size_t smem, smem_rev; };
 
 // all instantiations of the packed kernel, sorted by the number of read rows one strip covers (cap = 2 * G * KR)
 std::vector<StripCfg> g_strips;
@@ -88,8 +88,6 @@ int LONG_BIN = 0;                        // pseudo-bin of the multi-strip clampe
 int WIDE_BIN = 0;                        // pseudo-bin of the 32-bit kernel
 constexpr int LONG_KR = 16;
 
-void set_strip_attributes();
-
 void build_strip_table()
 {
     if (!g_strips.empty()) return;
@@ -98,7 +96,7 @@ void build_strip_table()
     for (int p = 0; p < 4; ++p)
         for (int k = 0; k < counts[p]; ++k) {
             const StripEntry& e = parts[p][k];
-            g_strips.push_back(StripCfg{e.G, e.KR, 2 * e.G * e.KR, e.fn, e.fn_rev, e.smem, e.smem_rev, 1, 1});
+            g_strips.push_back(StripCfg{e.G, e.KR, 2 * e.G * e.KR, e.fn, e.fn_rev, e.smem, e.smem_rev});
         }
     std::stable_sort(g_strips.begin(), g_strips.end(), [](const StripCfg& a, const StripCfg& b) { return a.cap < b.cap; });
     N_STRIPS = (int)g_strips.size();
@@ -110,29 +108,6 @@ void build_strip_table()
         while (g_strips[k].cap < len) ++k;
         g_bin_of_len[len] = (int16_t)k;
     }
-    set_strip_attributes();
-    // resident blocks per SM of every instantiation (all devices of a box are the same part): queried once, under the call_once of
-    // mpn_engine_create, so that engines created concurrently (one per device, mpn_pool) never write the table while another launches
-    for (int c = 0; c < N_STRIPS; ++c) {
-        int nb = 0, nbr = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, g_strips[c].fn, STRIP_BLOCK_THREADS, g_strips[c].smem));
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nbr, g_strips[c].fn_rev, STRIP_BLOCK_THREADS, g_strips[c].smem_rev));
-        g_strips[c].blocks_per_sm = nb > 0 ? nb : 1;
-        g_strips[c].blocks_per_sm_rev = nbr > 0 ? nbr : 1;
-        if (getenv("MPN_VERBOSE")) fprintf(stderr, "[mpn_ssw] strip G=%d KR=%d cap=%d smem=%zu/%zu blocks/SM=%d/%d\n", g_strips[c].G, g_strips[c].KR, g_strips[c].cap, g_strips[c].smem, g_strips[c].smem_rev, nb, nbr);
-    }
-}
-
-// the forward instantiations keep two checkpoint slots per thread in shared memory (sw_strip16.cuh): above the 48 KB default, so the
-// limit is raised and the carve-out set to all-shared per kernel; attributes are per device -> once per engine
-void set_strip_attributes()
-{
-    auto one = [](StripFn fn, size_t smem) {
-        if (smem > 48 * 1024) CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CK(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    };
-    for (int c = 0; c < N_STRIPS; ++c) { one(g_strips[c].fn, g_strips[c].smem); one(g_strips[c].fn_rev, g_strips[c].smem_rev); }
-    for (const StripEntry* e : {&g_strip_n_a, &g_strip_n_b, &g_strip_n_c, &g_strip_n_d}) { one(e->fn, e->smem); one(e->fn_rev, e->smem_rev); }
 }
 
 }  // namespace
@@ -142,7 +117,11 @@ struct mpn_engine {
     int sm_count = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
     int64_t launches = 0, pairs = 0, cells = 0, wide_pairs = 0;
-    bool occ_done = false;
+    // per strip instantiation (forward / reverse, then the 4 N variants): resident blocks per SM, 0 = not prepared yet on this device.
+    // Preparation (shared-memory limit above 48 KB, all-shared carve-out, occupancy query) happens at the first launch of an instantiation,
+    // not at engine creation: touching all ~80 kernels up front loads every one of them and costs seconds in a process that aligns a
+    // handful of pairs (the reference's process-per-position model, realignment.sh:50-60).
+    std::vector<int> strip_blocks;
     bool profile = false;
     static constexpr int NAUX = 3;                   // side streams: the bins of one score pass run concurrently, so the tail of one launch overlaps the next
     cudaStream_t aux[NAUX] = {nullptr, nullptr, nullptr};
@@ -179,7 +158,7 @@ struct mpn_batch {
     Score16 sc16{};
     FinishParams fin{};
     // device
-    DevBuf seq, mask, tasks_fwd, tasks_rev, ends_fwd, ends_rev, colrec, fwdres, finalres, counters, dmat, scratch, cig, wide_boundary, long_boundary, warp_dir, bandrec, flaglist, bandq_items, bandq_meta, relist;
+    DevBuf seq, mask, tasks_fwd, tasks_rev, ends_fwd, ends_rev, colrec, fwdres, finalres, counters, dmat, scratch, cig, wide_boundary, long_boundary, warp_dir, bandrec, flaglist, bandq_items, bandq_meta, relist, pack_stage;
     size_t seq_reads_bytes = 0, seq_bytes = 0;
     int64_t colrec_words = 0;
     unsigned long long scratch_bytes = 0, cig_cap = 0;
@@ -220,7 +199,7 @@ extern "C" mpn_engine* mpn_engine_create(int device)
     CK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
     static std::once_flag once;
     std::call_once(once, build_strip_table);
-    set_strip_attributes();                       // function attributes are per device
+    e->strip_blocks.assign((size_t)2 * (N_STRIPS + 4), 0);
     return e;
 }
 
@@ -303,7 +282,7 @@ extern "C" void mpn_batch_free(mpn_batch* b)
     // after run but before a successful fetch, or on an error path).  After a fetch the stream is already idle and this returns at once.
     if (b->st) cudaStreamSynchronize(b->st);
     DevBuf* bufs[] = {&b->seq, &b->mask, &b->tasks_fwd, &b->tasks_rev, &b->ends_fwd, &b->ends_rev,
-                      &b->colrec, &b->fwdres, &b->finalres, &b->counters, &b->dmat, &b->scratch, &b->cig, &b->wide_boundary, &b->long_boundary, &b->warp_dir, &b->bandrec, &b->flaglist, &b->bandq_items, &b->bandq_meta, &b->relist};
+                      &b->colrec, &b->fwdres, &b->finalres, &b->counters, &b->dmat, &b->scratch, &b->cig, &b->wide_boundary, &b->long_boundary, &b->warp_dir, &b->bandrec, &b->flaglist, &b->bandq_items, &b->bandq_meta, &b->relist, &b->pack_stage};
     for (DevBuf* d : bufs) b->e->pool.give(*d);
     delete b;
 }
@@ -442,7 +421,8 @@ static mpn_batch* upload_impl(mpn_engine* e, int slot_id, const mpn_params* p, c
     pool.take(b->dmat, (size_t)n * n + 16);
     pool.take(b->relist, 2 * sizeof(int) * (size_t)(npairs + 2));       // pairs refused by the packed kernel (reads with N): [count, task indices...] per pass
     if (npairs) {
-        src.copy_arena(b->seq.as<int8_t>(), st);
+        if (src.staging_bytes()) pool.take(b->pack_stage, src.staging_bytes());
+        src.copy_arena(b->seq.as<int8_t>(), b->pack_stage.as<uint8_t>(), st);
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(b->mask.p, masklen, sizeof(int32_t) * npairs, cudaMemcpyHostToDevice, st));
         CK(cudaMemcpyAsync(b->tasks_fwd.p, h_tasks, sizeof(SwTask) * npairs, cudaMemcpyHostToDevice, st));
@@ -450,7 +430,7 @@ static mpn_batch* upload_impl(mpn_engine* e, int slot_id, const mpn_params* p, c
     sl.pin_misc.reserve(4096 + (size_t)n * n);
     memcpy(sl.pin_misc.as<char>() + 4096, b->mat.data(), (size_t)n * n);
     CK(cudaMemcpyAsync(b->dmat.p, sl.pin_misc.as<char>() + 4096, (size_t)n * n, cudaMemcpyHostToDevice, st));
-    b->h2d_bytes = b->seq_bytes + (sizeof(int32_t) + sizeof(SwTask)) * (size_t)npairs + (size_t)n * n;
+    b->h2d_bytes = src.h2d_bytes() + (sizeof(int32_t) + sizeof(SwTask)) * (size_t)npairs + (size_t)n * n;
 
     // ---- boundary rows of the 32-bit kernel (one slot per resident warp)
     b->wide_blocks = e->sm_count * 3;
@@ -530,6 +510,22 @@ static int* relist_of(mpn_batch* b, bool forward)
     return b->relist.as<int>() + (forward ? 0 : b->npairs + 2);
 }
 
+// first use of a strip instantiation on this engine's device: raise its dynamic shared-memory limit (the checkpoint slots of
+// sw_strip16.cuh need more than the 48 KB default), prefer the all-shared carve-out, and ask how many blocks fit on an SM
+static int prepare_strip(mpn_engine* e, size_t slot, StripFn fn, size_t smem)
+{
+    int& nb = e->strip_blocks[slot];
+    if (nb == 0) {
+        if (smem > 48 * 1024) CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        int q = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, fn, STRIP_BLOCK_THREADS, smem));
+        nb = q > 0 ? q : 1;
+        if (getenv("MPN_VERBOSE")) fprintf(stderr, "[mpn_ssw] device %d: strip kernel slot %zu smem=%zu blocks/SM=%d\n", e->device, slot, smem, nb);
+    }
+    return nb;
+}
+
 static void launch_strips(mpn_batch* b, const SwTask* tasks, bool forward, SwEnds* ends, int counter_base)
 {
     mpn_engine* e = b->e;
@@ -564,7 +560,8 @@ static void launch_strips(mpn_batch* b, const SwTask* tasks, bool forward, SwEnd
             const StripCfg& c = g_strips[bl.cfg];
             const int groups_per_block = STRIP_BLOCK_THREADS / c.G;
             int64_t blocks = (bl.count + groups_per_block - 1) / groups_per_block;
-            blocks = std::min<int64_t>(blocks, (int64_t)e->sm_count * (forward ? c.blocks_per_sm : c.blocks_per_sm_rev));
+            const int per_sm = prepare_strip(e, (size_t)2 * bl.cfg + (forward ? 0 : 1), forward ? c.fn : c.fn_rev, forward ? c.smem : c.smem_rev);
+            blocks = std::min<int64_t>(blocks, (int64_t)e->sm_count * per_sm);
             (forward ? c.fn : c.fn_rev)<<<(unsigned)blocks, STRIP_BLOCK_THREADS, forward ? c.smem : c.smem_rev, st>>>(tasks + bl.first, (int)bl.count, counter, b->seq.as<int8_t>(), b->sc16,
                                                                   forward ? b->colrec.as<uint32_t>() : nullptr, ends, relist_of(b, forward), (int)bl.first);
         }
@@ -591,6 +588,7 @@ static void launch_n_variants(mpn_batch* b, const SwTask* tasks, bool forward, S
         const StripEntry& c = *nv[k];
         const int cap = 2 * c.G * c.KR;
         if (b->max_rd > min_len) {
+            prepare_strip(e, (size_t)2 * (N_STRIPS + k) + (forward ? 0 : 1), forward ? c.fn : c.fn_rev, forward ? c.smem : c.smem_rev);
             int* counter = reinterpret_cast<int*>(b->counters.as<unsigned long long>() + counter_base + k);
             (forward ? c.fn : c.fn_rev)<<<(unsigned)(e->sm_count * 2), STRIP_BLOCK_THREADS, forward ? c.smem : c.smem_rev, b->st>>>(tasks, 0, counter, b->seq.as<int8_t>(), b->sc16,
                                                                   forward ? b->colrec.as<uint32_t>() : nullptr, ends, relist, min_len);
@@ -794,6 +792,71 @@ extern "C" int mpn_batch_fetch(mpn_batch* b, mpn_result* out, uint32_t* cigar, i
     return fetch_impl(b, out, cigar, cigar_cap, 0, nullptr);
 }
 
+// ---- nibble-packed input (mpn_align_batch_packed4): expand `nbases` nibbles starting at nibble `first` of src into int8 codes
+__global__ void __launch_bounds__(256) unpack4_kernel(const uint8_t* __restrict__ src, int64_t first, int64_t nbases, int8_t* __restrict__ dst, int mis)
+{
+    // 16 output bases per thread, laid out so that the interior threads store one ALIGNED 16-byte word (dst itself may sit at any byte of the
+    // arena: `mis` = its address modulo 16); the nibbles of a thread lie in 8 or 9 staging bytes (the staging buffer is padded by 16 bytes)
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t k0 = t * 16 - mis;               // first output base of this thread (negative part of thread 0 is skipped)
+    if (k0 >= nbases) return;
+    const int64_t ka = k0 < 0 ? 0 : k0;
+    const int64_t n0 = first + ka;                 // nibble index of the first base handled
+    const uint8_t* p = src + (n0 >> 1);
+    unsigned long long lo = 0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) lo |= (unsigned long long)p[q] << (8 * q);
+    if (n0 & 1) lo = (lo >> 4) | ((unsigned long long)p[8] << 60);
+    uint32_t w[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const uint32_t x = (uint32_t)(lo >> (16 * q)) & 0xffffu;             // 4 nibbles -> 4 bytes
+        w[q] = (x & 0xfu) | ((x & 0xf0u) << 4) | ((x & 0xf00u) << 8) | ((x & 0xf000u) << 12);
+    }
+    if (k0 >= 0 && k0 + 16 <= nbases) *reinterpret_cast<uint4*>(dst + k0) = make_uint4(w[0], w[1], w[2], w[3]);
+    else {
+        const int cnt = (int)(((k0 + 16 < nbases) ? k0 + 16 : nbases) - ka);
+        for (int q = 0; q < cnt; ++q) dst[ka + q] = (int8_t)((w[q >> 2] >> (8 * (q & 3))) & 0xffu);
+    }
+}
+
+void mpn::launch_unpack4(const uint8_t* src, int64_t first_base, int64_t nbases, int8_t* dst, cudaStream_t st)
+{
+    if (nbases <= 0) return;
+    const int mis = (int)(reinterpret_cast<uintptr_t>(dst) & 15u);
+    const int64_t threads = (nbases + mis + 15) / 16;
+    unpack4_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(src, first_base, nbases, dst, mis);
+}
+
+extern "C" void mpn_pack4(const int8_t* codes, int64_t n, uint8_t* out)
+{
+    mpn::parallel_for((n + 1) / 2, 1 << 20, [&](int64_t k) {
+        const int64_t i = 2 * k;
+        out[k] = (uint8_t)((codes[i] & 15) | ((i + 1 < n ? codes[i + 1] & 15 : 0) << 4));
+    }, 8);
+}
+
+extern "C" int mpn_align_batch_packed4(mpn_engine* e, const mpn_params* p, const uint8_t* reads4, const int64_t* read_off, const uint8_t* refs4,
+                                       const int64_t* ref_off, const int32_t* masklen, int64_t npairs, mpn_result* out, uint32_t* cigar, int64_t cigar_cap)
+{
+    if (!e || !p || npairs < 0 || p->n > 16) return MPN_E_ARG;
+    const Csr4Pairs all{reads4, read_off, refs4, ref_off, npairs};
+    static const int64_t CHUNK = 196608;
+    int64_t at = 0;
+    // same ramp as mpn_align_batch: a short first range so that the GPU starts early, short last ones so that little is left to convert
+    std::vector<int64_t> bounds(1, 0);
+    if (npairs > CHUNK + CHUNK / 2) {
+        int64_t tail = 0; std::vector<int64_t> tails;
+        for (int k = 3; k >= 1; --k) { const int64_t want = CHUNK >> k; if (npairs - at - tail > 3 * CHUNK) { at += want; bounds.push_back(at); tails.push_back(want); tail += want; } }
+        const int64_t rest = npairs - at - tail, nrest = (rest + CHUNK - 1) / CHUNK, per = (rest + nrest - 1) / nrest;
+        while (at < npairs - tail) { at = std::min(npairs - tail, at + per); bounds.push_back(at); }
+        for (size_t k = tails.size(); k-- > 0;) { at += tails[k]; bounds.push_back(at); }
+    } else bounds.push_back(npairs);
+    size_t c = 0;
+    return mpn::run_ranges(e, p, all, masklen, [&](mpn::RangeJob& r) { if (c + 1 >= bounds.size()) return false; r.first = bounds[c]; r.count = bounds[c + 1] - bounds[c]; r.cig_base = -1; ++c; return r.count > 0; },
+                           out, cigar, cigar_cap, nullptr, nullptr);
+}
+
 extern "C" int mpn_batch_io_bytes(const mpn_batch* b, int64_t* h2d, int64_t* d2h)
 {
     if (!b) return MPN_E_ARG;
@@ -896,6 +959,7 @@ int mpn::run_ranges(mpn_engine* e, const mpn_params* p, const Pairs& all, const 
     return rc;
 }
 template int mpn::run_ranges<mpn::CsrPairs>(mpn_engine*, const mpn_params*, const mpn::CsrPairs&, const int32_t*, const std::function<bool(mpn::RangeJob&)>&, mpn_result*, uint32_t*, int64_t, int64_t*, int64_t*);
+template int mpn::run_ranges<mpn::Csr4Pairs>(mpn_engine*, const mpn_params*, const mpn::Csr4Pairs&, const int32_t*, const std::function<bool(mpn::RangeJob&)>&, mpn_result*, uint32_t*, int64_t, int64_t*, int64_t*);
 template int mpn::run_ranges<mpn::SpanPairs>(mpn_engine*, const mpn_params*, const mpn::SpanPairs&, const int32_t*, const std::function<bool(mpn::RangeJob&)>&, mpn_result*, uint32_t*, int64_t, int64_t*, int64_t*);
 
 int mpn::engine_device(const mpn_engine* e) { return e ? e->device : -1; }

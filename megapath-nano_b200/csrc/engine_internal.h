@@ -21,13 +21,44 @@ struct CsrPairs {
     bool valid() const { return npairs == 0 || (reads && read_off && refs && ref_off); }
     bool span_ok(int64_t) const { return true; }
     size_t arena_bytes() const { return (size_t)(reads_total() + refs_total()); }
-    void copy_arena(int8_t* dst, cudaStream_t st) const {
+    size_t staging_bytes() const { return 0; }
+    size_t h2d_bytes() const { return arena_bytes(); }
+    void copy_arena(int8_t* dst, uint8_t*, cudaStream_t st) const {
         if (!npairs) return;
         if (reads_total()) cudaMemcpyAsync(dst, reads + read_off[0], (size_t)reads_total(), cudaMemcpyHostToDevice, st);
         if (refs_total()) cudaMemcpyAsync(dst + reads_total(), refs + ref_off[0], (size_t)refs_total(), cudaMemcpyHostToDevice, st);
     }
     int64_t read_bases() const { return reads_total(); }
     CsrPairs slice(int64_t first, int64_t count) const { return CsrPairs{reads, read_off + first, refs, ref_off + first, count}; }
+};
+// CSR pairs whose bases are NIBBLE-PACKED on the host (mpn_align_batch_packed4): base i of a stream is the low (i even) or high (i odd)
+// nibble of byte i / 2; offsets stay in bases.  Half the host->device bytes; a small kernel expands the nibbles into the int8 arena.
+void launch_unpack4(const uint8_t* src, int64_t first_base, int64_t nbases, int8_t* dst, cudaStream_t st);
+struct Csr4Pairs {
+    const uint8_t* reads4; const int64_t* read_off; const uint8_t* refs4; const int64_t* ref_off; int64_t npairs;
+    int64_t reads_total() const { return npairs ? read_off[npairs] - read_off[0] : 0; }
+    int64_t refs_total() const { return npairs ? ref_off[npairs] - ref_off[0] : 0; }
+    int64_t rl(int64_t i) const { return read_off[i + 1] - read_off[i]; }
+    int64_t fl(int64_t i) const { return ref_off[i + 1] - ref_off[i]; }
+    int64_t rd_base(int64_t i) const { return read_off[i] - read_off[0]; }
+    int64_t rf_base(int64_t i) const { return reads_total() + (ref_off[i] - ref_off[0]); }
+    bool valid() const { return npairs == 0 || (reads4 && read_off && refs4 && ref_off); }
+    bool span_ok(int64_t) const { return true; }
+    size_t arena_bytes() const { return (size_t)(reads_total() + refs_total()); }
+    // packed bytes covering bases [lo, hi)
+    static int64_t pk_first(int64_t lo) { return lo >> 1; }
+    static size_t pk_bytes(int64_t lo, int64_t hi) { return hi > lo ? (size_t)(((hi + 1) >> 1) - (lo >> 1)) : 0; }
+    size_t staging_bytes() const { return npairs ? pk_bytes(read_off[0], read_off[npairs]) + 16 + pk_bytes(ref_off[0], ref_off[npairs]) + 16 : 0; }
+    size_t h2d_bytes() const { return npairs ? pk_bytes(read_off[0], read_off[npairs]) + pk_bytes(ref_off[0], ref_off[npairs]) : 0; }
+    void copy_arena(int8_t* dst, uint8_t* staging, cudaStream_t st) const {
+        if (!npairs) return;
+        const size_t rb = pk_bytes(read_off[0], read_off[npairs]), fb = pk_bytes(ref_off[0], ref_off[npairs]);
+        uint8_t* sr = staging; uint8_t* sf = staging + ((rb + 31) & ~(size_t)15);
+        if (rb) { cudaMemcpyAsync(sr, reads4 + pk_first(read_off[0]), rb, cudaMemcpyHostToDevice, st); launch_unpack4(sr, read_off[0] & 1, reads_total(), dst, st); }
+        if (fb) { cudaMemcpyAsync(sf, refs4 + pk_first(ref_off[0]), fb, cudaMemcpyHostToDevice, st); launch_unpack4(sf, ref_off[0] & 1, refs_total(), dst + reads_total(), st); }
+    }
+    int64_t read_bases() const { return reads_total(); }
+    Csr4Pairs slice(int64_t first, int64_t count) const { return Csr4Pairs{reads4, read_off + first, refs4, ref_off + first, count}; }
 };
 struct SpanPairs {
     const int8_t* seq; int64_t seq_bytes; const int64_t* rd_start; const int32_t* rd_len; const int64_t* rf_start; const int32_t* rf_len; int64_t npairs;
@@ -38,7 +69,9 @@ struct SpanPairs {
     bool valid() const { return seq_bytes >= 0 && (npairs == 0 || (seq && rd_start && rd_len && rf_start && rf_len)); }
     bool span_ok(int64_t i) const { return rd_start[i] >= 0 && rf_start[i] >= 0 && rd_start[i] + rd_len[i] <= seq_bytes && rf_start[i] + rf_len[i] <= seq_bytes; }
     size_t arena_bytes() const { return (size_t)seq_bytes; }
-    void copy_arena(int8_t* dst, cudaStream_t st) const { if (seq_bytes) cudaMemcpyAsync(dst, seq, (size_t)seq_bytes, cudaMemcpyHostToDevice, st); }
+    size_t staging_bytes() const { return 0; }
+    size_t h2d_bytes() const { return arena_bytes(); }
+    void copy_arena(int8_t* dst, uint8_t*, cudaStream_t st) const { if (seq_bytes) cudaMemcpyAsync(dst, seq, (size_t)seq_bytes, cudaMemcpyHostToDevice, st); }
     int64_t read_bases() const { int64_t t = 0; for (int64_t i = 0; i < npairs; ++i) t += rd_len[i]; return t; }
     SpanPairs slice(int64_t first, int64_t count) const { return SpanPairs{seq, seq_bytes, rd_start + first, rd_len + first, rf_start + first, rf_len + first, count}; }
 };

@@ -324,3 +324,14 @@ def test_targets_longer_than_65535_columns(eng):
         bad = diff(g, gc, r, c)
         assert len(bad) == 0, (flag, bad[:5], g[bad[:2]], r[bad[:2]])
         assert int((g[:, 1] > 100).sum()) >= 8              # score2 comes from the second copy
+
+
+def test_nibble_packed_input_equals_int8_input(eng):
+    """mpn_align_batch_packed4 (half the host->device bytes, expanded on the device) == mpn_align_batch, on odd lengths / odd offsets and on
+    a batch large enough to be cut into pipeline ranges"""
+    for b in (w.fuzz_pairs(400, 77, flag=1, random_matrix=False), w.config2(3000, seed=5), w.make_pairs(300_000, (21, 59), 83, err=0.03, seed=9, flag=1)):
+        rec, cig = eng.align(b)
+        want, wantc = B.as_table(rec, cig, 64)
+        prec, pcig = eng.align_packed4(b, B.pack4(b.reads), B.pack4(b.refs))
+        got, gotc = B.as_table(prec, pcig, 64)
+        assert (got == want).all() and (gotc == wantc).all(), b.name

@@ -45,7 +45,7 @@ def test_pool_equals_single_engine(flag):
         assert (got == want).all() and (gotc == wantc).all(), (devices, np.nonzero((got != want).any(axis=1))[0][:5])
         assert sum(s["pairs"] for s in shares) == b.npairs and sum(s["cells"] for s in shares) == b.cells
         if len(devices) > 1:
-            assert all(s["pairs"] > 0 for s in shares), shares          # every device worker took part
+            assert sum(s["pairs"] > 0 for s in shares) >= 2, shares    # the queue was shared (a small batch has fewer ranges than an 8-GPU box has devices)
 
 
 def test_pool_spans_form():
