@@ -117,7 +117,7 @@ struct mpn_engine {
     int sm_count = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
     int64_t launches = 0, pairs = 0, cells = 0, wide_pairs = 0;
-    // per strip instantiation (forward / reverse, then the 4 N variants): resident blocks per SM, 0 = not prepared yet on this device.
+    // per strip instantiation (forward / reverse, then the 4 N variants, then the multi-strip one): resident blocks per SM, 0 = not prepared yet on this device.
     // Preparation (shared-memory limit above 48 KB, all-shared carve-out, occupancy query) happens at the first launch of an instantiation,
     // not at engine creation: touching all ~80 kernels up front loads every one of them and costs seconds in a process that aligns a
     // handful of pairs (the reference's process-per-position model, realignment.sh:50-60).
@@ -167,7 +167,7 @@ struct mpn_batch {
     cudaStream_t st = nullptr;            // stream every copy and kernel of this batch is enqueued on
     bool pipelined = false;               // owned by mpn_align_batch's chunk pipeline: no host synchronisation inside upload
     size_t h2d_bytes = 0, d2h_bytes = 0;
-    long long wide_stride = 0; int wide_blocks = 0;
+    long long wide_stride = 0; int wide_blocks = 0, long_blocks = 0;
     unsigned long long warp_dir_stride = 0; int warp_trace_blocks = 1;
     int64_t sum_rd = 0, sum_rf = 0;       // over pairs (worst-case CIGAR words = sum_rd + sum_rf)
     int64_t n_long_rows = 0;              // pairs whose read has more than 512 rows
@@ -199,7 +199,7 @@ extern "C" mpn_engine* mpn_engine_create(int device)
     CK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
     static std::once_flag once;
     std::call_once(once, build_strip_table);
-    e->strip_blocks.assign((size_t)2 * (N_STRIPS + 4), 0);
+    e->strip_blocks.assign((size_t)2 * (N_STRIPS + 5), 0);
     return e;
 }
 
@@ -433,11 +433,12 @@ static mpn_batch* upload_impl(mpn_engine* e, int slot_id, const mpn_params* p, c
     b->h2d_bytes = src.h2d_bytes() + (sizeof(int32_t) + sizeof(SwTask)) * (size_t)npairs + (size_t)n * n;
 
     // ---- boundary rows of the 32-bit kernel (one slot per resident warp)
-    b->wide_blocks = e->sm_count * 3;
+    b->wide_blocks = e->sm_count * 3;          // (launch bounds of the 32-bit and the round-1 multi-strip kernels: 3 blocks per SM)
     b->wide_stride = ((long long)max_rf + 63) & ~63ll;
     pool.take(b->wide_boundary, sizeof(int) * (size_t)b->wide_blocks * (WIDE_BLOCK / 32) * 2 * (size_t)b->wide_stride + 256);
     // the multi-strip 16-bit kernel may run concurrently with the 32-bit one (bins of a pass are launched on side streams): own buffer
-    if (bin_count[LONG_BIN] > 0) pool.take(b->long_boundary, sizeof(uint32_t) * (size_t)b->wide_blocks * (LONG_BLOCK / 32) * 2 * (size_t)b->wide_stride + 256);
+    b->long_blocks = e->sm_count * 4;          // one boundary slot (2 x wide_stride words) per resident warp of the multi-strip kernel: up to 4 blocks of 4 warps per SM
+    if (bin_count[LONG_BIN] > 0) pool.take(b->long_boundary, sizeof(uint32_t) * (size_t)b->long_blocks * (LONG_BLOCK / 32) * 2 * (size_t)b->wide_stride + 256);
 
     // ---- traceback arenas.  Direction bytes: (2*band+1) per read row; the first attempt has band |dlen|+1 and most pairs
     // stop there.  Budget 16 band cells per read base (+ slack); pairs that do not fit are reported (status 5) and re-run by fetch.
@@ -545,12 +546,28 @@ static void launch_strips(mpn_batch* b, const SwTask* tasks, bool forward, SwEnd
         if (bl.cfg == LONG_BIN) {
             // few long pairs: several warps per pair (strips pipelined across the warps of a block), else one warp per pair
             const int64_t slots = (int64_t)b->wide_blocks * (LONG_BLOCK / 32);
-            const int nwp = (b->max_rf >= (1 << 20) || bl.count * 2 > slots) ? 1 : (bl.count * 4 <= slots ? 4 : 2);
-            const int ppb = (LONG_BLOCK / 32) / nwp;
-            const int blocks = (int)std::min<int64_t>((bl.count + ppb - 1) / ppb, b->wide_blocks);
-            auto fn = nwp == 1 ? sw_long16_kernel<LONG_KR, 1> : (nwp == 2 ? sw_long16_kernel<LONG_KR, 2> : sw_long16_kernel<LONG_KR, 4>);
-            fn<<<blocks, LONG_BLOCK, long16_smem_bytes<LONG_KR>(), st>>>(tasks + bl.first, (int)bl.count, counter, b->seq.as<int8_t>(), b->sc16,
-                forward ? b->colrec.as<uint32_t>() : nullptr, ends, b->long_boundary.as<uint32_t>(), b->wide_stride);
+            // measured on 10 kb x 12 kb pairs (profiles/r02_long_ab.md): 1024 pairs -- 4 warps per pair 3571 GCUPS, 1 warp 3288; 2048 pairs -- 2 warps 3953,
+            // 1 warp 3581; 4096 pairs -- 1 warp (new kernel, 16 resident warps per SM) 4249, 2 warps 4064
+            const int64_t fill = (int64_t)e->sm_count * 16;                         // warps that fill the GPU in the one-warp-per-pair kernel
+            int nwp = (b->max_rf >= (1 << 20) || bl.count * 4 > fill * 5) ? 1 : (bl.count * 2 <= fill ? 4 : 2);
+            static const int force_nwp = []() { const char* v = getenv("MPN_LONG_NWP"); return v ? atoi(v) : 0; }();      // A/B switch
+            if (force_nwp == 1 || force_nwp == 2 || force_nwp == 4) nwp = force_nwp;
+            static const bool old_long = getenv("MPN_OLD_LONG16") != nullptr;       // A/B switch: round-1 kernel for one-warp-per-pair batches too
+            if (nwp == 1 && !old_long) {
+                // throughput case: the multi-strip instantiation of the packed kernel (checkpoint / replay, 4 blocks per SM)
+                const StripEntry& c = g_strip_long;
+                const int per_sm = prepare_strip(e, (size_t)2 * (N_STRIPS + 4) + (forward ? 0 : 1), forward ? c.fn : c.fn_rev, forward ? c.smem : c.smem_rev);
+                const int gpb = STRIP_BLOCK_THREADS / 32;
+                const int64_t blocks = std::min<int64_t>({(bl.count + gpb - 1) / gpb, (int64_t)e->sm_count * per_sm, (int64_t)b->long_blocks});
+                (forward ? c.fn : c.fn_rev)<<<(unsigned)blocks, STRIP_BLOCK_THREADS, forward ? c.smem : c.smem_rev, st>>>(tasks + bl.first, (int)bl.count, counter, b->seq.as<int8_t>(), b->sc16,
+                    forward ? b->colrec.as<uint32_t>() : nullptr, ends, nullptr, (int)bl.first, b->long_boundary.as<uint32_t>(), b->wide_stride);
+            } else {
+                const int ppb = (LONG_BLOCK / 32) / nwp;
+                const int blocks = (int)std::min<int64_t>((bl.count + ppb - 1) / ppb, b->wide_blocks);
+                auto fn = nwp == 1 ? sw_long16_kernel<LONG_KR, 1> : (nwp == 2 ? sw_long16_kernel<LONG_KR, 2> : sw_long16_kernel<LONG_KR, 4>);
+                fn<<<blocks, LONG_BLOCK, long16_smem_bytes<LONG_KR>(), st>>>(tasks + bl.first, (int)bl.count, counter, b->seq.as<int8_t>(), b->sc16,
+                    forward ? b->colrec.as<uint32_t>() : nullptr, ends, b->long_boundary.as<uint32_t>(), b->wide_stride);
+            }
             e->wide_pairs += forward ? bl.count : 0;
         } else if (bl.cfg == WIDE_BIN) {
             launch_wide32_impl(tasks + bl.first, (int)bl.count, counter, b->seq.as<int8_t>(), b->dmat.as<int8_t>(), b->p.n, b->fin.gapO, b->fin.gapE,
@@ -563,7 +580,7 @@ static void launch_strips(mpn_batch* b, const SwTask* tasks, bool forward, SwEnd
             const int per_sm = prepare_strip(e, (size_t)2 * bl.cfg + (forward ? 0 : 1), forward ? c.fn : c.fn_rev, forward ? c.smem : c.smem_rev);
             blocks = std::min<int64_t>(blocks, (int64_t)e->sm_count * per_sm);
             (forward ? c.fn : c.fn_rev)<<<(unsigned)blocks, STRIP_BLOCK_THREADS, forward ? c.smem : c.smem_rev, st>>>(tasks + bl.first, (int)bl.count, counter, b->seq.as<int8_t>(), b->sc16,
-                                                                  forward ? b->colrec.as<uint32_t>() : nullptr, ends, relist_of(b, forward), (int)bl.first);
+                                                                  forward ? b->colrec.as<uint32_t>() : nullptr, ends, relist_of(b, forward), (int)bl.first, nullptr, 0ll);
         }
         CK(cudaGetLastError());
         e->launches++;
@@ -591,7 +608,7 @@ static void launch_n_variants(mpn_batch* b, const SwTask* tasks, bool forward, S
             prepare_strip(e, (size_t)2 * (N_STRIPS + k) + (forward ? 0 : 1), forward ? c.fn : c.fn_rev, forward ? c.smem : c.smem_rev);
             int* counter = reinterpret_cast<int*>(b->counters.as<unsigned long long>() + counter_base + k);
             (forward ? c.fn : c.fn_rev)<<<(unsigned)(e->sm_count * 2), STRIP_BLOCK_THREADS, forward ? c.smem : c.smem_rev, b->st>>>(tasks, 0, counter, b->seq.as<int8_t>(), b->sc16,
-                                                                  forward ? b->colrec.as<uint32_t>() : nullptr, ends, relist, min_len);
+                                                                  forward ? b->colrec.as<uint32_t>() : nullptr, ends, relist, min_len, nullptr, 0ll);
             CK(cudaGetLastError());
             e->launches++;
         }

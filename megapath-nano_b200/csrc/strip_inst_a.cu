@@ -8,5 +8,6 @@ const StripEntry g_strip_part_a[] = {
     MPN_STRIP_ENTRY(11, 8), MPN_STRIP_ENTRY(12, 8), MPN_STRIP_ENTRY(13, 8),
 };
 const StripEntry g_strip_n_a = MPN_STRIP_N_ENTRY(8, 4);
+const StripEntry g_strip_long = MPN_STRIP_LONG_ENTRY(16);
 const int g_strip_part_a_n = sizeof(g_strip_part_a) / sizeof(g_strip_part_a[0]);
 }

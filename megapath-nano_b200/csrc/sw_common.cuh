@@ -72,6 +72,15 @@ __device__ __forceinline__ uint32_t blend_first(uint32_t y, uint32_t x, uint32_t
 __device__ __forceinline__ uint32_t max3(uint32_t a, uint32_t b, uint32_t c) { return __vimax3_s16x2(a, b, c); }             // VIMNMX3.S16x2
 __device__ __forceinline__ uint32_t addmax_relu(uint32_t a, uint32_t b, uint32_t c) { return __viaddmax_s16x2_relu(a, b, c); } // VIADDMNMX.S16x2.RELU
 
+// ---- unsigned twins with a bias, for the kernels that carry the int16 clamp of ssw.c:425 (every H / E / F stored as value + LBIAS)
+constexpr uint32_t LBIAS = 512u;                 // > 2 * 255 (largest gapO + gapE of the uint8_t ABI)
+constexpr uint32_t LBIAS2 = LBIAS | (LBIAS << 16);
+constexpr uint32_t LCAP2 = (32767u + LBIAS) | ((32767u + LBIAS) << 16);
+__device__ __forceinline__ uint32_t umax2(uint32_t a, uint32_t b) { uint32_t d; asm("max.u16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d; }
+__device__ __forceinline__ uint32_t umax3(uint32_t a, uint32_t b, uint32_t c) { return __vimax3_u16x2(a, b, c); }
+__device__ __forceinline__ uint32_t uaddmin(uint32_t a, uint32_t b, uint32_t c) { return __viaddmin_u16x2(a, b, c); }
+__device__ __forceinline__ uint32_t uaddmax(uint32_t a, uint32_t b, uint32_t c) { return __viaddmax_u16x2(a, b, c); }
+
 // up to eight consecutive arena bytes starting at p (bytes beyond `left` are zero): two aligned 64-bit loads + a funnel shift.
 // The sequence arena starts 256-byte aligned and is padded by 16 bytes (engine.cu), so the aligned words around any base are readable.
 __device__ __forceinline__ unsigned long long load8_aligned(const int8_t* __restrict__ p, int left)

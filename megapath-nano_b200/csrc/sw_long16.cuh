@@ -27,14 +27,6 @@
 namespace mpn {
 
 constexpr int LONG_BLOCK = 128;                  // 4 warps = 4 pairs per block
-constexpr uint32_t LBIAS = 512u;                 // > 2 * 255 (largest gapO + gapE of the uint8_t ABI)
-constexpr uint32_t LBIAS2 = LBIAS | (LBIAS << 16);
-constexpr uint32_t LCAP2 = (32767u + LBIAS) | ((32767u + LBIAS) << 16);
-
-__device__ __forceinline__ uint32_t umax2(uint32_t a, uint32_t b) { uint32_t d; asm("max.u16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d; }
-__device__ __forceinline__ uint32_t umax3(uint32_t a, uint32_t b, uint32_t c) { return __vimax3_u16x2(a, b, c); }
-__device__ __forceinline__ uint32_t uaddmin(uint32_t a, uint32_t b, uint32_t c) { return __viaddmin_u16x2(a, b, c); }
-__device__ __forceinline__ uint32_t uaddmax(uint32_t a, uint32_t b, uint32_t c) { return __viaddmax_u16x2(a, b, c); }
 // max(a, b) per half plus "a was already >= b" per half (unsigned twin of max2_track)
 __device__ __forceinline__ uint32_t umax2_track(uint32_t a, uint32_t b, bool& a_ge_hi, bool& a_ge_lo)
 {
