@@ -680,12 +680,13 @@ extern "C" int mpn_batch_run(mpn_batch* b)
             {
                 const unsigned rows_blocks = (unsigned)std::max<int64_t>(1, std::min<int64_t>((n + ROWS_BLOCK - 1) / ROWS_BLOCK, (int64_t)e->sm_count * 8));
                 int* const nflag = reinterpret_cast<int*>(b->counters.as<unsigned long long>() + 103);
-#define MPN_ROWS_LAUNCH(CLS) sw_band_rows_kernel<CLS><<<rows_blocks, ROWS_BLOCK, 0, st>>>(b->tasks_fwd.as<SwTask>(), b->seq.as<int8_t>(), b->fwdres.as<FwdResult>(), tp, ar, \
+#define MPN_ROWS_LAUNCH(NY, ...) sw_band_rows_kernel<__VA_ARGS__><<<dim3(rows_blocks, NY), ROWS_BLOCK, 0, st>>>(b->seq.as<int8_t>(), tp, ar, \
                     b->finalres.as<FinalResult>(), b->bandrec.as<BandRec>(), b->flaglist.as<int>(), nflag, bq)
-                MPN_ROWS_LAUNCH(0); MPN_ROWS_LAUNCH(1); MPN_ROWS_LAUNCH(2); MPN_ROWS_LAUNCH(3);
+                // a failed attempt re-queues its pair for the doubled band: widths that feed each other go to successive launches
+                MPN_ROWS_LAUNCH(4, 1, 3, 5, 7); MPN_ROWS_LAUNCH(2, 2, 6, 0, 0); MPN_ROWS_LAUNCH(1, 4, 0, 0, 0);
 #undef MPN_ROWS_LAUNCH
                 CK(cudaGetLastError());
-                e->launches += 5;
+                e->launches += 4;
             }
             sw_band_trace_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(b->tasks_fwd.as<SwTask>(), (int)n, b->fwdres.as<FwdResult>(), b->bandrec.as<BandRec>(), ar,
                 b->cig.as<uint32_t>(), b->cig_cap, b->counters.as<unsigned long long>() + 65, b->finalres.as<FinalResult>());

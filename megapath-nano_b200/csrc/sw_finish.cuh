@@ -89,8 +89,17 @@ sw_finish_kernel(const SwTask* __restrict__ fwd_tasks, int ntasks, const SwEnds*
                 const int cmj = (int)(w & 0xffffu), Bj = (int)(w >> 16);
                 if (j < e1) offer(kL, cmj, j);
                 else if (j >= e2) offer(kR, cmj, j);
-                // pad candidates carry at most Bj: skipped unless Bj can still beat (or tie, at a smaller column) what this lane holds
-                if (P > 0 && Bj > 0 && ((e1 > 0 && (uint32_t)Bj >= (kL >> 16)) || (e2 < rf_len && (uint32_t)Bj >= (kR >> 16)))) {
+                // pad candidates: skipped unless one of them can still beat (or tie, at a smaller column) what the warp holds.  Left range: Bj lands
+                // on column j + 1.  Right range: Bj itself if the range starts within the P columns behind j, else only the eroded value, which
+                // has lost gapO + (distance) * gapE by the time it gets there -- so columns far left of the range never qualify.
+                bool may = false;
+                if (P > 0 && Bj > 0) {
+                    may = j + 1 < e1 && (uint32_t)Bj >= (kL >> 16);
+                    int vR = Bj;
+                    if (e2 > j + P) vR = Bj - fp.gapO - (e2 - P - 1 - j) * fp.gapE;
+                    may = may || (e2 < rf_len && vR > 0 && (uint32_t)vR >= (kR >> 16));
+                }
+                if (may) {
                     if (j + 1 < e1) offer(kL, Bj, j + 1);
                     if (j + P + 1 < e1) offer(kL, Bj - fp.gapO, j + P + 1);
                     const int c2 = max(j + 1, e2);

@@ -1,5 +1,3 @@
-for n in 1024 2048 4096; do
-python tools/phase_bench.py $n 4 0 2>&1 | tail -1
-MPN_LONG_NWP=2 python tools/phase_bench.py $n 4 0 2>&1 | tail -1
-done
-MPN_LONG_NWP=4 python tools/phase_bench.py 1024 4 0 2>&1 | tail -1
+python tools/phase_bench.py 1000000 2 2>&1 | tail -1
+python tools/phase_bench.py 150000 2 2>&1 | tail -1
+python -m pytest tests/test_gpu_parity.py tests/test_gpu_realigner.py tests/test_gpu_ssw_cpp.py -x -q 2>&1 | tail -3
