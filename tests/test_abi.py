@@ -124,3 +124,16 @@ def test_fastpass_and_assembler_struct_layouts(tmp_path):
     assert got == [32, 8, 28, 8, 8 + 500 * 8, 8, 40]
     D = importlib.import_module("megapath-nano_b200.debruijn")
     assert ct.sizeof(D.DBGPointer) == got[4] and D.DBGPointer.consensus.offset == got[5]
+
+
+def test_pack4_is_host_code_and_matches_numpy(built):
+    """mpn_pack4 (the host helper of the nibble-packed entry point) needs no GPU: base i -> low / high nibble of byte i // 2"""
+    import numpy as np
+    B = importlib.import_module("megapath-nano_b200.batch")
+    rng = np.random.default_rng(3)
+    for n in (0, 1, 2, 7, 1000, 12345):
+        codes = rng.integers(0, 5, size=n, dtype=np.int8)
+        got = B.pack4(codes)
+        pad = np.concatenate([codes, np.zeros(n % 2, np.int8)]).astype(np.uint8)
+        want = (pad[0::2] | (pad[1::2] << 4)).astype(np.uint8)
+        assert got.dtype == np.uint8 and (got == want).all()
