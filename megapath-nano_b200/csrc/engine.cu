@@ -141,7 +141,7 @@ struct mpn_engine {
     DevBuf fp_text, fp_haps, fp_regions, fp_rstart, fp_rlen, fp_places, fp_score, fp_flag;
     cudaEvent_t fp_ev[2] = {nullptr, nullptr};
     float fp_kernel_ms = 0.f;
-    bool fp_attr_done = false, warptr_attr_done = false;
+    bool fp_attr_done = false;
 };
 
 struct BinLaunch { int cfg; int64_t first; int64_t count; };
@@ -692,10 +692,6 @@ extern "C" int mpn_batch_run(mpn_batch* b)
                 b->cig.as<uint32_t>(), b->cig_cap, b->counters.as<unsigned long long>() + 65, b->finalres.as<FinalResult>());
             CK(cudaGetLastError());
             // wide bands: one warp per flagged pair
-            if (!e->warptr_attr_done) {      // three sets of row buffers per warp: above the 48 KB default
-                CK(cudaFuncSetAttribute(sw_trace_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)warptr_smem_bytes(127)));
-                e->warptr_attr_done = true;
-            }
             sw_trace_warp_kernel<<<b->warp_trace_blocks, 32 * WARPTR_WARPS, warptr_smem_bytes(b->p.n), st>>>(b->tasks_fwd.as<SwTask>(), b->flaglist.as<int>(),
                 reinterpret_cast<int*>(b->counters.as<unsigned long long>() + 103), reinterpret_cast<int*>(b->counters.as<unsigned long long>() + 104), b->seq.as<int8_t>(),
                 b->fwdres.as<FwdResult>(), tp, b->warp_dir.as<uint8_t>(), b->warp_dir_stride, b->cig.as<uint32_t>(), b->cig_cap, b->counters.as<unsigned long long>() + 65, b->finalres.as<FinalResult>(), b->bandrec.as<BandRec>());

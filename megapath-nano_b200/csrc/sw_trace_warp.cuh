@@ -10,11 +10,6 @@
 //     neighbours (ssw.c:596-599), so ties resolve exactly as in the scalar loop;
 //   * direction bytes (layout of sw_trace_wide_kernel) go to a region owned by the warp and reused for every band attempt and
 //     every pair, so ONT-scale pairs (10 kb rows x hundreds of band cells, several doubling attempts) cannot exhaust an arena;
-//   * a warp at a few warps per SM is latency bound (row after row, each a chain of shared-memory round trips and a warp scan), and the
-//     reference's band doubling (ssw.c:555,614-616) makes an ONT-scale pair go through three or four attempts.  Up to WARPTR_SPEC attempts
-//     -- bw, 2 bw, 4 bw -- therefore run SIDE BY SIDE, row by row, each with its own row buffers and its own slice of the direction
-//     region: three independent dependency chains in one instruction stream.  The first attempt (in the reference's order) whose maximum
-//     reaches the score is the one the reference would have stopped at; the others' directions are simply not read.
 //   * the traceback walk (ssw.c:618-697) is done by all lanes in lock-step (same loads, broadcast) while each lane prefetches the
 //     band neighbourhood of one of the next 32 rows, which hides the dependent-load latency of the walk.
 #pragma once
@@ -25,8 +20,7 @@ namespace mpn {
 constexpr int WARPTR_MAXCPL = 17;                       // band cells <= 32 * 17 = 544  (bw <= 271)
 constexpr int WARPTR_CELLS = 32 * WARPTR_MAXCPL;
 constexpr int WARPTR_WARPS = 2;                         // warps per block
-constexpr int WARPTR_SPEC = 3;                          // band attempts of a pair that run side by side (bw, 2 bw, 4 bw)
-inline size_t warptr_smem_bytes(int n) { return (size_t)WARPTR_WARPS * WARPTR_SPEC * 4 * (WARPTR_CELLS + 2) * sizeof(int) + (((size_t)n * n + 15) & ~(size_t)15); }
+inline size_t warptr_smem_bytes(int n) { return (size_t)WARPTR_WARPS * 4 * (WARPTR_CELLS + 2) * sizeof(int) + (((size_t)n * n + 15) & ~(size_t)15); }
 // bytes of direction storage one warp needs for reads up to max_rows rows
 inline size_t warptr_region_bytes(int max_rows) { return (((size_t)WARPTR_CELLS * (size_t)max_rows) + 255) & ~(size_t)255; }
 
@@ -134,17 +128,13 @@ sw_trace_warp_kernel(const SwTask* __restrict__ order, const int* __restrict__ f
     extern __shared__ int wsmem[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     constexpr int ROW = WARPTR_CELLS + 2;               // index 0 = band coordinate 0 (left boundary), cell p lives at p + 1
-    WarpRowCtx cs[WARPTR_SPEC];
-    int8_t* smat = reinterpret_cast<int8_t*>(wsmem + WARPTR_WARPS * WARPTR_SPEC * 4 * ROW);
-#pragma unroll
-    for (int a = 0; a < WARPTR_SPEC; ++a) {
-        WarpRowCtx& c = cs[a];
-        c.Hp = wsmem + (wid * WARPTR_SPEC + a) * 4 * ROW; c.Ep = c.Hp + ROW; c.Hc = c.Ep + ROW; c.Ec = c.Hc + ROW;
-        c.n = tp.n; c.gapO = tp.gapO; c.gapE = tp.gapE; c.gm = min(tp.gapO, tp.gapE); c.lane = lane; c.smat = smat;
-    }
-    for (int q = threadIdx.x; q < tp.n * tp.n; q += blockDim.x) smat[q] = tp.mat[q];
+    WarpRowCtx c;
+    c.Hp = wsmem + wid * 4 * ROW; c.Ep = c.Hp + ROW; c.Hc = c.Ep + ROW; c.Ec = c.Hc + ROW;
+    int8_t* smat = reinterpret_cast<int8_t*>(wsmem + WARPTR_WARPS * 4 * ROW);
+    c.n = tp.n; c.gapO = tp.gapO; c.gapE = tp.gapE; c.gm = min(tp.gapO, tp.gapE); c.lane = lane; c.smat = smat;
+    for (int q = threadIdx.x; q < c.n * c.n; q += blockDim.x) smat[q] = tp.mat[q];
     __syncthreads();
-    uint8_t* const dir0 = dir_base + (unsigned long long)(blockIdx.x * WARPTR_WARPS + wid) * dir_stride;
+    uint8_t* const dir = dir_base + (unsigned long long)(blockIdx.x * WARPTR_WARPS + wid) * dir_stride;
 
     for (;;) {
         int li = 0;
@@ -156,73 +146,34 @@ sw_trace_warp_kernel(const SwTask* __restrict__ order, const int* __restrict__ f
         const FwdResult f = fr[i];
         FinalResult r = out[i];
         const int sub_ref = f.ref_end1 - r.ref_begin1 + 1, sub_read = f.read_end1 - r.read_begin1 + 1, score = f.score1;
-#pragma unroll
-        for (int a = 0; a < WARPTR_SPEC; ++a) {
-            cs[a].ref = seq + tk.rf_base + r.ref_begin1;
-            cs[a].read = seq + tk.rd_base + r.read_begin1;
-            cs[a].sub_ref = sub_ref;
-        }
+        c.ref = seq + tk.rf_base + r.ref_begin1;
+        c.read = seq + tk.rd_base + r.read_begin1;
+        c.sub_ref = sub_ref;
         int bw = recs[i].bw;                            // first band of the doubling sequence that the narrow kernel did not try
         int maxv = 0, width_d = 0;
         bool fail = false;
-        uint8_t* dir = dir0;                            // direction bytes of the attempt that succeeded
         do {
-            // how many attempts of the doubling sequence fit side by side: each needs its band within the kernel's cell limit and its
-            // direction bytes (width x rows) within the warp's region, one slice after the other
-            int nspec = 0;
-            unsigned long long off[WARPTR_SPEC + 1]; off[0] = 0;
-#pragma unroll
-            for (int a = 0; a < WARPTR_SPEC; ++a) {
-                const int wd = 2 * (bw << a) + 1;
-                off[a + 1] = off[a] + (((unsigned long long)wd * (unsigned long long)sub_read + 15ull) & ~15ull);
-                if (nspec == a && wd <= WARPTR_CELLS && off[a + 1] <= dir_stride) nspec = a + 1;
-            }
-            if (nspec == 0) { r.status = 8; fail = true; break; }                // left to the generic kernel
-            int mx[WARPTR_SPEC];
-#pragma unroll
-            for (int a = 0; a < WARPTR_SPEC; ++a) {
-                WarpRowCtx& c = cs[a];
-                c.bw = bw << a; c.width = 2 * c.bw + 3; c.width_d = 2 * c.bw + 1;
-                mx[a] = 0;
-                if (a < nspec) for (int q = lane; q < ROW; q += 32) { c.Hp[q] = 0; c.Ep[q] = 0; c.Hc[q] = 0; c.Ec[q] = 0; }
-            }
+            c.bw = bw; c.width = 2 * bw + 3; c.width_d = width_d = 2 * bw + 1;
+            if (width_d > WARPTR_CELLS || (unsigned long long)width_d * (unsigned long long)sub_read > dir_stride) { r.status = 8; fail = true; break; }   // left to the generic kernel
+            for (int q = lane; q < ROW; q += 32) { c.Hp[q] = 0; c.Ep[q] = 0; c.Hc[q] = 0; c.Ec[q] = 0; }
             __syncwarp();
+            const int cpl = (width_d + 31) >> 5;
             for (int ii = 0; ii < sub_read; ++ii) {
-#pragma unroll
-                for (int a = 0; a < WARPTR_SPEC; ++a) {
-                    if (a < nspec) {
-                        WarpRowCtx& c = cs[a];
-                        uint8_t* line = dir0 + off[a] + (size_t)c.width_d * (size_t)ii;
-                        const int cpl = (c.width_d + 31) >> 5;
-                        int mh;
-                        if (cpl <= 3) mh = warp_band_row<3>(c, ii, line);
-                        else if (cpl <= 5) mh = warp_band_row<5>(c, ii, line);
-                        else if (cpl <= 9) mh = warp_band_row<9>(c, ii, line);
-                        else mh = warp_band_row<WARPTR_MAXCPL>(c, ii, line);
-                        mx[a] = max(mx[a], mh);
-                    }
-                }
+                uint8_t* line = dir + (size_t)width_d * (size_t)ii;
+                int mh;
+                if (cpl <= 3) mh = warp_band_row<3>(c, ii, line);
+                else if (cpl <= 5) mh = warp_band_row<5>(c, ii, line);
+                else if (cpl <= 9) mh = warp_band_row<9>(c, ii, line);
+                else mh = warp_band_row<WARPTR_MAXCPL>(c, ii, line);
+                maxv = max(maxv, mh);
                 __syncwarp();
-#pragma unroll
-                for (int a = 0; a < WARPTR_SPEC; ++a) { WarpRowCtx& c = cs[a]; int* t = c.Hp; c.Hp = c.Hc; c.Hc = t; t = c.Ep; c.Ep = c.Ec; c.Ec = t; }
+                int* t = c.Hp; c.Hp = c.Hc; c.Hc = t; t = c.Ep; c.Ep = c.Ec; c.Ec = t;
             }
-            // the first attempt, in doubling order, whose running maximum reaches the score ends the sequence (ssw.c:614-616: the
-            // reference's `max` is not reset between attempts)
-            int chosen = -1;
 #pragma unroll
-            for (int a = 0; a < WARPTR_SPEC; ++a) {
-                if (a < nspec) {
-#pragma unroll
-                    for (int o2 = 16; o2 >= 1; o2 >>= 1) mx[a] = max(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], o2));
-                    if (chosen < 0) {
-                        maxv = max(maxv, mx[a]);
-                        if (maxv >= score) chosen = a;
-                    }
-                }
-            }
-            if (chosen >= 0) { bw <<= chosen; width_d = 2 * bw + 1; dir = dir0 + off[chosen]; }
-            else bw <<= nspec;                                                    // every attempt of this round failed: go on with the next doubling
+            for (int off = 16; off >= 1; off >>= 1) maxv = max(maxv, __shfl_xor_sync(0xffffffffu, maxv, off));
+            bw *= 2;
         } while (maxv < score);
+        bw /= 2;
         if (fail) { if (lane == 0) out[i] = r; continue; }
         __syncwarp();
         {
