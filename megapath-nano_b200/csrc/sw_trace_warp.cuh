@@ -10,8 +10,8 @@
 //     neighbours (ssw.c:596-599), so ties resolve exactly as in the scalar loop;
 //   * direction bytes (layout of sw_trace_wide_kernel) go to a region owned by the warp and reused for every band attempt and
 //     every pair, so ONT-scale pairs (10 kb rows x hundreds of band cells, several doubling attempts) cannot exhaust an arena;
-//   * the traceback walk (ssw.c:618-697) is done by all lanes in lock-step (same loads, broadcast) while each lane prefetches the
-//     band neighbourhood of one of the next 32 rows, which hides the dependent-load latency of the walk.
+//   * the traceback walk (ssw.c:618-697) is done by all lanes in lock-step from a shared-memory window that the lanes fill together,
+//     one of the next 32 rows each, so that the DRAM latency of the direction bytes is paid once per 32 rows instead of once per step.
 #pragma once
 #include "sw_trace_narrow.cuh"
 
@@ -21,8 +21,9 @@ constexpr int WARPTR_MAXCPL = 17;                       // band cells <= 32 * 17
 constexpr int WARPTR_CELLS = 32 * WARPTR_MAXCPL;
 constexpr int WARPTR_WARPS = 2;                         // warps per block
 inline size_t warptr_smem_bytes(int n) { return (size_t)WARPTR_WARPS * 4 * (WARPTR_CELLS + 2) * sizeof(int) + (((size_t)n * n + 15) & ~(size_t)15); }
-// bytes of direction storage one warp needs for reads up to max_rows rows
-inline size_t warptr_region_bytes(int max_rows) { return (((size_t)WARPTR_CELLS * (size_t)max_rows) + 255) & ~(size_t)255; }
+// bytes of direction storage one warp needs for reads up to max_rows rows, plus room behind them for the CIGAR words of the walk
+// (at most one word per read row and per target column of the sub-rectangle: 3 words per row covers any band the kernel takes)
+inline size_t warptr_region_bytes(int max_rows) { return (((size_t)(WARPTR_CELLS + 12) * (size_t)max_rows) + 4096 + 255) & ~(size_t)255; }
 
 struct WarpRowCtx {
     int* Hp; int* Ep; int* Hc; int* Ec;
@@ -177,55 +178,82 @@ sw_trace_warp_kernel(const SwTask* __restrict__ order, const int* __restrict__ f
         if (fail) { if (lane == 0) out[i] = r; continue; }
         __syncwarp();
         {
-            // ---- traceback (ssw.c:618-697), pass 0 counts, pass 1 writes back to front.  Every lane walks the same path.
+            // ---- traceback (ssw.c:618-697).  Every lane walks the same path.  By now the direction bytes of a long read have left the L2 (a
+            //      batch writes gigabytes of them), so a walk that loads one byte per step waits for DRAM ten thousand times.  Instead the warp
+            //      loads a WINDOW -- for each of the next 32 rows the 48 bytes around the column the path would reach on a pure diagonal, one row
+            //      per lane, all in flight together -- into shared memory (the row buffers of the DP are free now) and walks from there; a cell
+            //      outside its row's window (more than ~16 net indels within 32 rows, or the aliasing of ssw.c's flat index) is read from memory.
+            //      The CIGAR comes out back to front and its length only at the end: the words go to the unused tail of the warp's direction
+            //      region and are copied, reversed, into the arena once the length is known (one walk instead of count + write).
             const long long total = (long long)width_d * sub_read;
+            const long long tail = (total + 15) & ~15ll;
+            uint32_t* const tmp = reinterpret_cast<uint32_t*>(dir + tail);
+            const long long tmp_cap = ((long long)dir_stride - tail) / 4;
+            uint8_t* const win = reinterpret_cast<uint8_t*>(c.Hp < c.Hc ? c.Hp : c.Hc);        // 32 rows x 48 bytes
+            long long* const wbase = reinterpret_cast<long long*>(win + 32 * 48);               // 32 window start indices
             int l = 0; unsigned long long coff = 0; bool bad = false;
-            for (int pass = 0; pass < 2 && !bad; ++pass) {
-                int ti = sub_read - 1, tj = sub_ref - 1, state = 2, run = 0, cnt = 0, op = 0, prev = 0, since = 32;
-                while (ti > 0) {
-                    if (pass == 0 && since >= 16) {             // pull the band neighbourhood of rows ti - 16 - lane towards the SM
-                        const int rr = ti - 16 - lane;
-                        if (rr >= 0) {
-                            const int pc = tj - (ti - rr) - band_x(rr, bw);          // band coordinate if the path stayed on the diagonal
-                            const long long row0 = (long long)width_d * rr;
-                            asm volatile("prefetch.global.L1 [%0];" :: "l"(dir + row0 + min(max(pc - 40, 0), width_d - 1)));
-                            asm volatile("prefetch.global.L1 [%0];" :: "l"(dir + row0 + min(max(pc + 40, 0), width_d - 1)));
-                        }
-                        since = 0;
+            int ti = sub_read - 1, tj = sub_ref - 1, state = 2, run = 0, cnt = 0, op = 0, prev = 0;
+            int top = -1;                                       // the window holds rows top, top - 1, ..., top - 31
+            auto emit = [&](uint32_t word) {
+                if ((long long)cnt >= tmp_cap) bad = true;
+                else if (lane == 0) tmp[cnt] = word;
+                ++cnt;
+            };
+            while (ti > 0 && !bad) {
+                if (top < 0 || ti < top - 31) {
+                    __syncwarp();
+                    top = ti;
+                    const int rr = ti - lane;
+                    long long sb = -1;
+                    if (rr >= 0) {
+                        const int pc = tj - (ti - rr) - band_x(rr, bw);          // band coordinate if the path stays on the diagonal
+                        long long a0 = (long long)width_d * rr + pc - 16;
+                        a0 = a0 < 0 ? 0 : a0;
+                        sb = a0 & ~15ll;
+                        if (sb + 48 > (long long)dir_stride) sb = ((long long)dir_stride - 48) & ~15ll;
+                        const uint4* src = reinterpret_cast<const uint4*>(dir + sb);
+                        uint4* dst = reinterpret_cast<uint4*>(win + lane * 48);
+                        const uint4 v0 = src[0], v1 = src[1], v2 = src[2];
+                        dst[0] = v0; dst[1] = v1; dst[2] = v2;
                     }
-                    const long long idx = (long long)width_d * ti + (tj - band_x(ti, bw));
-                    const int cell = (idx >= 0 && idx < total) ? (int)dir[idx] : 0;
-                    int d;
-                    if (state == 2) d = cell >> 2; else if (state == 0) d = (cell & 1) ? 3 : 2; else d = (cell & 2) ? 5 : 4;
-                    if ((cell >> 2) == 0) d = 0;
-                    const int ti0 = ti;
-                    if (d == 1) { --ti; --tj; state = 2; op = 0; }
-                    else if (d == 2) { --ti; state = 0; op = 1; }
-                    else if (d == 3) { --ti; state = 2; op = 1; }
-                    else if (d == 4) { --tj; state = 1; op = 2; }
-                    else if (d == 5) { --tj; state = 2; op = 2; }
-                    else { r.status = 3; r.cigar_len = 0; bad = true; break; }
-                    since += ti0 - ti;
-                    if (op == prev) ++run;
-                    else {
-                        if (pass && lane == 0) cig[coff + (unsigned)(l - 1 - cnt)] = ((uint32_t)run << 4) | (uint32_t)prev;
-                        ++cnt; prev = op; run = 1;
-                    }
+                    wbase[lane] = sb;
+                    __syncwarp();
                 }
-                if (bad) break;
-                if (op == 0) { if (pass && lane == 0) cig[coff + (unsigned)(l - 1 - cnt)] = ((uint32_t)(run + 1) << 4); ++cnt; }
-                else {
-                    if (pass && lane == 0) { cig[coff + (unsigned)(l - 1 - cnt)] = ((uint32_t)run << 4) | (uint32_t)op; cig[coff + (unsigned)(l - 2 - cnt)] = 1u << 4; }
-                    cnt += 2;
+                const int slot = top - ti;
+                const long long idx = (long long)width_d * ti + (tj - band_x(ti, bw));
+                int cell = 0;
+                if (idx >= 0 && idx < total) {
+                    const long long o = idx - wbase[slot];
+                    cell = (o >= 0 && o < 48) ? (int)win[slot * 48 + (int)o] : (int)dir[idx];
                 }
-                if (!pass) {
-                    l = cnt;
-                    if (lane == 0) coff = atomicAdd(cig_used, (unsigned long long)l);
-                    coff = __shfl_sync(0xffffffffu, coff, 0);
-                    if (coff + (unsigned long long)l > cig_cap) { r.status = 6; bad = true; }
-                }
+                int d;
+                if (state == 2) d = cell >> 2; else if (state == 0) d = (cell & 1) ? 3 : 2; else d = (cell & 2) ? 5 : 4;
+                if ((cell >> 2) == 0) d = 0;
+                if (d == 1) { --ti; --tj; state = 2; op = 0; }
+                else if (d == 2) { --ti; state = 0; op = 1; }
+                else if (d == 3) { --ti; state = 2; op = 1; }
+                else if (d == 4) { --tj; state = 1; op = 2; }
+                else if (d == 5) { --tj; state = 2; op = 2; }
+                else { r.status = 3; r.cigar_len = 0; bad = true; break; }
+                if (op == prev) ++run;
+                else { emit(((uint32_t)run << 4) | (uint32_t)prev); prev = op; run = 1; }
             }
-            if (!bad) { r.status = 0; r.cigar_len = l; r.cigar_off = (int64_t)coff; }
+            if (!bad) {
+                if (op == 0) emit((uint32_t)(run + 1) << 4);
+                else { emit(((uint32_t)run << 4) | (uint32_t)op); emit(1u << 4); }
+            }
+            if (bad && r.status != 3) r.status = 8;             // no room for the words behind the direction bytes: left to the generic kernel
+            if (!bad) {
+                l = cnt;
+                if (lane == 0) coff = atomicAdd(cig_used, (unsigned long long)l);
+                coff = __shfl_sync(0xffffffffu, coff, 0);
+                if (coff + (unsigned long long)l > cig_cap) { r.status = 6; bad = true; }
+            }
+            __syncwarp();
+            if (!bad) {
+                for (int k = lane; k < l; k += 32) cig[coff + (unsigned)k] = tmp[l - 1 - k];
+                r.status = 0; r.cigar_len = l; r.cigar_off = (int64_t)coff;
+            }
             if (lane == 0) out[i] = r;
         }
         __syncwarp();
