@@ -7,6 +7,7 @@
 #include "sw_wide32.cuh"
 #include "sw_long16.cuh"
 #include "sw_finish.cuh"
+#include "sw_revband.cuh"
 #include "sw_trace.cuh"
 #include "sw_trace_narrow.cuh"
 #include "sw_trace_warp.cuh"
@@ -158,7 +159,10 @@ struct mpn_batch {
     Score16 sc16{};
     FinishParams fin{};
     // device
-    DevBuf seq, mask, tasks_fwd, tasks_rev, ends_fwd, ends_rev, colrec, fwdres, finalres, counters, dmat, scratch, cig, wide_boundary, long_boundary, warp_dir, bandrec, flaglist, bandq_items, bandq_meta, relist, pack_stage;
+    DevBuf seq, mask, tasks_fwd, tasks_rev, ends_fwd, ends_rev, colrec, fwdres, finalres, counters, dmat, scratch, cig, wide_boundary, long_boundary, warp_dir, bandrec, flaglist, bandq_items, bandq_meta, relist, pack_stage, revq_items, revq_meta;
+    bool revband = false;                 // reverse passes of the packed bins go through the banded lane-per-pair kernel (sw_revband.cuh)
+    rb::Score rbsc{};
+    int64_t strip_tasks = 0;              // tasks [0, strip_tasks) belong to the packed short-read bins
     size_t seq_reads_bytes = 0, seq_bytes = 0;
     int64_t colrec_words = 0;
     unsigned long long scratch_bytes = 0, cig_cap = 0;
@@ -282,7 +286,7 @@ extern "C" void mpn_batch_free(mpn_batch* b)
     // after run but before a successful fetch, or on an error path).  After a fetch the stream is already idle and this returns at once.
     if (b->st) cudaStreamSynchronize(b->st);
     DevBuf* bufs[] = {&b->seq, &b->mask, &b->tasks_fwd, &b->tasks_rev, &b->ends_fwd, &b->ends_rev,
-                      &b->colrec, &b->fwdres, &b->finalres, &b->counters, &b->dmat, &b->scratch, &b->cig, &b->wide_boundary, &b->long_boundary, &b->warp_dir, &b->bandrec, &b->flaglist, &b->bandq_items, &b->bandq_meta, &b->relist, &b->pack_stage};
+                      &b->colrec, &b->fwdres, &b->finalres, &b->counters, &b->dmat, &b->scratch, &b->cig, &b->wide_boundary, &b->long_boundary, &b->warp_dir, &b->bandrec, &b->flaglist, &b->bandq_items, &b->bandq_meta, &b->relist, &b->pack_stage, &b->revq_items, &b->revq_meta};
     for (DevBuf* d : bufs) b->e->pool.give(*d);
     delete b;
 }
@@ -328,6 +332,28 @@ static mpn_batch* upload_impl(mpn_engine* e, int slot_id, const mpn_params* p, c
     b->fin.have_byte = have_byte; b->fin.have_word = p->score_size == 1 || p->score_size == 2;
     b->fin.gapO = p->gapO & 0xff; b->fin.gapE = p->gapE & 0xff;
     b->fin.flag = p->flag & 0xff; b->fin.filters = p->filters & 0xffff;
+    {   // banded reverse pass (sw_revband_core.h): 5-letter alphabet, one match score > 0 on the diagonal of ACGT, one mismatch score < 0
+        // elsewhere among ACGT, N constant per column (so the N variants of the packed kernel can take what the band refuses), gapO >= gapE >= 1
+        static const bool off = getenv("MPN_NO_REVBAND") != nullptr;         // A/B switch
+        bool ok = !off && n == 5 && b->sc16.ncol_ok && b->fin.gapO >= b->fin.gapE && b->fin.gapE >= 1 && (b->fin.flag != 0);
+        const int mt = ok ? p->mat[0] : 0, mm = ok ? p->mat[1] : 0;
+        ok = ok && mt > 0 && mm < 0;
+        bool n_mm = true;
+        for (int r = 0; ok && r < 5; ++r)
+            for (int c = 0; c < 5; ++c) {
+                const int v = p->mat[r * 5 + c];
+                if (r < 4 && c < 4) ok = ok && v == (r == c ? mt : mm);
+                else n_mm = n_mm && v == mm;
+            }
+        b->revband = ok;
+        if (ok) {
+            const uint32_t m8 = (uint32_t)(uint8_t)(int8_t)mm;
+            b->rbsc.tlo = (uint32_t)(uint8_t)(int8_t)mt | (m8 << 8) | (m8 << 16) | (m8 << 24);
+            b->rbsc.thi = m8 * 0x01010101u;
+            b->rbsc.mgo2 = b->sc16.mgapO2; b->rbsc.mge2 = b->sc16.mgapE2;
+            b->rbsc.mt = mt; b->rbsc.gapO = b->fin.gapO; b->rbsc.gapE = b->fin.gapE; b->rbsc.n_is_mismatch = n_mm ? 1 : 0;
+        }
+    }
 
     // ---- per-pair lengths, binning
     std::vector<int32_t>& bin = e->h_bin;
@@ -406,6 +432,8 @@ static mpn_batch* upload_impl(mpn_engine* e, int slot_id, const mpn_params* p, c
         }
     }
     for (int c = 0; c <= N_STRIPS + 1; ++c) if (bin_count[c] > 0) b->bins.push_back(BinLaunch{c, bin_first[c], bin_count[c]});
+    b->strip_tasks = bin_first[N_STRIPS];
+    if (b->strip_tasks == 0) b->revband = false;
 
     // ---- device buffers + uploads (straight from the caller's buffers: pinned caller memory gives full PCIe rate)
     DevPool& pool = e->pool;
@@ -420,6 +448,7 @@ static mpn_batch* upload_impl(mpn_engine* e, int slot_id, const mpn_params* p, c
     pool.take(b->counters, 512 * sizeof(unsigned long long));   // [0,128) misc (arena cursors at 64/65, task cursors at 100..104), [128,256) forward bins, [256,384) reverse bins
     pool.take(b->dmat, (size_t)n * n + 16);
     pool.take(b->relist, 2 * sizeof(int) * (size_t)(npairs + 2));       // pairs refused by the packed kernel (reads with N): [count, task indices...] per pass
+    if (b->revband) { pool.take(b->revq_items, sizeof(int) * (size_t)REVBAND_CLASSES * (size_t)(b->strip_tasks + 1)); pool.take(b->revq_meta, 16 * sizeof(int)); }
     if (npairs) {
         if (src.staging_bytes()) pool.take(b->pack_stage, src.staging_bytes());
         src.copy_arena(b->seq.as<int8_t>(), b->pack_stage.as<uint8_t>(), st);
@@ -527,7 +556,7 @@ static int prepare_strip(mpn_engine* e, size_t slot, StripFn fn, size_t smem)
     return nb;
 }
 
-static void launch_strips(mpn_batch* b, const SwTask* tasks, bool forward, SwEnds* ends, int counter_base)
+static void launch_strips(mpn_batch* b, const SwTask* tasks, bool forward, SwEnds* ends, int counter_base, bool skip_packed = false)
 {
     mpn_engine* e = b->e;
     cudaStream_t main_st = b->st;
@@ -541,6 +570,7 @@ static void launch_strips(mpn_batch* b, const SwTask* tasks, bool forward, SwEnd
     int turn = 0;
     for (size_t bi = b->bins.size(); bi-- > 0;) {
         const BinLaunch& bl = b->bins[bi];
+        if (skip_packed && bl.cfg < N_STRIPS) continue;          // done by the banded reverse kernels
         cudaStream_t st = fork ? e->aux[turn++ % mpn_engine::NAUX] : main_st;
         int* counter = reinterpret_cast<int*>(b->counters.as<unsigned long long>() + slot++);
         if (bl.cfg == LONG_BIN) {
@@ -593,6 +623,31 @@ static void launch_strips(mpn_batch* b, const SwTask* tasks, bool forward, SwEnd
     }
 }
 
+// reverse passes of the packed bins through the banded kernels: setup (one queue per band class; what does not qualify goes on the
+// reverse list of the N variants, flagged), then one lane-per-pair kernel per class
+static void launch_revband(mpn_batch* b)
+{
+    mpn_engine* e = b->e;
+    cudaStream_t st = b->st;
+    const int nt = (int)b->strip_tasks;
+    CK(cudaMemsetAsync(b->revq_meta.p, 0, 16 * sizeof(int), st));
+    RevBandQueues q{b->revq_items.as<int>(), b->revq_meta.as<int>(), b->revq_meta.as<int>() + 8, nt + 1};
+    int* relist = b->relist.as<int>() + b->npairs + 2;
+    const SwTask* tasks = b->tasks_rev.as<SwTask>();
+    SwEnds* ends = b->ends_rev.as<SwEnds>();
+    sw_revband_setup_kernel<<<(unsigned)((nt + 127) / 128), 128, 0, st>>>(tasks, nt, b->rbsc, q, ends, relist);
+    CK(cudaGetLastError());
+    // persistent grids: a warp takes 32 queue items at a time.  Widest class first (its pairs take longest).
+    const int64_t warps = ((int64_t)nt + 31) / 32, wpb = REVBAND_BLOCK / 32;
+    auto grid = [&](int per_sm) { return (unsigned)std::max<int64_t>(1, std::min<int64_t>((warps + wpb - 1) / wpb, (int64_t)e->sm_count * per_sm)); };
+    sw_revband_kernel<16><<<grid(4), REVBAND_BLOCK, 0, st>>>(tasks, b->seq.as<int8_t>(), b->rbsc, q, ends, relist);
+    sw_revband_kernel<12><<<grid(4), REVBAND_BLOCK, 0, st>>>(tasks, b->seq.as<int8_t>(), b->rbsc, q, ends, relist);
+    sw_revband_kernel<8><<<grid(5), REVBAND_BLOCK, 0, st>>>(tasks, b->seq.as<int8_t>(), b->rbsc, q, ends, relist);
+    sw_revband_kernel<4><<<grid(8), REVBAND_BLOCK, 0, st>>>(tasks, b->seq.as<int8_t>(), b->rbsc, q, ends, relist);
+    CK(cudaGetLastError());
+    e->launches += 5;
+}
+
 // re-run of the listed pairs in the N variants of the packed kernel (one per group width, each takes its length class)
 static void launch_n_variants(mpn_batch* b, const SwTask* tasks, bool forward, SwEnds* ends, int counter_base)
 {
@@ -605,9 +660,11 @@ static void launch_n_variants(mpn_batch* b, const SwTask* tasks, bool forward, S
         const StripEntry& c = *nv[k];
         const int cap = 2 * c.G * c.KR;
         if (b->max_rd > min_len) {
-            prepare_strip(e, (size_t)2 * (N_STRIPS + k) + (forward ? 0 : 1), forward ? c.fn : c.fn_rev, forward ? c.smem : c.smem_rev);
             int* counter = reinterpret_cast<int*>(b->counters.as<unsigned long long>() + counter_base + k);
-            (forward ? c.fn : c.fn_rev)<<<(unsigned)(e->sm_count * 2), STRIP_BLOCK_THREADS, forward ? c.smem : c.smem_rev, b->st>>>(tasks, 0, counter, b->seq.as<int8_t>(), b->sc16,
+            const int per_sm = prepare_strip(e, (size_t)2 * (N_STRIPS + k) + (forward ? 0 : 1), forward ? c.fn : c.fn_rev, forward ? c.smem : c.smem_rev);
+            // (reverse passes in band mode: these kernels take every pair the band refuses, which may be most of a noisy batch -> full grid)
+            const unsigned nblocks = (unsigned)(e->sm_count * ((!forward && b->revband) ? per_sm : std::min(per_sm, 2)));
+            (forward ? c.fn : c.fn_rev)<<<nblocks, STRIP_BLOCK_THREADS, forward ? c.smem : c.smem_rev, b->st>>>(tasks, 0, counter, b->seq.as<int8_t>(), b->sc16,
                                                                   forward ? b->colrec.as<uint32_t>() : nullptr, ends, relist, min_len, nullptr, 0ll);
             CK(cudaGetLastError());
             e->launches++;
@@ -655,7 +712,8 @@ extern "C" int mpn_batch_run(mpn_batch* b)
     if (e->profile) { CK(cudaEventRecord(e->ev[2], st)); e->ev_valid = 3; }
     const bool any_rev = !(b->fin.flag == 0);
     if (any_rev) {
-        launch_strips(b, b->tasks_rev.as<SwTask>(), false, b->ends_rev.as<SwEnds>(), 256);
+        if (b->revband) launch_revband(b);
+        launch_strips(b, b->tasks_rev.as<SwTask>(), false, b->ends_rev.as<SwEnds>(), 256, b->revband);
         launch_n_variants(b, b->tasks_rev.as<SwTask>(), false, b->ends_rev.as<SwEnds>(), 114);
         launch_wide32_impl(b->tasks_rev.as<SwTask>(), (int)n, reinterpret_cast<int*>(b->counters.as<unsigned long long>() + 101),
                            b->seq.as<int8_t>(), b->dmat.as<int8_t>(), b->p.n, b->fin.gapO, b->fin.gapE, nullptr, b->ends_rev.as<SwEnds>(),
