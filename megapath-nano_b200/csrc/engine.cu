@@ -143,6 +143,7 @@ struct mpn_engine {
     cudaEvent_t fp_ev[2] = {nullptr, nullptr};
     float fp_kernel_ms = 0.f;
     bool fp_attr_done = false;
+    int revband_blocks[4] = {0, 0, 0, 0};           // resident blocks per SM of the four banded reverse kernels (0 = not asked yet)
 };
 
 struct BinLaunch { int cfg; int64_t first; int64_t count; };
@@ -640,11 +641,35 @@ static void launch_revband(mpn_batch* b)
     // persistent grids: a warp takes 32 queue items at a time.  Widest class first (its pairs take longest).
     const int64_t warps = ((int64_t)nt + 31) / 32, wpb = REVBAND_BLOCK / 32;
     auto grid = [&](int per_sm) { return (unsigned)std::max<int64_t>(1, std::min<int64_t>((warps + wpb - 1) / wpb, (int64_t)e->sm_count * per_sm)); };
-    sw_revband_kernel<16><<<grid(4), REVBAND_BLOCK, 0, st>>>(tasks, b->seq.as<int8_t>(), b->rbsc, q, ends, relist);
-    sw_revband_kernel<12><<<grid(4), REVBAND_BLOCK, 0, st>>>(tasks, b->seq.as<int8_t>(), b->rbsc, q, ends, relist);
-    sw_revband_kernel<8><<<grid(5), REVBAND_BLOCK, 0, st>>>(tasks, b->seq.as<int8_t>(), b->rbsc, q, ends, relist);
-    sw_revband_kernel<4><<<grid(8), REVBAND_BLOCK, 0, st>>>(tasks, b->seq.as<int8_t>(), b->rbsc, q, ends, relist);
+    // the four classes side by side on the side streams (a class's tail of half-empty SMs is filled by the next one); a batch of the
+    // chunk pipeline stays on its own stream, the other ranges in flight fill its tails
+    static const bool no_fork = getenv("MPN_RB_NOFORK") != nullptr;      // A/B switch
+    const bool fork = !b->pipelined && !no_fork;
+    cudaStream_t s16 = st, s12 = st, s8 = st;
+    if (fork) {
+        CK(cudaEventRecord(e->ev_fork, st));
+        for (int k = 0; k < mpn_engine::NAUX; ++k) CK(cudaStreamWaitEvent(e->aux[k], e->ev_fork, 0));
+        s16 = e->aux[0]; s12 = e->aux[1]; s8 = e->aux[2];
+    }
+    int* occ = e->revband_blocks;
+    if (occ[0] == 0) {
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[0], sw_revband_kernel<4>, REVBAND_BLOCK, 0));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[1], sw_revband_kernel<8>, REVBAND_BLOCK, 0));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[2], sw_revband_kernel<12>, REVBAND_BLOCK, 0));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[3], sw_revband_kernel<16>, REVBAND_BLOCK, 0));
+        for (int k = 0; k < 4; ++k) occ[k] = std::max(1, std::min(occ[k], 8));
+    }
+    sw_revband_kernel<16><<<grid(occ[3]), REVBAND_BLOCK, 0, s16>>>(tasks, b->seq.as<int8_t>(), b->rbsc, q, ends, relist);
+    sw_revband_kernel<12><<<grid(occ[2]), REVBAND_BLOCK, 0, s12>>>(tasks, b->seq.as<int8_t>(), b->rbsc, q, ends, relist);
+    sw_revband_kernel<8><<<grid(occ[1]), REVBAND_BLOCK, 0, s8>>>(tasks, b->seq.as<int8_t>(), b->rbsc, q, ends, relist);
+    sw_revband_kernel<4><<<grid(occ[0]), REVBAND_BLOCK, 0, st>>>(tasks, b->seq.as<int8_t>(), b->rbsc, q, ends, relist);
     CK(cudaGetLastError());
+    if (fork) {
+        for (int k = 0; k < mpn_engine::NAUX; ++k) {
+            CK(cudaEventRecord(e->ev_join[k], e->aux[k]));
+            CK(cudaStreamWaitEvent(st, e->ev_join[k], 0));
+        }
+    }
     e->launches += 5;
 }
 

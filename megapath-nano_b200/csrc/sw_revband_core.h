@@ -217,17 +217,22 @@ MPN_HD int lane(const int8_t* seq, int64_t rd_base, int64_t rf_base, int L, int 
     const int m_end = (L + C) / 2 + 1;                // diagonals 0 .. L + C - 2
     int m_stop = m_end;
     int best = 0x7fffffff;
+    uint64_t ca = 0, cb = 0;
     uint64_t na = chunk(seq, rd_base, ia, L, false, sc.n_is_mismatch, bail);
     uint64_t nb = chunk(seq, rf_base, jb, C, true, sc.n_is_mismatch, bail);
-    for (int m0 = 0; m0 < m_stop && !bail; m0 += 8) {
-        const uint64_t ca = na, cb = nb;
-        ia += 8; jb += 8;
-        na = chunk(seq, rd_base, ia, L, false, sc.n_is_mismatch, bail);       // one octet ahead: nothing below waits for these loads
-        nb = chunk(seq, rf_base, jb, C, true, sc.n_is_mismatch, bail);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            const int m = m0 + q;
-            if (m >= m_stop) break;
+    // one step = two anti-diagonals.  The loop is NOT unrolled: its body is 100-330 instructions per class, and an unrolled-by-8 version
+    // (static byte selectors for the pushes) ran out of instruction cache -- `no_instruction` was the top stall of the three wider classes.
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int m = 0; m < m_stop && !bail; ++m) {
+        if ((m & 7) == 0) {
+            ca = na; cb = nb;
+            ia += 8; jb += 8;
+            na = chunk(seq, rd_base, ia, L, false, sc.n_is_mismatch, bail);       // one octet ahead: nothing below waits for these loads
+            nb = chunk(seq, rf_base, jb, C, true, sc.n_is_mismatch, bail);
+        }
+        {
             uint32_t acc = 0u;
             // ---- even diagonal k = 2m: E side (i, j-1) is the same slot of the odd diagonal before, F side (i-1, j) the slot below
             {
@@ -248,7 +253,8 @@ MPN_HD int lane(const int8_t* seq, int64_t rd_base, int64_t rf_base, int L, int 
                     if (u & 1) acc = rmax3(acc, He[u - 1], h);
                 }
             }
-            push_a(q < 4 ? (uint32_t)ca : (uint32_t)(ca >> 32), q & 3);
+            push_a((uint32_t)ca, 0);
+            ca >>= 8;
             // ---- odd diagonal k = 2m + 1: F side is the same slot of the even diagonal before, E side the slot above
             {
 #pragma unroll
@@ -265,7 +271,8 @@ MPN_HD int lane(const int8_t* seq, int64_t rd_base, int64_t rf_base, int L, int 
                     if (u & 1) acc = rmax3(acc, Ho[u - 1], h);
                 }
             }
-            push_b(q < 4 ? (uint32_t)cb : (uint32_t)(cb >> 32), q & 3);
+            push_b((uint32_t)cb, 0);
+            cb >>= 8;
             // ---- S reached on one of the two diagonals?  (no cell exceeds S, so the maximum equals S iff a cell does)
             const uint32_t x = acc ^ S2;
             if (((x - 0x00010001u) & ~x & 0x80008000u) != 0u) {
