@@ -563,7 +563,8 @@ static void launch_strips(mpn_batch* b, const SwTask* tasks, bool forward, SwEnd
     cudaStream_t main_st = b->st;
     int slot = counter_base;
     // fork: with more than one bin, launches alternate over the side streams (largest strips first) and join back on the batch stream
-    const bool fork = b->bins.size() > 1 && !b->pipelined;
+    static const bool pipe_fork = getenv("MPN_PIPE_FORK") != nullptr;       // A/B switch: side streams for the ranges of the chunk pipeline too
+    const bool fork = b->bins.size() > 1 && (!b->pipelined || pipe_fork);
     if (fork) {
         CK(cudaEventRecord(e->ev_fork, main_st));
         for (int k = 0; k < mpn_engine::NAUX; ++k) CK(cudaStreamWaitEvent(e->aux[k], e->ev_fork, 0));
@@ -644,7 +645,8 @@ static void launch_revband(mpn_batch* b)
     // the four classes side by side on the side streams (a class's tail of half-empty SMs is filled by the next one); a batch of the
     // chunk pipeline stays on its own stream, the other ranges in flight fill its tails
     static const bool no_fork = getenv("MPN_RB_NOFORK") != nullptr;      // A/B switch
-    const bool fork = !b->pipelined && !no_fork;
+    static const bool pipe_fork = getenv("MPN_PIPE_FORK") != nullptr;
+    const bool fork = (!b->pipelined || pipe_fork) && !no_fork;
     cudaStream_t s16 = st, s12 = st, s8 = st;
     if (fork) {
         CK(cudaEventRecord(e->ev_fork, st));
@@ -937,22 +939,38 @@ extern "C" void mpn_pack4(const int8_t* codes, int64_t n, uint8_t* out)
     }, 8);
 }
 
+// Range boundaries of a large batch for the chunk pipeline: equal ranges of about CHUNK pairs, except that the first ones are an eighth, a
+// quarter and a half of that, so the GPU starts after a short upload instead of waiting for a full range to be scheduled and copied, and
+// the last ones shrink the same way, so little is left to copy back and convert after the last kernel ends.
+static int64_t range_chunk_pairs()
+{
+    static const int64_t CHUNK = []() { const char* v = getenv("MPN_CHUNK_PAIRS"); const long long c = v ? atoll(v) : 0; return c >= 1024 ? (int64_t)c : (int64_t)196608; }();
+    return CHUNK;
+}
+static std::vector<int64_t> range_bounds(int64_t npairs)
+{
+    const int64_t CHUNK = range_chunk_pairs();
+    static const int LADDER = []() { const char* v = getenv("MPN_CHUNK_LADDER"); return v ? atoi(v) : 3; }();     // steps of the ramp at either end (A/B on config 2: 2 -> 75.6 ms, 3 -> 74.2 ms, 4 -> 79.9 ms per step)
+    std::vector<int64_t> bounds(1, 0);
+    if (npairs <= CHUNK + CHUNK / 2) { bounds.push_back(npairs); return bounds; }
+    int64_t at = 0, tail = 0;
+    std::vector<int64_t> tail_sizes;
+    for (int k = LADDER; k >= 1; --k) {
+        const int64_t want = CHUNK >> k;
+        if (want >= 4096 && npairs - at - tail > 3 * CHUNK) { at += want; bounds.push_back(at); tail_sizes.push_back(want); tail += want; }
+    }
+    const int64_t rest = npairs - at - tail, nrest = (rest + CHUNK - 1) / CHUNK, per = (rest + nrest - 1) / nrest;
+    while (at < npairs - tail) { at = std::min(npairs - tail, at + per); bounds.push_back(at); }
+    for (size_t k = tail_sizes.size(); k-- > 0;) { at += tail_sizes[k]; bounds.push_back(at); }
+    return bounds;
+}
+
 extern "C" int mpn_align_batch_packed4(mpn_engine* e, const mpn_params* p, const uint8_t* reads4, const int64_t* read_off, const uint8_t* refs4,
                                        const int64_t* ref_off, const int32_t* masklen, int64_t npairs, mpn_result* out, uint32_t* cigar, int64_t cigar_cap)
 {
     if (!e || !p || npairs < 0 || p->n > 16) return MPN_E_ARG;
     const Csr4Pairs all{reads4, read_off, refs4, ref_off, npairs};
-    static const int64_t CHUNK = 196608;
-    int64_t at = 0;
-    // same ramp as mpn_align_batch: a short first range so that the GPU starts early, short last ones so that little is left to convert
-    std::vector<int64_t> bounds(1, 0);
-    if (npairs > CHUNK + CHUNK / 2) {
-        int64_t tail = 0; std::vector<int64_t> tails;
-        for (int k = 3; k >= 1; --k) { const int64_t want = CHUNK >> k; if (npairs - at - tail > 3 * CHUNK) { at += want; bounds.push_back(at); tails.push_back(want); tail += want; } }
-        const int64_t rest = npairs - at - tail, nrest = (rest + CHUNK - 1) / CHUNK, per = (rest + nrest - 1) / nrest;
-        while (at < npairs - tail) { at = std::min(npairs - tail, at + per); bounds.push_back(at); }
-        for (size_t k = tails.size(); k-- > 0;) { at += tails[k]; bounds.push_back(at); }
-    } else bounds.push_back(npairs);
+    const std::vector<int64_t> bounds = range_bounds(npairs);
     size_t c = 0;
     return mpn::run_ranges(e, p, all, masklen, [&](mpn::RangeJob& r) { if (c + 1 >= bounds.size()) return false; r.first = bounds[c]; r.count = bounds[c + 1] - bounds[c]; r.cig_base = -1; ++c; return r.count > 0; },
                            out, cigar, cigar_cap, nullptr, nullptr);
@@ -970,10 +988,10 @@ extern "C" int mpn_align_batch(mpn_engine* e, const mpn_params* p, const int8_t*
                                const int64_t* ref_off, const int32_t* masklen, int64_t npairs, mpn_result* out, uint32_t* cigar, int64_t cigar_cap)
 {
     if (!e || npairs < 0) return MPN_E_ARG;
-    // Small batches: one chunk on the engine stream.  Large batches: chunks of ~192 k pairs alternate between two pipeline slots
-    // (own stream + own pinned staging each), so the H2D copies and host-side scheduling of chunk k+1 overlap the kernels of chunk k
-    // and the D2H of chunk k-1.
-    static const int64_t CHUNK = []() { const char* v = getenv("MPN_CHUNK_PAIRS"); const long long c = v ? atoll(v) : 0; return c >= 1024 ? (int64_t)c : (int64_t)196608; }();
+    // Small batches: one chunk on the engine stream.  Large batches: ranges of ~192 k pairs go through the pipeline slots
+    // (own stream + own pinned staging each), so the H2D copies and host-side scheduling of range k+1 overlap the kernels of range k
+    // and the D2H of range k-1.
+    const int64_t CHUNK = range_chunk_pairs();
     if (npairs <= CHUNK + CHUNK / 2) {
         mpn_batch* b = mpn_batch_upload(e, p, reads, read_off, refs, ref_off, masklen, npairs);
         if (!b) return MPN_E_ARG;
@@ -982,22 +1000,7 @@ extern "C" int mpn_align_batch(mpn_engine* e, const mpn_params* p, const int8_t*
         mpn_batch_free(b);
         return rc;
     }
-    // chunk boundaries: equal chunks of about CHUNK pairs, except that the first two are a quarter and a half of that, so the GPU starts
-    // after a short upload instead of waiting for a full chunk to be scheduled and copied
-    std::vector<int64_t> bounds(1, 0);
-    {
-        // ... and the last ones shrink again, so little is left to copy back and convert after the last kernel ends
-        static const int LADDER = []() { const char* v = getenv("MPN_CHUNK_LADDER"); return v ? atoi(v) : 3; }();     // steps of the ramp at either end (A/B on config 2: 2 -> 75.6 ms, 3 -> 74.2 ms, 4 -> 79.9 ms per step)
-        int64_t at = 0, tail = 0;
-        std::vector<int64_t> tail_sizes;
-        for (int k = LADDER; k >= 1; --k) {
-            const int64_t want = CHUNK >> k;
-            if (want >= 4096 && npairs - at - tail > 3 * CHUNK) { at += want; bounds.push_back(at); tail_sizes.push_back(want); tail += want; }
-        }
-        const int64_t rest = npairs - at - tail, nrest = (rest + CHUNK - 1) / CHUNK, per = (rest + nrest - 1) / nrest;
-        while (at < npairs - tail) { at = std::min(npairs - tail, at + per); bounds.push_back(at); }
-        for (size_t k = tail_sizes.size(); k-- > 0;) { at += tail_sizes[k]; bounds.push_back(at); }
-    }
+    const std::vector<int64_t> bounds = range_bounds(npairs);
     const int64_t nchunks = (int64_t)bounds.size() - 1;
     int64_t c = 0;
     return mpn::run_ranges(e, p, CsrPairs{reads, read_off, refs, ref_off, npairs}, masklen,

@@ -1,3 +1,2 @@
-timeout 600 python -m pytest tests/test_gpu_revband.py -x -q 2>&1 | tail -3
-python bench.py --steps 5 --warmup 3 --no-configs --cpu-sample 20000 > gpurun_out/r02af_fork.json 2> gpurun_out/r02af_fork.err; echo rc=$?
-MPN_RB_NOFORK=1 python bench.py --steps 5 --warmup 3 --no-configs --cpu-sample 20000 > gpurun_out/r02af_nofork.json 2> gpurun_out/r02af_nofork.err; echo rc=$?
+timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+python bench.py --steps 5 --warmup 3 > gpurun_out/r02ai_bench_full.json 2> gpurun_out/r02ai_bench_full.err; echo rc=$?
