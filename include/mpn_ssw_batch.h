@@ -95,6 +95,18 @@ int mpn_align_batch_packed4(mpn_engine* e, const mpn_params* p, const uint8_t* r
 void mpn_pack4(const int8_t* codes, int64_t n, uint8_t* out /* (n + 1) / 2 bytes */);
 
 /*
+ * The same with FOUR bases per byte: base i of a stream sits in bits 2 (i & 3) .. 2 (i & 3) + 1 of reads2[i / 4] (refs2[i / 4]); read_off / ref_off
+ * stay in BASES.  Codes above 3 (N) are stored as 0 and listed per stream in read_exc / ref_exc as (position << 4 | code), sorted by position
+ * (position counted over the whole stream, like the offsets).  A quarter of the host->device bytes of mpn_align_batch: on an 8-GPU box every
+ * rank's batch has to arrive through the same host before its kernels can start.  mpn_pack2 converts int8 codes and returns
+ * the number of exceptions found (call again with a larger array if it exceeds exc_cap).
+ */
+int mpn_align_batch_packed2(mpn_engine* e, const mpn_params* p, const uint8_t* reads2, const int64_t* read_off, const int64_t* read_exc, int64_t n_read_exc,
+                            const uint8_t* refs2, const int64_t* ref_off, const int64_t* ref_exc, int64_t n_ref_exc,
+                            const int32_t* masklen, int64_t npairs, mpn_result* out, uint32_t* cigar, int64_t cigar_cap);
+int64_t mpn_pack2(const int8_t* codes, int64_t n, uint8_t* out /* (n + 3) / 4 bytes */, int64_t* exc, int64_t exc_cap);
+
+/*
  * Same call for pairs that SHARE sequences (one haplotype against many reads, realigner.cpp:351-384): one arena of int8
  * codes plus, per pair, the start and length of its read and of its target inside the arena.  Spans may overlap or repeat;
  * every distinct sequence is uploaded once.

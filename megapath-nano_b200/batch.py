@@ -173,6 +173,41 @@ def pack4(codes):
     return out
 
 
+def pack2(codes):
+    """int8 codes -> (four-per-byte uint8 array, exceptions) for Engine.align_packed2 (mpn_pack2: base i in bits 2 (i & 3) of byte i // 4; codes
+    above 3 are stored as 0 and listed as position << 4 | code, sorted)"""
+    codes = np.ascontiguousarray(codes, dtype=np.int8)
+    out = np.zeros((len(codes) + 3) // 4, dtype=np.uint8)
+    L = lib()
+    L.mpn_pack2.restype = ct.c_int64
+    L.mpn_pack2.argtypes = [ct.c_void_p, ct.c_int64, ct.c_void_p, ct.c_void_p, ct.c_int64]
+    exc = np.zeros(1024, dtype=np.int64)
+    n = L.mpn_pack2(_ptr(codes), len(codes), _ptr(out), _ptr(exc), len(exc))
+    if n > len(exc):
+        exc = np.zeros(n, dtype=np.int64)
+        n = L.mpn_pack2(_ptr(codes), len(codes), _ptr(out), _ptr(exc), len(exc))
+    return out, exc[:n].copy()
+
+
+def _align_packed2(self, b, reads2, read_exc, refs2, ref_exc, cigar_cap=None, out=None, cig=None):
+    """mpn_align_batch_packed2: b carries offsets (in bases), maskLen and scoring as usual; reads2 / refs2 are the four-per-byte streams,
+    read_exc / ref_exc their exception lists (int64 arrays or pinned tensors)."""
+    n = int(b.npairs)
+    if cigar_cap is None:
+        cigar_cap = n * 24 + int(b.read_off[-1]) // 4 + 4096
+    out = np.zeros(n, dtype=RESULT_DTYPE) if out is None else out
+    cig = np.zeros(max(cigar_cap, 1), dtype=np.uint32) if cig is None else cig
+    keep = []
+    p = self._params(b, keep)
+    self.L.mpn_align_batch_packed2.argtypes = [ct.c_void_p, ct.POINTER(MpnParams), ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_int64, ct.c_void_p, ct.c_void_p, ct.c_void_p, ct.c_int64,
+                                               ct.c_void_p, ct.c_int64, ct.c_void_p, ct.c_void_p, ct.c_int64]
+    rc = self.L.mpn_align_batch_packed2(self.h, ct.byref(p), _ptr(reads2), _ptr(b.read_off), _ptr(read_exc) if len(read_exc) else None, len(read_exc),
+                                        _ptr(refs2), _ptr(b.ref_off), _ptr(ref_exc) if len(ref_exc) else None, len(ref_exc), _ptr(b.masklen), n, _ptr(out), _ptr(cig), int(cigar_cap))
+    if rc:
+        raise RuntimeError(f"mpn_align_batch_packed2 -> {rc}")
+    return out, cig
+
+
 def _align_packed4(self, b, reads4, refs4, cigar_cap=None, out=None, cig=None):
     """mpn_align_batch_packed4: b carries offsets (in bases), maskLen and scoring as usual; reads4 / refs4 are the nibble-packed streams."""
     n = int(b.npairs)
@@ -189,6 +224,7 @@ def _align_packed4(self, b, reads4, refs4, cigar_cap=None, out=None, cig=None):
 
 
 Engine.align_packed4 = _align_packed4
+Engine.align_packed2 = _align_packed2
 
 
 class Pool:

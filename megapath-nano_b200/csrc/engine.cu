@@ -134,7 +134,7 @@ struct mpn_engine {
     int64_t ev_runs = 0;                             // completed profiled runs since profiling was switched on
     DevPool pool;
     struct Slot { cudaStream_t st = nullptr; PinBuf pin_tasks, pin_fwd, pin_fin, pin_misc; };
-    static constexpr int NSLOT = 5;                  // slot 0 serves the phased API on the engine stream; 1..4 are the pipeline of mpn_align_batch
+    static constexpr int NSLOT = 9;                  // slot 0 serves the phased API on the engine stream; 1..8 are the pipeline of mpn_align_batch (run_ranges uses the first MPN_PIPE_DEPTH, default 4)
     Slot slot[NSLOT];
     std::vector<int32_t> h_bin;
     std::vector<int64_t> h_order, h_idx, h_cnt;
@@ -939,6 +939,68 @@ extern "C" void mpn_pack4(const int8_t* codes, int64_t n, uint8_t* out)
     }, 8);
 }
 
+// ---- 2-bit packed input (mpn_align_batch_packed2): expand `nbases` 2-bit codes starting at code `first` of src into int8 codes
+__global__ void __launch_bounds__(256) unpack2_kernel(const uint8_t* __restrict__ src, int64_t first, int64_t nbases, int8_t* __restrict__ dst, int mis)
+{
+    // same layout as unpack4_kernel: 16 output bases per thread, interior threads store one aligned 16-byte word; the 16 codes of a thread
+    // lie in 4 or 5 staging bytes (the staging buffer is padded)
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t k0 = t * 16 - mis;
+    if (k0 >= nbases) return;
+    const int64_t ka = k0 < 0 ? 0 : k0;
+    const int64_t n0 = first + ka;                 // index of the first code handled
+    const uint8_t* p = src + (n0 >> 2);
+    unsigned long long v = 0;
+#pragma unroll
+    for (int q = 0; q < 5; ++q) v |= (unsigned long long)p[q] << (8 * q);
+    v >>= 2 * (unsigned)(n0 & 3);
+    uint32_t w[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const uint32_t x = (uint32_t)(v >> (8 * q)) & 0xffu;                 // 4 codes -> 4 bytes
+        w[q] = (x & 0x3u) | ((x & 0xcu) << 6) | ((x & 0x30u) << 12) | ((x & 0xc0u) << 18);
+    }
+    if (k0 >= 0 && k0 + 16 <= nbases) *reinterpret_cast<uint4*>(dst + k0) = make_uint4(w[0], w[1], w[2], w[3]);
+    else {
+        const int cnt = (int)(((k0 + 16 < nbases) ? k0 + 16 : nbases) - ka);
+        for (int q = 0; q < cnt; ++q) dst[ka + q] = (int8_t)((w[q >> 2] >> (8 * (q & 3))) & 0xffu);
+    }
+}
+
+void mpn::launch_unpack2(const uint8_t* src, int64_t first_base, int64_t nbases, int8_t* dst, cudaStream_t st)
+{
+    if (nbases <= 0) return;
+    const int mis = (int)(reinterpret_cast<uintptr_t>(dst) & 15u);
+    const int64_t threads = (nbases + mis + 15) / 16;
+    unpack2_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(src, first_base, nbases, dst, mis);
+}
+
+// codes that do not fit two bits: entry = position << 4 | code, position counted in the caller's stream; base_pos = stream position of dst[0]
+__global__ void __launch_bounds__(256) patch_exceptions_kernel(const int64_t* __restrict__ exc, int64_t n, int64_t base_pos, int8_t* __restrict__ dst)
+{
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) dst[(exc[t] >> 4) - base_pos] = (int8_t)(exc[t] & 15);
+}
+
+void mpn::launch_patch_exceptions(const int64_t* exc_dev, int64_t n, int64_t base_pos, int8_t* dst, cudaStream_t st)
+{
+    if (n <= 0) return;
+    patch_exceptions_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(exc_dev, n, base_pos, dst);
+}
+
+extern "C" int64_t mpn_pack2(const int8_t* codes, int64_t n, uint8_t* out, int64_t* exc, int64_t exc_cap)
+{
+    mpn::parallel_for((n + 3) / 4, 1 << 20, [&](int64_t k) {
+        uint8_t b = 0;
+        for (int q = 0; q < 4; ++q) { const int64_t i = 4 * k + q; if (i < n && (codes[i] & 15) < 4) b |= (uint8_t)((codes[i] & 3) << (2 * q)); }
+        out[k] = b;
+    }, 8);
+    int64_t ne = 0;
+    for (int64_t i = 0; i < n; ++i)
+        if ((codes[i] & 15) >= 4) { if (ne < exc_cap && exc) exc[ne] = (i << 4) | (codes[i] & 15); ++ne; }
+    return ne;          // > exc_cap: call again with a larger array
+}
+
 // Range boundaries of a large batch for the chunk pipeline: equal ranges of about CHUNK pairs, except that the first ones are an eighth, a
 // quarter and a half of that, so the GPU starts after a short upload instead of waiting for a full range to be scheduled and copied, and
 // the last ones shrink the same way, so little is left to copy back and convert after the last kernel ends.
@@ -970,6 +1032,19 @@ extern "C" int mpn_align_batch_packed4(mpn_engine* e, const mpn_params* p, const
 {
     if (!e || !p || npairs < 0 || p->n > 16) return MPN_E_ARG;
     const Csr4Pairs all{reads4, read_off, refs4, ref_off, npairs};
+    const std::vector<int64_t> bounds = range_bounds(npairs);
+    size_t c = 0;
+    return mpn::run_ranges(e, p, all, masklen, [&](mpn::RangeJob& r) { if (c + 1 >= bounds.size()) return false; r.first = bounds[c]; r.count = bounds[c + 1] - bounds[c]; r.cig_base = -1; ++c; return r.count > 0; },
+                           out, cigar, cigar_cap, nullptr, nullptr);
+}
+
+extern "C" int mpn_align_batch_packed2(mpn_engine* e, const mpn_params* p, const uint8_t* reads2, const int64_t* read_off, const int64_t* read_exc, int64_t n_read_exc,
+                                       const uint8_t* refs2, const int64_t* ref_off, const int64_t* ref_exc, int64_t n_ref_exc,
+                                       const int32_t* masklen, int64_t npairs, mpn_result* out, uint32_t* cigar, int64_t cigar_cap)
+{
+    if (!e || !p || npairs < 0 || n_read_exc < 0 || n_ref_exc < 0) return MPN_E_ARG;
+    const Csr2Pairs all{reads2, read_off, refs2, ref_off, npairs, read_exc, n_read_exc, ref_exc, n_ref_exc};
+    if (!all.valid()) return MPN_E_ARG;
     const std::vector<int64_t> bounds = range_bounds(npairs);
     size_t c = 0;
     return mpn::run_ranges(e, p, all, masklen, [&](mpn::RangeJob& r) { if (c + 1 >= bounds.size()) return false; r.first = bounds[c]; r.count = bounds[c + 1] - bounds[c]; r.cig_base = -1; ++c; return r.count > 0; },
@@ -1015,13 +1090,14 @@ int mpn::run_ranges(mpn_engine* e, const mpn_params* p, const Pairs& all, const 
     // ring of in-flight ranges, one pipeline slot each (own stream + own pinned staging).  Several ranges are queued on the GPU at any
     // time, so the persistent grids of range k+1 fill the SMs that the tail of range k leaves idle, and the host work of a range
     // (scheduling, H2D enqueue, D2H + record conversion) hides behind the kernels of the others.  Fetch order = issue order.
-    constexpr int DEPTH = mpn_engine::NSLOT - 1;
+    constexpr int MAXDEPTH = mpn_engine::NSLOT - 1;
+    static const int DEPTH = []() { const char* v = getenv("MPN_PIPE_DEPTH"); const int d = v ? atoi(v) : 4; return d >= 1 && d <= MAXDEPTH ? d : 4; }();
     static const bool timing = getenv("MPN_TIMING") != nullptr;
     auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const double t_begin = now();
     double t_upload = 0, t_run = 0, t_drain = 0, t_first = 0;
-    mpn_batch* inflight[DEPTH] = {};
-    RangeJob job_of[DEPTH];
+    mpn_batch* inflight[MAXDEPTH] = {};
+    RangeJob job_of[MAXDEPTH];
     int64_t cig_cursor = 0, npairs = 0, ncells = 0;
     int rc = 0;
     auto drain = [&](int s) {
@@ -1063,6 +1139,7 @@ int mpn::run_ranges(mpn_engine* e, const mpn_params* p, const Pairs& all, const 
     return rc;
 }
 template int mpn::run_ranges<mpn::CsrPairs>(mpn_engine*, const mpn_params*, const mpn::CsrPairs&, const int32_t*, const std::function<bool(mpn::RangeJob&)>&, mpn_result*, uint32_t*, int64_t, int64_t*, int64_t*);
+template int mpn::run_ranges<mpn::Csr2Pairs>(mpn_engine*, const mpn_params*, const mpn::Csr2Pairs&, const int32_t*, const std::function<bool(mpn::RangeJob&)>&, mpn_result*, uint32_t*, int64_t, int64_t*, int64_t*);
 template int mpn::run_ranges<mpn::Csr4Pairs>(mpn_engine*, const mpn_params*, const mpn::Csr4Pairs&, const int32_t*, const std::function<bool(mpn::RangeJob&)>&, mpn_result*, uint32_t*, int64_t, int64_t*, int64_t*);
 template int mpn::run_ranges<mpn::SpanPairs>(mpn_engine*, const mpn_params*, const mpn::SpanPairs&, const int32_t*, const std::function<bool(mpn::RangeJob&)>&, mpn_result*, uint32_t*, int64_t, int64_t*, int64_t*);
 

@@ -15,10 +15,12 @@ sys.path.insert(0, ROOT)
 VARIANTS = [
     ("default", {}),
     ("timing", {"MPN_TIMING": "1"}),
-    ("pipe_fork", {"MPN_PIPE_FORK": "1"}),
-    ("chunk160k", {"MPN_CHUNK_PAIRS": "163840"}),
-    ("chunk224k", {"MPN_CHUNK_PAIRS": "229376"}),
-    ("no_revband", {"MPN_NO_REVBAND": "1"}),
+    ("depth6", {"MPN_PIPE_DEPTH": "6"}),
+    ("depth8", {"MPN_PIPE_DEPTH": "8"}),
+    ("depth8_chunk96k", {"MPN_PIPE_DEPTH": "8", "MPN_CHUNK_PAIRS": "98304"}),
+    ("depth6_chunk128k", {"MPN_PIPE_DEPTH": "6", "MPN_CHUNK_PAIRS": "131072"}),
+    ("depth3", {"MPN_PIPE_DEPTH": "3"}),
+    ("depth2_chunk384k_ladder4", {"MPN_PIPE_DEPTH": "2", "MPN_CHUNK_PAIRS": "393216", "MPN_CHUNK_LADDER": "4"}),
 ]
 
 

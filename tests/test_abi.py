@@ -137,3 +137,19 @@ def test_pack4_is_host_code_and_matches_numpy(built):
         pad = np.concatenate([codes, np.zeros(n % 2, np.int8)]).astype(np.uint8)
         want = (pad[0::2] | (pad[1::2] << 4)).astype(np.uint8)
         assert got.dtype == np.uint8 and (got == want).all()
+
+
+def test_pack2_is_host_code_and_matches_numpy(built):
+    """mpn_pack2 (the host helper of the 2-bit entry point) needs no GPU: base i -> bits 2 (i & 3) of byte i // 4, codes above 3 as exceptions"""
+    import numpy as np
+    B = importlib.import_module("megapath-nano_b200.batch")
+    rng = np.random.default_rng(4)
+    for n in (0, 1, 3, 4, 9, 1000, 12345):
+        codes = rng.integers(0, 5, size=n, dtype=np.int8)
+        got, exc = B.pack2(codes)
+        pad = np.concatenate([codes, np.zeros((-n) % 4, np.int8)]).astype(np.uint8)
+        pad = np.where(pad > 3, 0, pad).astype(np.uint8)
+        want = (pad[0::4] | (pad[1::4] << 2) | (pad[2::4] << 4) | (pad[3::4] << 6)).astype(np.uint8)
+        assert got.dtype == np.uint8 and (got == want).all()
+        pos = np.nonzero(codes > 3)[0]
+        assert (exc == ((pos.astype(np.int64) << 4) | codes[pos].astype(np.int64))).all()

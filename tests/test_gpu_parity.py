@@ -335,3 +335,17 @@ def test_nibble_packed_input_equals_int8_input(eng):
         prec, pcig = eng.align_packed4(b, B.pack4(b.reads), B.pack4(b.refs))
         got, gotc = B.as_table(prec, pcig, 64)
         assert (got == want).all() and (gotc == wantc).all(), b.name
+
+
+def test_two_bit_packed_input_equals_int8_input(eng):
+    """mpn_align_batch_packed2 (a quarter of the host->device bytes; N codes travel as an exception list) == mpn_align_batch, on odd lengths /
+    odd offsets, with and without N, and on a batch large enough to be cut into pipeline ranges"""
+    for b in (w.fuzz_pairs(400, 78, flag=1, random_matrix=False), w.config2(3000, seed=6), w.make_pairs(5000, (20, 90), 130, err=0.04, seed=10, flag=1, n_frac=0.02),
+              w.make_pairs(300_000, (21, 59), 83, err=0.03, seed=11, flag=1, n_frac=0.001)):
+        rec, cig = eng.align(b)
+        want, wantc = B.as_table(rec, cig, 64)
+        r2, rx = B.pack2(b.reads)
+        f2, fx = B.pack2(b.refs)
+        prec, pcig = eng.align_packed2(b, r2, rx, f2, fx)
+        got, gotc = B.as_table(prec, pcig, 64)
+        assert (got == want).all() and (gotc == wantc).all(), b.name

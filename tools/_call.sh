@@ -1,2 +1,2 @@
-timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
-python bench.py --steps 5 --warmup 3 > gpurun_out/r02ai_bench_full.json 2> gpurun_out/r02ai_bench_full.err; echo rc=$?
+timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -k "packed" 2>&1 | tail -3
+python bench.py --steps 5 --warmup 3 --no-configs --cpu-sample 20000 > gpurun_out/r02ak_bench.json 2> gpurun_out/r02ak_bench.err; echo rc=$?
