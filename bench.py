@@ -10,7 +10,8 @@ against 1 kb haplotypes, flag = 1, maskLen = readLen/2, +4/-6, gapO 8 / gapE 2 (
 (weak scaling, no collective: pairs are independent).  GCUPS counts forward-matrix cells only.
 
   value    : all ranks' cells / max-over-ranks device time of K steps, inputs already resident in HBM (CUDA events on the launch stream)
-  e2e      : the same through the public call Engine.align() with pinned HOST buffers: H2D copies, scheduling, kernels, D2H inside the timed region
+  e2e      : the same through the public call with pinned HOST buffers: H2D copies, scheduling, kernels, D2H inside the timed region.  Three input formats are
+             timed: 2 bits per base (mpn_align_batch_packed2, the headline), 4 bits (mpn_align_batch_packed4), one int8 code per base (mpn_align_batch)
   roofline : integer-ALU / DPX issue roofline of the dominant (forward score) kernel -- 4.5 alu-pipe instructions per 2 cells at
              64 lanes/clk/SM (profiles/r01_ubench_cell_pipes.md) -> 28.44 cells/clk/SM -- plus the HBM figure showing it is non-binding
   parity   : a stratified sample (>= 100 k pairs at full size) of the TIMED batch's records and CIGARs diffed against the compiled, unmodified
