@@ -143,7 +143,7 @@ struct mpn_engine {
     cudaEvent_t fp_ev[2] = {nullptr, nullptr};
     float fp_kernel_ms = 0.f;
     bool fp_attr_done = false;
-    int revband_blocks[4] = {0, 0, 0, 0};           // resident blocks per SM of the four banded reverse kernels (0 = not asked yet)
+    int revband_blocks[5] = {0, 0, 0, 0, 0};           // resident blocks per SM of the four banded reverse kernels (0 = not asked yet)
 };
 
 struct BinLaunch { int cfg; int64_t first; int64_t count; };
@@ -449,7 +449,7 @@ static mpn_batch* upload_impl(mpn_engine* e, int slot_id, const mpn_params* p, c
     pool.take(b->counters, 512 * sizeof(unsigned long long));   // [0,128) misc (arena cursors at 64/65, task cursors at 100..104), [128,256) forward bins, [256,384) reverse bins
     pool.take(b->dmat, (size_t)n * n + 16);
     pool.take(b->relist, 2 * sizeof(int) * (size_t)(npairs + 2));       // pairs refused by the packed kernel (reads with N): [count, task indices...] per pass
-    if (b->revband) { pool.take(b->revq_items, sizeof(int) * (size_t)REVBAND_CLASSES * (size_t)(b->strip_tasks + 1)); pool.take(b->revq_meta, 16 * sizeof(int)); }
+    if (b->revband) { pool.take(b->revq_items, sizeof(int) * (size_t)REVBAND_CLASSES * (size_t)(b->strip_tasks + 1)); pool.take(b->revq_meta, 32 * sizeof(int)); }
     if (npairs) {
         if (src.staging_bytes()) pool.take(b->pack_stage, src.staging_bytes());
         src.copy_arena(b->seq.as<int8_t>(), b->pack_stage.as<uint8_t>(), st);
@@ -632,8 +632,8 @@ static void launch_revband(mpn_batch* b)
     mpn_engine* e = b->e;
     cudaStream_t st = b->st;
     const int nt = (int)b->strip_tasks;
-    CK(cudaMemsetAsync(b->revq_meta.p, 0, 16 * sizeof(int), st));
-    RevBandQueues q{b->revq_items.as<int>(), b->revq_meta.as<int>(), b->revq_meta.as<int>() + 8, nt + 1};
+    CK(cudaMemsetAsync(b->revq_meta.p, 0, 32 * sizeof(int), st));
+    RevBandQueues q{b->revq_items.as<int>(), b->revq_meta.as<int>(), b->revq_meta.as<int>() + 16, nt + 1};
     int* relist = b->relist.as<int>() + b->npairs + 2;
     const SwTask* tasks = b->tasks_rev.as<SwTask>();
     SwEnds* ends = b->ends_rev.as<SwEnds>();
@@ -659,8 +659,10 @@ static void launch_revband(mpn_batch* b)
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[1], sw_revband_kernel<8>, REVBAND_BLOCK, 0));
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[2], sw_revband_kernel<12>, REVBAND_BLOCK, 0));
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[3], sw_revband_kernel<16>, REVBAND_BLOCK, 0));
-        for (int k = 0; k < 4; ++k) occ[k] = std::max(1, std::min(occ[k], 8));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[4], sw_revband_kernel<20>, REVBAND_BLOCK, 0));
+        for (int k = 0; k < 5; ++k) occ[k] = std::max(1, std::min(occ[k], 8));
     }
+    sw_revband_kernel<20><<<grid(occ[4]), REVBAND_BLOCK, 0, s16>>>(tasks, b->seq.as<int8_t>(), b->rbsc, q, ends, relist);
     sw_revband_kernel<16><<<grid(occ[3]), REVBAND_BLOCK, 0, s16>>>(tasks, b->seq.as<int8_t>(), b->rbsc, q, ends, relist);
     sw_revband_kernel<12><<<grid(occ[2]), REVBAND_BLOCK, 0, s12>>>(tasks, b->seq.as<int8_t>(), b->rbsc, q, ends, relist);
     sw_revband_kernel<8><<<grid(occ[1]), REVBAND_BLOCK, 0, s8>>>(tasks, b->seq.as<int8_t>(), b->rbsc, q, ends, relist);
@@ -672,7 +674,7 @@ static void launch_revband(mpn_batch* b)
             CK(cudaStreamWaitEvent(st, e->ev_join[k], 0));
         }
     }
-    e->launches += 5;
+    e->launches += 6;
 }
 
 // re-run of the listed pairs in the N variants of the packed kernel (one per group width, each takes its length class)

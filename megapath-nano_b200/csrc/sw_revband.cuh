@@ -1,7 +1,7 @@
 // Banded reverse pass (sm_100a): begin positions of ssw_align (ssw.c:820-832) for the pairs whose score leaves little room for gaps.
 // The per-lane routine, the band bound and why it is exact are in sw_revband_core.h.  Here: the kernel that sorts the reverse tasks
 // of the packed short-read bins into one queue per band class, and the kernel that walks a queue with one pair per lane.
-// Pairs that do not qualify (band wider than 64 diagonals, an N the score table cannot express) are put on the list the N variants of
+// Pairs that do not qualify (band wider than 80 diagonals, an N the score table cannot express) are put on the list the N variants of
 // sw_strip16_kernel walk, flagged SW_FLAG_NEEDS_WIDE: they get the full-matrix reverse pass.
 #pragma once
 #include "sw_common.cuh"
@@ -9,7 +9,7 @@
 
 namespace mpn {
 
-constexpr int REVBAND_CLASSES = 4;                 // NW = 4, 8, 12, 16 registers per anti-diagonal: bands of up to 16 / 32 / 48 / 64 diagonals
+constexpr int REVBAND_CLASSES = 5;                 // NW = 4, 8, 12, 16, 20 registers per anti-diagonal: bands of up to 16 / 32 / 48 / 64 / 80 diagonals
 constexpr int REVBAND_BLOCK = 128;
 
 struct RevBandQueues {
@@ -25,7 +25,7 @@ sw_revband_setup_kernel(const SwTask* __restrict__ rev_tasks, int ntasks, rb::Sc
 {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = k < ntasks;                  // whole warps stay: the appends are warp-aggregated
-    int dest = -1;                                 // -1 nothing to do, 0..3 band class, 4 full-matrix pass
+    int dest = -1;                                 // -1 nothing to do, 0 .. REVBAND_CLASSES - 1 band class, REVBAND_CLASSES full-matrix pass
     int out = 0;
     if (live) {
         const SwTask tk = rev_tasks[k];

@@ -180,7 +180,7 @@ template <int NW>
 MPN_HD int lane(const int8_t* seq, int64_t rd_base, int64_t rf_base, int L, int C, int S, int h0, const Score& sc, int& col, int& row)
 {
     constexpr int T = 2 * NW, NB = NW / 2;
-    static_assert(NW % 2 == 0 && T % 8 == 0, "slots come in octets");
+    static_assert(NW % 4 == 0, "slots come in octets");
     uint32_t He[NW], Ho[NW], E[NW], F[NW], Ra[NB], Rb[NB];
 #pragma unroll
     for (int u = 0; u < NW; ++u) He[u] = Ho[u] = E[u] = F[u] = 0u;
@@ -305,7 +305,7 @@ MPN_HD int lane(const int8_t* seq, int64_t rd_base, int64_t rf_base, int L, int 
     return 0;
 }
 
-// band of a pair: 0 = not eligible, else NW (4, 8, 12, 16) and h0
+// band of a pair: 0 = not eligible, else NW (4, 8, 12, 16, 20) and h0
 MPN_HD int classify(int L, int C, int S, const Score& sc, int& h0)
 {
     h0 = 0;
@@ -321,6 +321,7 @@ MPN_HD int classify(int L, int C, int S, const Score& sc, int& h0)
     if (W <= 32) return 8;
     if (W <= 48) return 12;
     if (W <= 64) return 16;
+    if (W <= 80) return 20;
     return 0;
 }
 

@@ -24,6 +24,7 @@ extern "C" int revband_host(const int8_t* seq, int64_t rd_base, int64_t rf_base,
         case 8: return lane<8>(seq, rd_base, rf_base, L, C, S, h0, sc, *col, *row);
         case 12: return lane<12>(seq, rd_base, rf_base, L, C, S, h0, sc, *col, *row);
         case 16: return lane<16>(seq, rd_base, rf_base, L, C, S, h0, sc, *col, *row);
+        case 20: return lane<20>(seq, rd_base, rf_base, L, C, S, h0, sc, *col, *row);
         default: return 2;
     }
 }

@@ -63,7 +63,7 @@ def test_short_reads_like_configs1(lib):
 
 
 def test_wider_class_gives_the_same_cell(lib):
-    st = run(lib, w.make_pairs(200, (150, 300), 1000, err=0.02, seed=13, flag=1), force_nw=16)
+    st = run(lib, w.make_pairs(200, (150, 300), 1000, err=0.02, seed=13, flag=1), force_nw=20)
     assert st["bad"] == 0 and st["done"] > 180
 
 
