@@ -58,8 +58,8 @@ sw_revband_setup_kernel(const SwTask* __restrict__ rev_tasks, int ntasks, rb::Sc
 
 // one pair per lane; a warp takes 32 consecutive queue items (queue order is about task order, i.e. read-length bin: similar trip counts)
 template <int NW>
-__global__ void __launch_bounds__(REVBAND_BLOCK)
-sw_revband_kernel(const SwTask* __restrict__ rev_tasks, const int8_t* __restrict__ seq, const rb::Score sc, RevBandQueues q, SwEnds* __restrict__ ends, int* __restrict__ relist)
+__device__ __forceinline__ void revband_body(const SwTask* __restrict__ rev_tasks, const int8_t* __restrict__ seq, const rb::Score& sc, const RevBandQueues& q,
+                                             SwEnds* __restrict__ ends, int* __restrict__ relist)
 {
     constexpr int cls = NW / 4 - 1;
     const int lane = threadIdx.x & 31;
@@ -87,6 +87,27 @@ sw_revband_kernel(const SwTask* __restrict__ rev_tasks, const int8_t* __restrict
             ends[tk.out] = e;
         }
         __syncwarp();
+    }
+}
+
+template <int NW>
+__global__ void __launch_bounds__(REVBAND_BLOCK)
+sw_revband_kernel(const SwTask* __restrict__ rev_tasks, const int8_t* __restrict__ seq, const rb::Score sc, RevBandQueues q, SwEnds* __restrict__ ends, int* __restrict__ relist)
+{
+    revband_body<NW>(rev_tasks, seq, sc, q, ends, relist);
+}
+
+// all classes in one launch (blockIdx.y = 0 is the widest): for the small ranges of the chunk pipeline, where a launch per class would cost
+// five times the latency of one pair's DP and none of them could fill the GPU; every class then runs at the widest one's register budget
+__global__ void __launch_bounds__(REVBAND_BLOCK)
+sw_revband_all_kernel(const SwTask* __restrict__ rev_tasks, const int8_t* __restrict__ seq, const rb::Score sc, RevBandQueues q, SwEnds* __restrict__ ends, int* __restrict__ relist)
+{
+    switch (blockIdx.y) {
+        case 0: revband_body<20>(rev_tasks, seq, sc, q, ends, relist); break;
+        case 1: revband_body<16>(rev_tasks, seq, sc, q, ends, relist); break;
+        case 2: revband_body<12>(rev_tasks, seq, sc, q, ends, relist); break;
+        case 3: revband_body<8>(rev_tasks, seq, sc, q, ends, relist); break;
+        default: revband_body<4>(rev_tasks, seq, sc, q, ends, relist); break;
     }
 }
 

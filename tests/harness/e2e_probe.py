@@ -15,12 +15,11 @@ sys.path.insert(0, ROOT)
 VARIANTS = [
     ("default", {}),
     ("timing", {"MPN_TIMING": "1"}),
+    ("no_pipe_fork", {"MPN_NO_PIPE_FORK": "1"}),
+    ("no_rb_merge", {"MPN_NO_RB_MERGE": "1"}),
+    ("neither", {"MPN_NO_PIPE_FORK": "1", "MPN_NO_RB_MERGE": "1"}),
     ("depth6", {"MPN_PIPE_DEPTH": "6"}),
-    ("depth8", {"MPN_PIPE_DEPTH": "8"}),
-    ("depth8_chunk96k", {"MPN_PIPE_DEPTH": "8", "MPN_CHUNK_PAIRS": "98304"}),
-    ("depth6_chunk128k", {"MPN_PIPE_DEPTH": "6", "MPN_CHUNK_PAIRS": "131072"}),
-    ("depth3", {"MPN_PIPE_DEPTH": "3"}),
-    ("depth2_chunk384k_ladder4", {"MPN_PIPE_DEPTH": "2", "MPN_CHUNK_PAIRS": "393216", "MPN_CHUNK_LADDER": "4"}),
+    ("chunk256k", {"MPN_CHUNK_PAIRS": "262144"}),
 ]
 
 
