@@ -124,9 +124,10 @@ struct mpn_engine {
     // handful of pairs (the reference's process-per-position model, realignment.sh:50-60).
     std::vector<int> strip_blocks;
     bool profile = false;
-    static constexpr int NAUX = 3;                   // side streams: the bins of one score pass run concurrently, so the tail of one launch overlaps the next
-    cudaStream_t aux[NAUX] = {nullptr, nullptr, nullptr};
-    cudaEvent_t ev_fork = nullptr, ev_join[NAUX] = {nullptr, nullptr, nullptr};
+    static constexpr int NAUX = 8;                   // side streams: the bins of one score pass run concurrently, so the tail of one launch overlaps the next
+    int naux = 3;                                    // ... of which the score passes use this many (MPN_NAUX, A/B switch); the band classes use the first three
+    cudaStream_t aux[NAUX] = {};
+    cudaEvent_t ev_fork = nullptr, ev_join[NAUX] = {};
     static constexpr int NEVSET = 16;                // phase events of the last NEVSET runs (mpn_engine_phase_ms_mean averages them)
     cudaEvent_t evs[NEVSET][5] = {};
     cudaEvent_t* ev = evs[0];                        // the set of the run being enqueued
@@ -202,6 +203,7 @@ extern "C" mpn_engine* mpn_engine_create(int device)
         CK(cudaEventCreateWithFlags(&e->ev_join[k], cudaEventDisableTiming));
     }
     CK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+    { const char* v = getenv("MPN_NAUX"); const int n = v ? atoi(v) : 3; e->naux = n >= 1 && n <= mpn_engine::NAUX ? n : 3; }
     static std::once_flag once;
     std::call_once(once, build_strip_table);
     e->strip_blocks.assign((size_t)2 * (N_STRIPS + 5), 0);
@@ -567,13 +569,13 @@ static void launch_strips(mpn_batch* b, const SwTask* tasks, bool forward, SwEnd
     const bool fork = b->bins.size() > 1 && (!b->pipelined || pipe_fork);
     if (fork) {
         CK(cudaEventRecord(e->ev_fork, main_st));
-        for (int k = 0; k < mpn_engine::NAUX; ++k) CK(cudaStreamWaitEvent(e->aux[k], e->ev_fork, 0));
+        for (int k = 0; k < e->naux; ++k) CK(cudaStreamWaitEvent(e->aux[k], e->ev_fork, 0));
     }
     int turn = 0;
     for (size_t bi = b->bins.size(); bi-- > 0;) {
         const BinLaunch& bl = b->bins[bi];
         if (skip_packed && bl.cfg < N_STRIPS) continue;          // done by the banded reverse kernels
-        cudaStream_t st = fork ? e->aux[turn++ % mpn_engine::NAUX] : main_st;
+        cudaStream_t st = fork ? e->aux[turn++ % e->naux] : main_st;
         int* counter = reinterpret_cast<int*>(b->counters.as<unsigned long long>() + slot++);
         if (bl.cfg == LONG_BIN) {
             // few long pairs: several warps per pair (strips pipelined across the warps of a block), else one warp per pair
@@ -618,7 +620,7 @@ static void launch_strips(mpn_batch* b, const SwTask* tasks, bool forward, SwEnd
         e->launches++;
     }
     if (fork) {
-        for (int k = 0; k < mpn_engine::NAUX; ++k) {
+        for (int k = 0; k < e->naux; ++k) {
             CK(cudaEventRecord(e->ev_join[k], e->aux[k]));
             CK(cudaStreamWaitEvent(main_st, e->ev_join[k], 0));
         }
@@ -661,7 +663,7 @@ static void launch_revband(mpn_batch* b)
     cudaStream_t s16 = st, s12 = st, s8 = st;
     if (fork) {
         CK(cudaEventRecord(e->ev_fork, st));
-        for (int k = 0; k < mpn_engine::NAUX; ++k) CK(cudaStreamWaitEvent(e->aux[k], e->ev_fork, 0));
+        for (int k = 0; k < 3; ++k) CK(cudaStreamWaitEvent(e->aux[k], e->ev_fork, 0));
         s16 = e->aux[0]; s12 = e->aux[1]; s8 = e->aux[2];
     }
     int* occ = e->revband_blocks;
@@ -680,7 +682,7 @@ static void launch_revband(mpn_batch* b)
     sw_revband_kernel<4><<<grid(occ[0]), REVBAND_BLOCK, 0, st>>>(tasks, b->seq.as<int8_t>(), b->rbsc, q, ends, relist);
     CK(cudaGetLastError());
     if (fork) {
-        for (int k = 0; k < mpn_engine::NAUX; ++k) {
+        for (int k = 0; k < 3; ++k) {
             CK(cudaEventRecord(e->ev_join[k], e->aux[k]));
             CK(cudaStreamWaitEvent(st, e->ev_join[k], 0));
         }

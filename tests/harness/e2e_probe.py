@@ -14,12 +14,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT)
 VARIANTS = [
     ("default", {}),
-    ("timing", {"MPN_TIMING": "1"}),
+    ("naux5", {"MPN_NAUX": "5"}),
+    ("naux8", {"MPN_NAUX": "8"}),
+    ("naux2", {"MPN_NAUX": "2"}),
+    ("depth6_naux5", {"MPN_PIPE_DEPTH": "6", "MPN_NAUX": "5"}),
+    ("chunk256k_naux5", {"MPN_CHUNK_PAIRS": "262144", "MPN_NAUX": "5"}),
     ("no_pipe_fork", {"MPN_NO_PIPE_FORK": "1"}),
-    ("no_rb_merge", {"MPN_NO_RB_MERGE": "1"}),
-    ("neither", {"MPN_NO_PIPE_FORK": "1", "MPN_NO_RB_MERGE": "1"}),
-    ("depth6", {"MPN_PIPE_DEPTH": "6"}),
-    ("chunk256k", {"MPN_CHUNK_PAIRS": "262144"}),
 ]
 
 
