@@ -1,2 +1,2 @@
-timeout 900 python -m pytest tests/test_gpu_parity.py -x -q 2>&1 | tail -3
-python bench.py --steps 5 --warmup 3 --no-configs --cpu-sample 20000 > gpurun_out/r02am_bench.json 2> gpurun_out/r02am_bench.err; echo rc=$?
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29551 bench.py --gpus 8 --steps 5 --warmup 3 --no-configs > gpurun_out/r02ap_n8.json 2> gpurun_out/r02ap_n8.err; echo rc=$?
+python bench.py --steps 5 --warmup 3 --no-configs > gpurun_out/r02ap_n1.json 2> gpurun_out/r02ap_n1.err; echo rc=$?
