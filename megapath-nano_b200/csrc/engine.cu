@@ -128,6 +128,7 @@ struct mpn_engine {
     int naux = 3;                                    // ... of which the score passes use this many (MPN_NAUX, A/B switch); the band classes use the first three
     cudaStream_t aux[NAUX] = {};
     cudaEvent_t ev_fork = nullptr, ev_join[NAUX] = {};
+    cudaEvent_t ev_arena = nullptr;                  // behind the upload of an arena shared by the ranges of one spans batch
     static constexpr int NEVSET = 16;                // phase events of the last NEVSET runs (mpn_engine_phase_ms_mean averages them)
     cudaEvent_t evs[NEVSET][5] = {};
     cudaEvent_t* ev = evs[0];                        // the set of the run being enqueued
@@ -162,6 +163,7 @@ struct mpn_batch {
     FinishParams fin{};
     // device
     DevBuf seq, mask, tasks_fwd, tasks_rev, ends_fwd, ends_rev, colrec, fwdres, finalres, counters, dmat, scratch, cig, wide_boundary, long_boundary, warp_dir, bandrec, flaglist, bandq_items, bandq_meta, relist, pack_stage, revq_items, revq_meta;
+    bool seq_shared = false;              // `seq` is a device arena shared by the ranges of one caller batch (not ours to free)
     bool revband = false;                 // reverse passes of the packed bins go through the banded lane-per-pair kernel (sw_revband.cuh)
     rb::Score rbsc{};
     int64_t strip_tasks = 0;              // tasks [0, strip_tasks) belong to the packed short-read bins
@@ -203,6 +205,7 @@ extern "C" mpn_engine* mpn_engine_create(int device)
         CK(cudaEventCreateWithFlags(&e->ev_join[k], cudaEventDisableTiming));
     }
     CK(cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&e->ev_arena, cudaEventDisableTiming));
     { const char* v = getenv("MPN_NAUX"); const int n = v ? atoi(v) : 3; e->naux = n >= 1 && n <= mpn_engine::NAUX ? n : 3; }
     static std::once_flag once;
     std::call_once(once, build_strip_table);
@@ -216,7 +219,7 @@ extern "C" void mpn_engine_destroy(mpn_engine* e)
     cudaSetDevice(e->device);
     cudaStreamDestroy(e->own_stream);
     for (int k = 0; k < mpn_engine::NAUX; ++k) { cudaStreamDestroy(e->aux[k]); cudaEventDestroy(e->ev_join[k]); }
-    cudaEventDestroy(e->ev_fork);
+    cudaEventDestroy(e->ev_fork); cudaEventDestroy(e->ev_arena);
     for (DevBuf* d : {&e->fp_text, &e->fp_haps, &e->fp_regions, &e->fp_rstart, &e->fp_rlen, &e->fp_places, &e->fp_score, &e->fp_flag}) e->pool.give(*d);
     if (e->fp_attr_done) { cudaEventDestroy(e->fp_ev[0]); cudaEventDestroy(e->fp_ev[1]); }
     e->pool.clear();
@@ -290,6 +293,7 @@ extern "C" void mpn_batch_free(mpn_batch* b)
     if (b->st) cudaStreamSynchronize(b->st);
     DevBuf* bufs[] = {&b->seq, &b->mask, &b->tasks_fwd, &b->tasks_rev, &b->ends_fwd, &b->ends_rev,
                       &b->colrec, &b->fwdres, &b->finalres, &b->counters, &b->dmat, &b->scratch, &b->cig, &b->wide_boundary, &b->long_boundary, &b->warp_dir, &b->bandrec, &b->flaglist, &b->bandq_items, &b->bandq_meta, &b->relist, &b->pack_stage, &b->revq_items, &b->revq_meta};
+    if (b->seq_shared) { b->seq.p = nullptr; b->seq.cap = 0; }          // the arena belongs to the caller of run_ranges
     for (DevBuf* d : bufs) b->e->pool.give(*d);
     delete b;
 }
@@ -442,7 +446,8 @@ static mpn_batch* upload_impl(mpn_engine* e, int slot_id, const mpn_params* p, c
     DevPool& pool = e->pool;
     const size_t reads_bytes = (size_t)src.read_bases();          // bases the traceback arenas are budgeted on
     b->seq_reads_bytes = reads_bytes; b->seq_bytes = src.arena_bytes();
-    pool.take(b->seq, b->seq_bytes + 16);
+    if (src.shared_arena()) { b->seq.p = src.shared_arena(); b->seq.cap = 0; b->seq_shared = true; }
+    else pool.take(b->seq, b->seq_bytes + 16);
     pool.take(b->mask, sizeof(int32_t) * (size_t)(npairs + 1));
     pool.take(b->tasks_fwd, sizeof(SwTask) * (size_t)(npairs + 1)); pool.take(b->tasks_rev, sizeof(SwTask) * (size_t)(npairs + 1));
     pool.take(b->ends_fwd, sizeof(SwEnds) * (size_t)(npairs + 1)); pool.take(b->ends_rev, sizeof(SwEnds) * (size_t)(npairs + 1));
@@ -454,7 +459,8 @@ static mpn_batch* upload_impl(mpn_engine* e, int slot_id, const mpn_params* p, c
     if (b->revband) { pool.take(b->revq_items, sizeof(int) * (size_t)REVBAND_CLASSES * (size_t)(b->strip_tasks + 1)); pool.take(b->revq_meta, 32 * sizeof(int)); }
     if (npairs) {
         if (src.staging_bytes()) pool.take(b->pack_stage, src.staging_bytes());
-        src.copy_arena(b->seq.as<int8_t>(), b->pack_stage.as<uint8_t>(), st);
+        if (b->seq_shared) { if (src.shared_ready()) CK(cudaStreamWaitEvent(st, src.shared_ready(), 0)); }
+        else src.copy_arena(b->seq.as<int8_t>(), b->pack_stage.as<uint8_t>(), st);
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(b->mask.p, masklen, sizeof(int32_t) * npairs, cudaMemcpyHostToDevice, st));
         CK(cudaMemcpyAsync(b->tasks_fwd.p, h_tasks, sizeof(SwTask) * npairs, cudaMemcpyHostToDevice, st));
@@ -514,6 +520,9 @@ extern "C" mpn_batch* mpn_batch_upload_spans(mpn_engine* e, const mpn_params* p,
     return upload_impl(e, 0, p, SpanPairs{seq, seq_bytes, rd_start, rd_len, rf_start, rf_len, npairs}, masklen, npairs);
 }
 
+static int64_t range_chunk_pairs();
+static std::vector<int64_t> range_bounds(int64_t npairs);
+
 extern "C" int mpn_align_batch_spans(mpn_engine* e, const mpn_params* p, const int8_t* seq, int64_t seq_bytes, const int64_t* rd_start, const int32_t* rd_len,
                                      const int64_t* rf_start, const int32_t* rf_len, const int32_t* masklen, int64_t npairs,
                                      mpn_result* out, uint32_t* cigar, int64_t cigar_cap)
@@ -521,6 +530,27 @@ extern "C" int mpn_align_batch_spans(mpn_engine* e, const mpn_params* p, const i
     if (!e || npairs < 0) return MPN_E_ARG;
     static const bool timing = getenv("MPN_TIMING") != nullptr;
     auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    static const bool no_pipe = getenv("MPN_NO_SPANS_PIPE") != nullptr;       // A/B switch
+    const int64_t CHUNK = range_chunk_pairs();
+    if (npairs > CHUNK + CHUNK / 2 && !no_pipe && seq_bytes > 0) {
+        // large batch (the realigner's regions x haplotypes x reads): the arena goes to the device once, the pairs through the chunk pipeline,
+        // so scheduling, kernels, D2H and record conversion of different ranges overlap
+        SpanPairs all{seq, seq_bytes, rd_start, rd_len, rf_start, rf_len, npairs};
+        if (!p || !all.valid()) return MPN_E_ARG;
+        CK(cudaSetDevice(e->device));
+        DevBuf arena;
+        e->pool.take(arena, (size_t)seq_bytes + 16);
+        CK(cudaMemcpyAsync(arena.p, seq, (size_t)seq_bytes, cudaMemcpyHostToDevice, e->stream));
+        CK(cudaEventRecord(e->ev_arena, e->stream));
+        all.dev_arena = arena.as<int8_t>(); all.ready = e->ev_arena;
+        const std::vector<int64_t> bounds = range_bounds(npairs);
+        size_t c = 0;
+        const int rc = mpn::run_ranges(e, p, all, masklen, [&](mpn::RangeJob& r) { if (c + 1 >= bounds.size()) return false; r.first = bounds[c]; r.count = bounds[c + 1] - bounds[c]; r.cig_base = -1; ++c; return r.count > 0; },
+                                       out, cigar, cigar_cap, nullptr, nullptr);
+        CK(cudaStreamSynchronize(e->stream));
+        e->pool.give(arena);
+        return rc;
+    }
     const double t0 = now();
     mpn_batch* b = mpn_batch_upload_spans(e, p, seq, seq_bytes, rd_start, rd_len, rf_start, rf_len, masklen, npairs);
     if (!b) return MPN_E_ARG;

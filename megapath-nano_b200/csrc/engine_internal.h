@@ -29,6 +29,8 @@ struct CsrPairs {
         if (refs_total()) cudaMemcpyAsync(dst + reads_total(), refs + ref_off[0], (size_t)refs_total(), cudaMemcpyHostToDevice, st);
     }
     int64_t read_bases() const { return reads_total(); }
+    int8_t* shared_arena() const { return nullptr; }
+    cudaEvent_t shared_ready() const { return nullptr; }
     CsrPairs slice(int64_t first, int64_t count) const { return CsrPairs{reads, read_off + first, refs, ref_off + first, count}; }
 };
 // CSR pairs whose bases are NIBBLE-PACKED on the host (mpn_align_batch_packed4): base i of a stream is the low (i even) or high (i odd)
@@ -58,6 +60,8 @@ struct Csr4Pairs {
         if (fb) { cudaMemcpyAsync(sf, refs4 + pk_first(ref_off[0]), fb, cudaMemcpyHostToDevice, st); launch_unpack4(sf, ref_off[0] & 1, refs_total(), dst + reads_total(), st); }
     }
     int64_t read_bases() const { return reads_total(); }
+    int8_t* shared_arena() const { return nullptr; }
+    cudaEvent_t shared_ready() const { return nullptr; }
     Csr4Pairs slice(int64_t first, int64_t count) const { return Csr4Pairs{reads4, read_off + first, refs4, ref_off + first, count}; }
 };
 // CSR pairs whose bases are packed FOUR PER BYTE (mpn_align_batch_packed2): base i of a stream is bits 2 (i & 3) .. 2 (i & 3) + 1 of byte i / 4.
@@ -110,10 +114,16 @@ struct Csr2Pairs {
         if (b > a) { cudaMemcpyAsync(se, ref_exc + a, (size_t)(b - a) * sizeof(int64_t), cudaMemcpyHostToDevice, st); launch_patch_exceptions(se, b - a, ref_off[0], dst + reads_total(), st); }
     }
     int64_t read_bases() const { return reads_total(); }
+    int8_t* shared_arena() const { return nullptr; }
+    cudaEvent_t shared_ready() const { return nullptr; }
     Csr2Pairs slice(int64_t first, int64_t count) const { return Csr2Pairs{reads2, read_off + first, refs2, ref_off + first, count, read_exc, n_read_exc, ref_exc, n_ref_exc}; }
 };
 struct SpanPairs {
     const int8_t* seq; int64_t seq_bytes; const int64_t* rd_start; const int32_t* rd_len; const int64_t* rf_start; const int32_t* rf_len; int64_t npairs;
+    // ranges of one caller batch share ONE device copy of the arena (uploaded by the caller of run_ranges, `ready` recorded behind the copy)
+    int8_t* dev_arena = nullptr; cudaEvent_t ready = nullptr;
+    int8_t* shared_arena() const { return dev_arena; }
+    cudaEvent_t shared_ready() const { return ready; }
     int64_t rl(int64_t i) const { return rd_len[i]; }
     int64_t fl(int64_t i) const { return rf_len[i]; }
     int64_t rd_base(int64_t i) const { return rd_start[i]; }
@@ -122,10 +132,10 @@ struct SpanPairs {
     bool span_ok(int64_t i) const { return rd_start[i] >= 0 && rf_start[i] >= 0 && rd_start[i] + rd_len[i] <= seq_bytes && rf_start[i] + rf_len[i] <= seq_bytes; }
     size_t arena_bytes() const { return (size_t)seq_bytes; }
     size_t staging_bytes() const { return 0; }
-    size_t h2d_bytes() const { return arena_bytes(); }
+    size_t h2d_bytes() const { return dev_arena ? 0 : arena_bytes(); }
     void copy_arena(int8_t* dst, uint8_t*, cudaStream_t st) const { if (seq_bytes) cudaMemcpyAsync(dst, seq, (size_t)seq_bytes, cudaMemcpyHostToDevice, st); }
     int64_t read_bases() const { int64_t t = 0; for (int64_t i = 0; i < npairs; ++i) t += rd_len[i]; return t; }
-    SpanPairs slice(int64_t first, int64_t count) const { return SpanPairs{seq, seq_bytes, rd_start + first, rd_len + first, rf_start + first, rf_len + first, count}; }
+    SpanPairs slice(int64_t first, int64_t count) const { return SpanPairs{seq, seq_bytes, rd_start + first, rd_len + first, rf_start + first, rf_len + first, count, dev_arena, ready}; }
 };
 
 // A contiguous run of pairs of a caller's batch, and where its CIGAR words go in the caller's arena.

@@ -349,3 +349,15 @@ def test_two_bit_packed_input_equals_int8_input(eng):
         prec, pcig = eng.align_packed2(b, r2, rx, f2, fx)
         got, gotc = B.as_table(prec, pcig, 64)
         assert (got == want).all() and (gotc == wantc).all(), b.name
+
+
+def test_large_spans_batch_goes_through_the_chunk_pipeline(eng):
+    """mpn_align_batch_spans with more pairs than one pipeline range: arena uploaded once, pairs cut into ranges -- same records as the CSR call"""
+    b = w.make_pairs(320_000, (21, 59), 83, err=0.03, seed=12, flag=1)
+    rec, cig = eng.align(b)
+    want, wantc = B.as_table(rec, cig, 64)
+    arena = np.concatenate([b.reads, b.refs])
+    rd_start = b.read_off[:-1]; rf_start = len(b.reads) + b.ref_off[:-1]
+    srec, scig = eng.align_spans(b, arena, rd_start, b.read_len.astype(np.int32), rf_start, b.ref_len.astype(np.int32), b.masklen)
+    got, gotc = B.as_table(srec, scig, 64)
+    assert (got == want).all() and (gotc == wantc).all()
