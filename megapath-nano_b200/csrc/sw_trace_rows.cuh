@@ -11,6 +11,7 @@
 //                            below the score, ssw.c:614-616) re-queues the pair in the queue of the doubled band, which is launched later.
 // Band-coordinate quirks (`edge` zeroing, ssw.c:580) and tie rules as in sw_trace_warp.cuh; direction words as sw_band_trace_kernel reads them.
 #pragma once
+#include <type_traits>
 #include "sw_trace_narrow.cuh"
 
 namespace mpn {
@@ -242,7 +243,8 @@ __device__ __forceinline__ void band_rows_body(const unsigned long long* __restr
         //      p + 2; slot 2 BW + 2 (above the last cell: outside the previous row's band) is never written and reads 0 -- which is also what
         //      ssw.c:580 zeroes there (sub_ref >= 2 BW + 2, see the setup kernel).  Cells right of the matrix (p > lim) do not exist: they are
         //      stored as 0 and leave no direction bits.  A finished lane runs with lim = -1.
-        auto band_row = [&](const int ii) {
+        auto band_row = [&](const int ii, auto clip_tag) {
+            constexpr bool CLIP = decltype(clip_tag)::value;       // false: every lane of the warp has all W cells inside its matrix (no per-cell test)
             win_lo = (win_lo >> 8) | (win_hi << 56);
             win_hi = (win_hi >> 8) | (tq_cur << 56);
             tq_cur >>= 8;
@@ -257,7 +259,7 @@ __device__ __forceinline__ void band_rows_body(const unsigned long long* __restr
             int hleft = 0, fv = 0, hdg = H[1];
 #pragma unroll
             for (int p = 0; p < W; ++p) {
-                const bool valid = p <= lim;
+                const bool valid = !CLIP || p <= lim;
                 const int hup = H[p + 2], eup = E[p + 2];
                 const uint32_t code = (uint32_t)((p < 8 ? win_lo >> (8 * p) : win_hi >> (8 * (p - 8)))) & 7u;
                 const int sc = (int)prmt(rs_lo, rs_hi, code * 0x1111u + 0x8880u);              // byte `code` of the 8 scores, sign-extended
@@ -279,12 +281,17 @@ __device__ __forceinline__ void band_rows_body(const unsigned long long* __restr
                 if (p < 8) dlo |= bits << (4 * p); else dhi |= bits << (4 * (p - 8));
                 hleft = hv;
             }
-            if (ii < rows) dirrow[ii] = ((unsigned long long)dhi << 32) | dlo;
+            if (!CLIP || ii < rows) dirrow[ii] = ((unsigned long long)dhi << 32) | dlo;
         };
 
         const int head = min(BW + 1, rows_max);
         for (int ii = 0; ii < head; ++ii) if (ii < rows) general_row(ii);
-        for (int ii = head; ii < rows_max; ++ii) band_row(ii);
+        for (int ii = head; ii < rows_max; ++ii) {
+            // most rows: every lane still has rows left and its band lies inside the matrix -> the row code without the clipping tests
+            const bool inside = ii < rows && sub_ref - 1 - (ii - BW) >= W - 1;
+            if (__all_sync(0xffffffffu, inside)) band_row(ii, std::false_type{});
+            else band_row(ii, std::true_type{});
+        }
 
         if (run) {
             if (maxv >= score) {                                                              // ssw.c:614-615
