@@ -145,7 +145,7 @@ struct mpn_engine {
     cudaEvent_t fp_ev[2] = {nullptr, nullptr};
     float fp_kernel_ms = 0.f;
     bool fp_attr_done = false;
-    int revband_blocks[5] = {0, 0, 0, 0, 0};           // resident blocks per SM of the four banded reverse kernels (0 = not asked yet)
+    int revband_blocks[5] = {0, 0, 0, 0, 0};           // resident blocks per SM of the banded reverse kernels, one per class (0 = not asked yet)
 };
 
 struct BinLaunch { int cfg; int64_t first; int64_t count; };
@@ -609,7 +609,6 @@ static void launch_strips(mpn_batch* b, const SwTask* tasks, bool forward, SwEnd
         int* counter = reinterpret_cast<int*>(b->counters.as<unsigned long long>() + slot++);
         if (bl.cfg == LONG_BIN) {
             // few long pairs: several warps per pair (strips pipelined across the warps of a block), else one warp per pair
-            const int64_t slots = (int64_t)b->wide_blocks * (LONG_BLOCK / 32);
             // measured on 10 kb x 12 kb pairs (profiles/r02_long_ab.md): 1024 pairs -- 4 warps per pair 3571 GCUPS, 1 warp 3288; 2048 pairs -- 2 warps 3953,
             // 1 warp 3581; 4096 pairs -- 1 warp (new kernel, 16 resident warps per SM) 4249, 2 warps 4064
             const int64_t fill = (int64_t)e->sm_count * 16;                         // warps that fill the GPU in the one-warp-per-pair kernel
@@ -685,7 +684,7 @@ static void launch_revband(mpn_batch* b)
         e->launches += 2;
         return;
     }
-    // the four classes side by side on the side streams (a class's tail of half-empty SMs is filled by the next one); a batch of the
+    // the classes side by side on the side streams (a class's tail of half-empty SMs is filled by the next one); a batch of the
     // chunk pipeline stays on its own stream, the other ranges in flight fill its tails
     static const bool no_fork = getenv("MPN_RB_NOFORK") != nullptr;      // A/B switch
     static const bool pipe_fork = getenv("MPN_NO_PIPE_FORK") == nullptr;
