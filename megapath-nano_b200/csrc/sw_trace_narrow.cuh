@@ -12,6 +12,10 @@ namespace mpn {
 constexpr int NARROW_BW = 7;
 constexpr int NARROW_MAX_ROWS = 1536;       // longer reads go to the warp-parallel kernel whatever their band
 
+// bytes of one row's direction word: 4 bits per band cell, 2 bw + 1 cells -> 16 bits up to bw = 1, 32 bits up to bw = 3, else 64 bits
+// (the path walk is bound by these reads: one thread per pair, 32-byte sectors of different pairs)
+__host__ __device__ constexpr int dir_row_bytes(int bw) { return bw <= 1 ? 2 : (bw <= 3 ? 4 : 8); }
+
 // per-pair hand-over from the DP kernel to the traceback kernel
 
 struct BandRec {
@@ -36,7 +40,13 @@ sw_band_trace_kernel(const SwTask* __restrict__ order, int ntasks, const FwdResu
     FinalResult r = out[i];
     const int sub_ref = f.ref_end1 - r.ref_begin1 + 1, sub_read = f.read_end1 - r.read_begin1 + 1;
     const int bw = br.bw, width_d = 2 * bw + 1;
-    const unsigned long long* dirrow = reinterpret_cast<const unsigned long long*>(scratch.base + br.dir_off);
+    const uint8_t* const dirbase = scratch.base + br.dir_off;
+    const int rowb = dir_row_bytes(bw);
+    auto row_word = [&](int r) -> unsigned long long {
+        if (rowb == 2) return reinterpret_cast<const uint16_t*>(dirbase)[r];
+        if (rowb == 4) return reinterpret_cast<const uint32_t*>(dirbase)[r];
+        return reinterpret_cast<const unsigned long long*>(dirbase)[r];
+    };
     int l = 0;
     unsigned long long coff = 0;
     // The walk yields the CIGAR back to front and its length is only known at the end.  Pass 0 counts and keeps the first SHORT words
@@ -49,7 +59,7 @@ sw_band_trace_kernel(const SwTask* __restrict__ order, int ntasks, const FwdResu
         int ti = walk && !failed ? sub_read - 1 : 0, tj = sub_ref - 1, state = 2, run = 0, cnt = 0;
         int op = 0, prev = 0;                               // BAM codes: 0 = M, 1 = I, 2 = D
         int cur_row = ti;
-        unsigned long long cur = walk ? dirrow[ti] : 0ull, nxt = ti > 0 ? dirrow[ti - 1] : 0ull;      // row ti and, prefetched, row ti-1
+        unsigned long long cur = walk ? row_word(ti) : 0ull, nxt = ti > 0 ? row_word(ti - 1) : 0ull;      // row ti and, prefetched, row ti-1
         auto emit = [&](uint32_t word) {
             if (pass) cig[coff + (unsigned)(l - 1 - cnt)] = word;
             else if (cnt < SHORT) buf[cnt] = word;
@@ -63,7 +73,7 @@ sw_band_trace_kernel(const SwTask* __restrict__ order, int ntasks, const FwdResu
             if (cpos >= 0 && cpos < width_d) word = cur;
             else {
                 const long long lin = (long long)width_d * ti + cpos;
-                if (lin >= 0 && lin < (long long)width_d * sub_read) { word = dirrow[lin / width_d]; cc = (int)(lin % width_d); }
+                if (lin >= 0 && lin < (long long)width_d * sub_read) { word = row_word((int)(lin / width_d)); cc = (int)(lin % width_d); }
                 else { word = 0; cc = 0; }
             }
             const int cell = (int)((word >> (4 * cc)) & 15ull);
@@ -82,7 +92,7 @@ sw_band_trace_kernel(const SwTask* __restrict__ order, int ntasks, const FwdResu
                 default: failed = true; ti = 0; break;          // invalid direction: the reference returns NULL (ssw.c:657-665, 840-843)
             }
             if (failed) break;
-            if (ti != cur_row) { cur = nxt; cur_row = ti; nxt = ti > 0 ? dirrow[ti - 1] : 0ull; }
+            if (ti != cur_row) { cur = nxt; cur_row = ti; nxt = ti > 0 ? row_word(ti - 1) : 0ull; }
             if (op == prev) ++run;
             else { emit(((uint32_t)run << 4) | (uint32_t)prev); prev = op; run = 1; }
         }

@@ -159,10 +159,11 @@ __device__ __forceinline__ void band_rows_body(const unsigned long long* __restr
             i = (int)nd1.x; kcur = (int)nd1.y;
             sub_ref = (int)(nd1.z & 0xffffu); sub_read = (int)(nd1.z >> 16); score = (int)(nd1.w & 0xffffu);
         }
-        // direction words: 8 bytes per read row; one arena claim per warp
+        // direction words: 2, 4 or 8 bytes per read row (dir_row_bytes); one arena claim per warp
         unsigned long long dir_off = 0;
         {
-            const unsigned long long need = ((unsigned long long)sub_read * 8ull + 15ull) & ~15ull;
+            constexpr unsigned long long RB = (unsigned long long)dir_row_bytes(BW);       // bytes per row of direction bits
+            const unsigned long long need = ((unsigned long long)sub_read * RB + 15ull) & ~15ull;
             unsigned long long incl = need;
 #pragma unroll
             for (int off = 1; off < 32; off <<= 1) { const unsigned long long v = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += v; }
@@ -172,8 +173,13 @@ __device__ __forceinline__ void band_rows_body(const unsigned long long* __restr
             dir_off = wbase_off + incl - need;
         }
         bool run = live;
-        if (run && dir_off + (unsigned long long)sub_read * 8ull > scratch.bytes) { out[i].status = 5; run = false; }
-        unsigned long long* const dirrow = reinterpret_cast<unsigned long long*>(scratch.base + (run ? dir_off : 0ull));
+        if (run && dir_off + (unsigned long long)sub_read * (unsigned long long)dir_row_bytes(BW) > scratch.bytes) { out[i].status = 5; run = false; }
+        uint8_t* const dirbase = scratch.base + (run ? dir_off : 0ull);
+        auto store_row = [&](int r, unsigned long long word) {
+            if (dir_row_bytes(BW) == 2) reinterpret_cast<uint16_t*>(dirbase)[r] = (uint16_t)word;
+            else if (dir_row_bytes(BW) == 4) reinterpret_cast<uint32_t*>(dirbase)[r] = (uint32_t)word;
+            else reinterpret_cast<unsigned long long*>(dirbase)[r] = word;
+        };
         const int rows = run ? sub_read : 0;
         int rows_max = rows;
 #pragma unroll
@@ -237,7 +243,7 @@ __device__ __forceinline__ void band_rows_body(const unsigned long long* __restr
                 }
                 hleft = hv;
             }
-            dirrow[ii] = dirword;
+            store_row(ii, dirword);
         };
         // ---- a row past the band's head (ii > BW): the band start moves by one per row, so the previous row's cell above band cell p sits at
         //      p + 2; slot 2 BW + 2 (above the last cell: outside the previous row's band) is never written and reads 0 -- which is also what
@@ -281,7 +287,7 @@ __device__ __forceinline__ void band_rows_body(const unsigned long long* __restr
                 if (p < 8) dlo |= bits << (4 * p); else dhi |= bits << (4 * (p - 8));
                 hleft = hv;
             }
-            if (!CLIP || ii < rows) dirrow[ii] = ((unsigned long long)dhi << 32) | dlo;
+            if (!CLIP || ii < rows) store_row(ii, ((unsigned long long)dhi << 32) | dlo);
         };
 
         const int head = min(BW + 1, rows_max);

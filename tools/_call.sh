@@ -1,2 +1,2 @@
-python bench.py --steps 1 --warmup 1 --no-configs --cpu-sample 2000 > gpurun_out/r02at_plain.json 2> gpurun_out/r02at_plain.err; echo rc=$?
-ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file gpurun_out/r02at_launches.csv python bench.py --steps 1 --warmup 1 --no-configs --cpu-sample 2000 > gpurun_out/r02at_ncu1.log 2>&1; echo rc=$?
+timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+python bench.py --steps 5 --warmup 3 --no-configs > gpurun_out/r02au_bench.json 2> gpurun_out/r02au_bench.err; echo rc=$?
