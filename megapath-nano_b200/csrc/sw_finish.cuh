@@ -21,6 +21,10 @@
 #include "sw_common.cuh"
 #include <climits>
 
+#ifndef MPN_FINISH_LOADS
+#define MPN_FINISH_LOADS 8          // column records a lane loads before it uses the first (A/B: 16)
+#endif
+
 namespace mpn {
 
 struct PairArrays {               // device pointers, one entry per pair of the batch (lengths / offsets travel in the SwTask)
@@ -108,16 +112,17 @@ sw_finish_kernel(const SwTask* __restrict__ fwd_tasks, int ntasks, const SwEnds*
                     if (c3 < rf_len) offer(kR, Bj - fp.gapO - (c3 - P - 1 - j) * fp.gapE, c3);
                 }
             };
-            // 256 columns per iteration: eight coalesced loads in flight per lane before any of them is used (the walk is latency bound otherwise)
-            for (int c0 = 0; c0 < rf_len; c0 += 256) {
-                uint32_t w8[8];
+            // FIN_Q x 32 columns per iteration: that many coalesced loads in flight per lane before any of them is used (the walk is latency bound otherwise)
+            constexpr int FIN_Q = MPN_FINISH_LOADS;
+            for (int c0 = 0; c0 < rf_len; c0 += 32 * FIN_Q) {
+                uint32_t w8[FIN_Q];
 #pragma unroll
-                for (int q = 0; q < 8; ++q) { const int j = c0 + 32 * q + lane; w8[q] = j < rf_len ? rec[j] : 0u; }
+                for (int q = 0; q < FIN_Q; ++q) { const int j = c0 + 32 * q + lane; w8[q] = j < rf_len ? rec[j] : 0u; }
 #pragma unroll
-                for (int q = 0; q < 8; ++q) { const int j = c0 + 32 * q + lane; if (j < rf_len) column(j, w8[q]); }
+                for (int q = 0; q < FIN_Q; ++q) { const int j = c0 + 32 * q + lane; if (j < rf_len) column(j, w8[q]); }
                 // share the keys across the warp (the result is their maximum anyway): from the second block on, the test that skips the pad
                 // candidates is then nearly warp-uniform and whole warps jump over that code
-                if (c0 + 256 < rf_len) {
+                if (c0 + 32 * FIN_Q < rf_len) {
 #pragma unroll
                     for (int off = 16; off >= 1; off >>= 1) {
                         kL = max(kL, __shfl_xor_sync(0xffffffffu, kL, off));
